@@ -1,0 +1,111 @@
+"""CPU: pin the oracle against the committed golden vectors and independent routes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import render as R
+from oracle import unet as U
+from oracle.gen_golden import RENDER_CASES, render_case_inputs, unet_case_inputs
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def test_stft_restatement_matches_torch_stft_f64():
+    rng = np.random.default_rng(0)
+    y = (rng.standard_normal(16000) * 0.1).astype(np.float32)
+    D = R.stft_librosa(y)
+    assert D.shape == (512, 32) and D.dtype == np.complex64
+    ref = torch.stft(torch.from_numpy(y).double(), 1023, 512,
+                     window=torch.hann_window(1023, periodic=True, dtype=torch.float64),
+                     center=True, pad_mode="reflect", return_complex=True).numpy()
+    assert np.abs(D - ref).max() / np.abs(ref).max() < 1e-6
+    assert np.abs(R.hann_periodic() - torch.hann_window(1023, periodic=True, dtype=torch.float64).numpy()).max() < 1e-15
+
+
+def test_fftconvolve_same_is_centred_crop_of_exact_convolution():
+    rng = np.random.default_rng(1)
+    mono = np.round(3000 * rng.standard_normal(16000)).astype(np.int16)
+    for L in (1, 2, 7, 4000, 7999, 16001, 20000, 32000, 48000):
+        h = (rng.standard_normal(L) * 0.05).astype(np.float32)
+        got = R.fftconvolve(mono, h, mode="same")
+        full = np.convolve(mono.astype(np.float64), h.astype(np.float64))
+        c = (L - 1) // 2
+        want = full[c:c + 16000]
+        assert got.shape == (16000,) and got.dtype == (np.float64 if L > 1 else np.float32)   # L == 1: scipy short-cuts to in1 * in2
+        assert np.abs(got - want).max() < 2e-2, L      # complex64 RIR spectrum noise
+
+
+def test_int16_wrap_semantics():
+    rir = np.zeros((1, 2), np.float32)
+    rir[0] = [2.0, -2.0]
+    mono = np.array([20000, -20000, 16384, 100], np.int16)
+    out = R.convolve_quantise(mono, rir)
+    np.testing.assert_array_equal(out[0] * 32768, [-25536, 25536, -32768, 200])
+    np.testing.assert_array_equal(out[1] * 32768, [25536, -25536, -32768, -200])
+
+
+@pytest.mark.parametrize("case", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])
+def test_render_golden(case, golden_dir):
+    name, K, lens, seed = case
+    g = np.load(os.path.join(golden_dir, f"render_{name}.npz"))
+    monos, rirs, _, _ = render_case_inputs(K, lens, seed)
+    sim = R.render_sim(list(monos), rirs)
+    np.testing.assert_array_equal(sim["mixed_bin_audio_mag"], g["sim_mixed_mag_f16"])
+    assert sim["mixed_bin_audio_mag"].dtype == np.float16 and sim["mixed_bin_audio_mag"].shape == (512, 32, 2)
+    np.testing.assert_array_equal(np.round(sim["_source_waves"] * 32768).astype(np.int16), g["source_waves_i16"])
+    ds = R.render_dataset(list(monos), rirs, target_class=3)
+    np.testing.assert_array_equal(ds[0], g["ds_mixed_logmag_f32"])
+    np.testing.assert_array_equal(ds[1][0], g["ds_gt_bin_mag_f32"])
+    assert ds[0].dtype == np.float32 and ds[2][0].shape == (512, 32, 1) and ds[3].dtype == np.int64
+    # independent route: exact f64 direct convolution, rounded, differs by at most a few 1-LSB flips
+    k0 = int(g["direct_conv_src"][0])
+    direct = np.round(g["direct_conv_src_ear0_f64"]).astype(np.int64).astype(np.int16)
+    flips = np.count_nonzero(direct != g["source_waves_i16"][k0, 0])
+    assert flips <= 40, flips
+    assert np.abs(direct.astype(np.int32) - g["source_waves_i16"][k0, 0].astype(np.int32)).max() <= 1 or flips == 0
+
+
+def test_gt_mono_is_rms_normalised():
+    mono = R.synth_monos(1, 1, seed=4)[0, 0]
+    mag = R.mono_gt_mag(mono, 1.2)
+    assert abs(np.sqrt(np.mean(mag.astype(np.float64) ** 2)) - 1.2) < 1e-4
+    assert np.all(R.mono_gt_mag(np.zeros(16000, np.int16), 1.2) == 0)
+
+
+@pytest.mark.parametrize("bin2mono", [False, True])
+def test_unet_restatement_matches_reference_golden(bin2mono, golden_dir):
+    g = np.load(os.path.join(golden_dir, "unet_bin2mono.npz" if bin2mono else "unet_binsep.npz"))
+    enc_sd, dec_sd = U.init_state(bin2mono, seed=3 + int(bin2mono))
+    cs = np.array([float(sum(v.double().sum() for v in enc_sd.values())),
+                   float(sum(v.double().sum() for v in dec_sd.values()))])
+    np.testing.assert_allclose(cs, g["weight_checksum"], rtol=1e-9)
+    obs, tc = unet_case_inputs(3, seed=5)
+    for mode in ("eval", "train"):
+        with torch.no_grad():
+            if bin2mono:
+                b, s = U.encoder_forward(enc_sd, torch.from_numpy(g["in_masks"]), None, True, obs, mode == "train")
+            else:
+                b, s = U.encoder_forward(enc_sd, obs, tc, False, None, mode == "train")
+            mask = U.decoder_forward(dec_sd, b, s, mode == "train")
+        assert tuple(mask.shape) == g[f"{mode}_mask"].shape
+        assert list(mask.stride()) == list(g[f"{mode}_mask_strides"])
+        assert rel_l2(b.numpy(), g[f"{mode}_bottleneck"]) < 1e-5
+        assert rel_l2(mask.numpy(), g[f"{mode}_mask"]) < 1e-5
+    # F1: no sigmoid - masks are unbounded
+    assert g["eval_mask"].min() < 0
+
+
+def test_supervised_loss_restatement():
+    g = torch.Generator().manual_seed(0)
+    mix = torch.rand(2, 512, 32, 2, generator=g)
+    mask = torch.randn(2, 512, 32, 2, generator=g)
+    gt = torch.rand(2, 512, 32, 2, generator=g)
+    bl, ml = U.supervised_losses(mix, mask, gt)
+    want = (mask * (torch.exp(mix) - 1) - gt).abs().mean()
+    assert ml is None and abs(float(bl) - float(want)) < 1e-7
