@@ -1,0 +1,104 @@
+/*
+ * m2h.h - C ABI of the B200-native Move2Hear audio hot path (libm2h_b200.so).
+ *
+ * The reference (SAGNIKMJR/move2hear-active-AV-separation) is pure Python and has no FFI for this
+ * path; the entry points below are what a ctypes binding placed at the reference's own call sites
+ * binds (INTEGRATION.md shows the stubs).  Every function takes raw DEVICE pointers, sizes and a
+ * CUDA stream (cudaStream_t passed as void*; NULL = legacy default stream), launches asynchronously
+ * on that stream, allocates nothing, and returns 0 on success or a negative m2h_status code
+ * (message via m2h_last_error()).  There is no CPU fallback: without a CUDA device every compute
+ * call fails with M2H_ERR_CUDA.
+ *
+ * Array layouts use the reference's own axis orders (C-contiguous).
+ */
+#ifndef M2H_H_
+#define M2H_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M2H_ABI_VERSION 1
+
+enum m2h_status {
+  M2H_OK = 0,
+  M2H_ERR_ARG = -1,        /* bad size / null pointer / unsupported shape */
+  M2H_ERR_CUDA = -2,       /* CUDA runtime error (no device, launch failure, ...) */
+  M2H_ERR_WORKSPACE = -3   /* caller-supplied workspace too small */
+};
+
+/* flags for m2h_render_mixture / m2h_stft_waves */
+enum m2h_render_flags {
+  M2H_RENDER_F16_OBS = 1,      /* simulator dtypes: magnitude -> fp16 -> log1p -> fp16, phases / GT in fp16
+                                  (habitat_audio/simulator_train.py:437-441, 483-486).  Otherwise the dataset's
+                                  fp32 outputs (audio_separation/pretrain/datasets/dataset.py:198, 226-228). */
+  M2H_RENDER_RAW_MAG = 2       /* write |STFT| of the mixture instead of log1p(|STFT|) */
+};
+
+int m2h_abi_version(void);
+const char* m2h_last_error(void);
+
+/* Upload the twiddle / chirp tables to `device` (idempotent; called lazily by every entry point). */
+int m2h_init(int device);
+
+/* Bytes of device workspace m2h_render_mixture / m2h_rir_convolve need (spectrum scratch, one slot per
+ * resident CTA; independent of B). */
+size_t m2h_render_workspace_bytes(int device);
+
+/*
+ * RIR convolution + quantisation for B*K (mixture, source) pairs.
+ * Replaces: scipy.signal.fftconvolve(mono, rir[:, ch], mode="same") -> np.round -> astype(int16)
+ *   habitat_audio/simulator_train.py:417-421, habitat_audio/simulator_eval.py:429-433,
+ *   audio_separation/pretrain/datasets/dataset.py:178-183.
+ *   mono     int16  [B, K, N]          source clips (N <= 16384; the reference uses N = 16000)
+ *   rir      float  [B, K, 2, Lmax]    binaural RIRs, ear-planar (transpose of the wav's [L, 2])
+ *   rir_len  int32  [B, K]             taps per RIR (<= Lmax); 0 = unreadable/empty file -> zeros
+ *                                      (simulator_train.py:407-415)
+ *   waves    int16  [B, K, 2, N]       OUT: rounded binaural waveform of each source, int16 full-scale units
+ *                                      (the reference's float value is waves * 2^-15)
+ */
+int m2h_rir_convolve(const int16_t* mono, const float* rir, const int32_t* rir_len,
+                     int B, int K, int N, int Lmax, int16_t* waves,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * STFT (n_fft 1023, hop 512, periodic Hann, centre/reflect) of the mixture of K quantised sources and,
+ * optionally, of the first n_gt sources alone.
+ * Replaces: librosa.stft / librosa.magphase / np.angle / np.log1p at
+ *   habitat_audio/simulator_train.py:425-441, 469-486, habitat_audio/simulator_eval.py:437-500,
+ *   audio_separation/pretrain/datasets/dataset.py:190-198, 216-228.
+ *   waves      int16 [B, K, 2, N]
+ *   mix_mag    OUT [B, 512, T, 2]  log1p(|STFT(mix)|)  (fp32, or fp16 with M2H_RENDER_F16_OBS), T = 1 + N/512
+ *   mix_phase  OUT [B, 512, T, 2]  angle(STFT(mix)) or NULL
+ *   gt         OUT or NULL.  gt_with_phase = 0: [B, n_gt, 512, T, 2] magnitudes (dataset.py:198);
+ *              gt_with_phase = 1: [B, n_gt, 512, T, 4] = (mag_l, phase_l, mag_r, phase_r)
+ *              (simulator_train.py:437-441).  dtype follows M2H_RENDER_F16_OBS.
+ */
+int m2h_stft_waves(const int16_t* waves, int B, int K, int N, int n_gt, int gt_with_phase, int flags,
+                   void* mix_mag, void* mix_phase, void* gt, void* stream);
+
+/*
+ * The whole per-step render: m2h_rir_convolve followed by m2h_stft_waves on the same stream.
+ * Replaces HabitatSimAudioEnabledTrain.get_current_mixed_bin_audio_mag_spec
+ * (habitat_audio/simulator_train.py:386-486; eval twin simulator_eval.py:396-500) and
+ * PassiveDataset.compute_audiospects (audio_separation/pretrain/datasets/dataset.py:162-228)
+ * minus the file reads and the cached monaural GT (see m2h_stft_f32).
+ */
+int m2h_render_mixture(const int16_t* mono, const float* rir, const int32_t* rir_len,
+                       int B, int K, int N, int Lmax, int n_gt, int gt_with_phase, int flags,
+                       int16_t* waves, void* mix_mag, void* mix_phase, void* gt,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * STFT magnitude (and optional phase) of arbitrary fp32 waveforms [B, C, N], C in {1, 2} -> [B, 512, T, C] fp32.
+ * Used for the per-sound cached monaural GT spectrograms (simulator_train.py:443-449, dataset.py:201-207).
+ */
+int m2h_stft_f32(const float* wave, int B, int C, int N, float* mag, float* phase, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* M2H_H_ */

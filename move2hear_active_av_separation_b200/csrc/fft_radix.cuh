@@ -1,0 +1,63 @@
+// In-register radix-R DFTs (R = 8, 16, 32) used by the shared-memory FFT passes.
+//
+// fft_reg<R, INV>(v): v[j], j < R natural order in; on return v[bitrev(k)] holds
+//     sum_j v[j] * exp(-/+ 2 pi i j k / R)      (- forward, + for INV).
+// All twiddles are compile-time constants once the loops are unrolled.
+#pragma once
+#include "m2h_common.cuh"
+
+M2H_HD constexpr float tw32_cos(int k) {   // cos(2 pi k / 32), 0 <= k < 16
+  return k == 0 ? 1.0f : k == 1 ? 0.9807852804032304f : k == 2 ? 0.9238795325112867f : k == 3 ? 0.8314696123025452f :
+         k == 4 ? 0.7071067811865476f : k == 5 ? 0.5555702330196023f : k == 6 ? 0.38268343236508984f :
+         k == 7 ? 0.19509032201612833f : k == 8 ? 0.0f : k == 9 ? -0.19509032201612833f : k == 10 ? -0.38268343236508984f :
+         k == 11 ? -0.5555702330196023f : k == 12 ? -0.7071067811865476f : k == 13 ? -0.8314696123025452f :
+         k == 14 ? -0.9238795325112867f : -0.9807852804032304f;
+}
+M2H_HD constexpr float tw32_sin(int k) {   // sin(2 pi k / 32), 0 <= k < 16
+  return k == 0 ? 0.0f : k == 1 ? 0.19509032201612825f : k == 2 ? 0.3826834323650898f : k == 3 ? 0.5555702330196022f :
+         k == 4 ? 0.7071067811865475f : k == 5 ? 0.8314696123025452f : k == 6 ? 0.9238795325112867f :
+         k == 7 ? 0.9807852804032304f : k == 8 ? 1.0f : k == 9 ? 0.9807852804032304f : k == 10 ? 0.9238795325112867f :
+         k == 11 ? 0.8314696123025452f : k == 12 ? 0.7071067811865475f : k == 13 ? 0.5555702330196022f :
+         k == 14 ? 0.3826834323650898f : 0.19509032201612825f;
+}
+
+// d * exp(-/+ 2 pi i k / 32) for a compile-time k in [0, 16)
+template <bool INV>
+M2H_DEV float2 mul_tw32(float2 d, int k) {
+  if (k == 0) return d;
+  if (k == 8) return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+  if (k == 4) {
+    const float s = 0.7071067811865476f;
+    return INV ? make_float2((d.x - d.y) * s, (d.x + d.y) * s) : make_float2((d.x + d.y) * s, (d.y - d.x) * s);
+  }
+  if (k == 12) {
+    const float s = 0.7071067811865476f;
+    return INV ? make_float2(-(d.x + d.y) * s, (d.x - d.y) * s) : make_float2((d.y - d.x) * s, -(d.x + d.y) * s);
+  }
+  const float c = tw32_cos(k), s = tw32_sin(k);
+  return INV ? make_float2(d.x * c - d.y * s, d.y * c + d.x * s)
+             : make_float2(d.x * c + d.y * s, d.y * c - d.x * s);
+}
+
+template <int R, bool INV>
+M2H_DEV void fft_reg(float2 (&v)[R]) {
+  M2H_UNROLL
+  for (int half = R / 2; half >= 1; half >>= 1) {
+    M2H_UNROLL
+    for (int blk = 0; blk < R; blk += 2 * half) {
+      M2H_UNROLL
+      for (int j = 0; j < half; ++j) {
+        const float2 a = v[blk + j], b = v[blk + j + half];
+        v[blk + j] = c_add(a, b);
+        v[blk + j + half] = mul_tw32<INV>(c_sub(a, b), j * (16 / half));
+      }
+    }
+  }
+}
+
+template <int BITS>
+M2H_HD constexpr int bitrev(int k) {
+  int r = 0;
+  for (int i = 0; i < BITS; ++i) r |= ((k >> i) & 1) << (BITS - 1 - i);
+  return r;
+}

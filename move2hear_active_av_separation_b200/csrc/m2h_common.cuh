@@ -1,0 +1,73 @@
+// Shared helpers for the render kernels.
+//
+// The kernel bodies in render_conv.cuh / render_stft.cuh are written as a sequence of
+// barrier-separated phases.  Under nvcc each phase runs once per thread (tid = threadIdx.x)
+// with __syncthreads() between phases.  Under -DM2H_HOST_EMU (plain g++, tests only) the same
+// source runs each phase as a loop over all thread ids, which lets the CPU test-suite check
+// every index computation of the kernels against the oracle without a GPU.  The emulation is
+// never part of the product library.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef M2H_HOST_EMU
+  #include <cmath>
+  #include <cstring>
+  struct float2 { float x, y; };
+  struct float4 { float x, y, z, w; };
+  static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+  static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+  #define M2H_DEV static inline
+  #define M2H_HD static inline
+  #define M2H_FOR_THREADS(tid, nthreads) for (int tid = 0; tid < (nthreads); ++tid)
+  #define M2H_SYNC() do {} while (0)
+  #define M2H_UNROLL
+  #define M2H_RESTRICT
+  M2H_DEV float m2h_rintf(float v) { return nearbyintf(v); }
+  M2H_DEV float m2h_ldg(const float* p) { return *p; }
+#else
+  #include <cuda_runtime.h>
+  #include <cuda_fp16.h>
+  #define M2H_DEV __device__ __forceinline__
+  #define M2H_HD __host__ __device__ __forceinline__
+  #define M2H_FOR_THREADS(tid, nthreads) for (int tid = threadIdx.x, m2h_once_ = 1; m2h_once_; m2h_once_ = 0)
+  #define M2H_SYNC() __syncthreads()
+  #define M2H_UNROLL _Pragma("unroll")
+  #define M2H_RESTRICT __restrict__
+  M2H_DEV float m2h_rintf(float v) { return rintf(v); }
+  M2H_DEV float m2h_ldg(const float* p) { return __ldg(p); }
+#endif
+
+// ---- complex arithmetic on float2 ---------------------------------------------------------
+M2H_DEV float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+M2H_DEV float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+M2H_DEV float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+M2H_DEV float2 c_mulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+M2H_DEV float2 c_conj(float2 a) { return make_float2(a.x, -a.y); }
+template <bool CONJ> M2H_DEV float2 c_mul_sel(float2 a, float2 w) { return CONJ ? c_mulc(a, w) : c_mul(a, w); }
+
+// ---- problem constants ----------------------------------------------------------------------
+// Reference STFT: n_fft = 1023, hop = 512 (simulator_train.py:426, dataset.py:20-21).
+#define M2H_NFFT 1023
+#define M2H_HOP 512
+#define M2H_NBINS 512
+// Linear-convolution FFT length.  For N <= 16384 samples only RIR taps inside
+// [c-N+1, c+N-1] (c = (L-1)/2) can reach the "same"-mode output window, i.e. at most 2N-1 taps,
+// and a circular length F >= 2N-1 keeps that window alias-free for every L.
+#define M2H_CONV_F 32768
+#define M2H_CONV_M 16384              // complex length of the packed real FFT
+#define M2H_MAX_SAMPLES 16384
+
+// twiddle tables living in device global memory (copied to shared memory by each CTA)
+struct M2hConvTables {
+  float2 tA[256];     // W_256^x     = exp(-2 pi i x / 256)       (= W_32768^(128 x))
+  float2 tB[128];     // W_32768^y
+  float2 t512[512];   // W_512^e
+};
+struct M2hStftTables {
+  float2 t2048[2048];   // W_2048^e
+  float2 bf[2048];      // FFT_2048 of the Bluestein chirp, stored in (k1,k2,k3) order: index (k1*16+k2)*8+k3 <-> f = k1+16*k2+256*k3
+  float2 wc[1024];      // hann[n] * conj(chirp[n]), n < 1023 (entry 1023 = 0)
+  float2 cc[1024];      // conj(chirp[m]) / 4096   (1/2048 inverse-FFT scale, 1/2 ear-untangle scale)
+};

@@ -1,0 +1,57 @@
+// Host-side construction of the twiddle / chirp tables (double precision, rounded once to fp32).
+// Shared by the CUDA library (m2h_render.cu) and by the CPU emulation harness used in the tests.
+#pragma once
+#include <math.h>
+#include <vector>
+#include "m2h_common.cuh"
+
+static float2 cis(double turns_neg) {     // exp(-2 pi i * turns)
+  const double a = -2.0 * M_PI * turns_neg;
+  return make_float2((float)cos(a), (float)sin(a));
+}
+
+static void build_conv_tables(M2hConvTables& t) {
+  for (int i = 0; i < 256; ++i) t.tA[i] = cis((double)i / 256.0);
+  for (int i = 0; i < 128; ++i) t.tB[i] = cis((double)i / 32768.0);
+  for (int i = 0; i < 512; ++i) t.t512[i] = cis((double)i / 512.0);
+}
+
+static void build_stft_tables(M2hStftTables& t) {
+  const int N = M2H_NFFT, F = 2048;
+  for (int i = 0; i < F; ++i) t.t2048[i] = cis((double)i / F);
+  std::vector<double> cr(N), ci(N);
+  for (int n = 0; n < N; ++n) {          // chirp c[n] = exp(+i pi n^2 / N), phase reduced exactly in integers
+    const long long m = ((long long)n * n) % (2 * N);
+    cr[n] = cos(M_PI * (double)m / N);
+    ci[n] = sin(M_PI * (double)m / N);
+  }
+  for (int n = 0; n < 1024; ++n) {
+    if (n < N) {
+      const double w = 0.5 - 0.5 * cos(2.0 * M_PI * n / N);       // periodic Hann (fftbins=True)
+      t.wc[n] = make_float2((float)(w * cr[n]), (float)(-w * ci[n]));
+      t.cc[n] = make_float2((float)(cr[n] / 4096.0), (float)(-ci[n] / 4096.0));
+    } else {
+      t.wc[n] = make_float2(0.f, 0.f);
+      t.cc[n] = make_float2(0.f, 0.f);
+    }
+  }
+  // b[j] = c[|j|] on the circle of 2048, Bf = DFT_2048(b) in double
+  std::vector<double> br(F, 0.0), bi(F, 0.0);
+  for (int j = 0; j < N; ++j) {
+    br[j] = cr[j]; bi[j] = ci[j];
+    if (j > 0) { br[F - j] = cr[j]; bi[F - j] = ci[j]; }
+  }
+  std::vector<double> wr(F), wi(F);
+  for (int i = 0; i < F; ++i) { wr[i] = cos(-2.0 * M_PI * i / F); wi[i] = sin(-2.0 * M_PI * i / F); }
+  for (int f = 0; f < F; ++f) {
+    double sr = 0.0, si = 0.0;
+    for (int j = 0; j < F; ++j) {
+      const int e = (int)(((long long)f * j) & (F - 1));
+      sr += br[j] * wr[e] - bi[j] * wi[e];
+      si += br[j] * wi[e] + bi[j] * wr[e];
+    }
+    const int k1 = f & 15, k2 = (f >> 4) & 15, k3 = f >> 8;
+    t.bf[(k1 * 16 + k2) * 8 + k3] = make_float2((float)sr, (float)si);
+  }
+}
+

@@ -1,0 +1,250 @@
+// Framed STFT (n_fft = 1023, hop = 512, periodic Hann, centre/reflect) -> magnitude / phase.
+//
+// Replaces librosa.stft + librosa.magphase (+ np.angle, np.log1p, fp16 casts) at
+// habitat_audio/simulator_train.py:425-441, 473-486, habitat_audio/simulator_eval.py:437-500 and
+// audio_separation/pretrain/datasets/dataset.py:190-228.
+//
+// 1023 = 3*11*31 has no radix-2 factor: each frame's 1023-point DFT is evaluated with Bluestein's chirp-z
+// identity as a 2048-point circular convolution.  The two ears of a frame ride together as one complex signal
+// (left + i*right) and are separated by conjugate symmetry afterwards, so one frame pair costs two complex
+// FFT-2048s.  A CTA of 512 threads = 4 groups of 128 threads; each group transforms one frame pair at a time in
+// a padded [16][16][8] shared buffer (position(i1,i2,i3) = i1*152 + i2*9 + i3, conflict-free for all passes).
+//
+// Signals: s = 0 is the mixture ((sum_k wave_k) * 2^-15 / K, exactly the fp32 arithmetic of
+// simulator_train.py:469-471), s >= 1 is source s-1 alone (wave * 2^-15).  A generic fp32 input mode serves the
+// cached monaural GT spectrograms (simulator_train.py:443-449, dataset.py:201-207).
+#pragma once
+#include "fft_radix.cuh"
+
+#define M2H_STFT_THREADS 512
+#define M2H_STFT_GROUPS 4
+#define M2H_STFT_S1 152
+#define M2H_STFT_S2 9
+#define M2H_STFT_BUF (16 * M2H_STFT_S1)
+
+enum {
+  M2H_OUT_MIX_LOG1P = 1,   // mixture magnitude is written as log1p(mag)
+  M2H_OUT_F16 = 2,         // simulator dtype: magnitude cast to fp16 BEFORE log1p, everything stored as fp16
+};
+
+struct StftParams {
+  // input A: quantised per-source waves
+  const int16_t* waves;    // [B, K, 2, N] or null
+  // input B: generic fp32 waveforms [B, C, N] (C = 1 or 2), used when waves == null
+  const float* fwave;
+  int fwave_channels;
+  int B, K, N, T;          // T = 1 + N / 512 frames
+  int n_signals;           // waves mode: 1 (mixture only) .. 1 + n_gt ; fwave mode: 1
+  int n_gt;                // number of leading sources that get their own GT spectrogram (0, 1 or K)
+  int flags;
+  // outputs (null = not wanted).  All [.., 512, T, C] with C innermost like the reference's np.stack(axis=-1).
+  void* mix_mag;           // [B, 512, T, 2]   fp32 or fp16
+  void* mix_phase;         // [B, 512, T, 2]
+  void* gt_mag;            // dataset layout: [B, n_gt, 512, T, 2] fp32 ; simulator layout: [B, n_gt, 512, T, 4] fp16
+  int gt_interleaved_phase;// 1: simulator layout (mag_l, phase_l, mag_r, phase_r)
+  void* f_mag;             // fwave mode: [B, 512, T, C] fp32
+  void* f_phase;           // fwave mode: [B, 512, T, C] fp32 or null
+};
+
+struct StftSmem {
+  float2 buf[M2H_STFT_GROUPS][M2H_STFT_BUF];
+  float2 t2048[2048];
+  float2 bf[2048];
+};
+
+M2H_DEV int stft_reflect(int i, int N) { return i < 0 ? -i : (i >= N ? 2 * (N - 1) - i : i); }
+
+// one sample of signal `sig` for item b, both ears
+M2H_DEV float2 stft_sample(const StftParams& P, int b, int sig, int i) {
+  if (P.waves) {
+    const int16_t* w = P.waves + (size_t)b * P.K * 2 * P.N;
+    if (sig == 0) {
+      int sl = 0, sr = 0;
+      for (int k = 0; k < P.K; ++k) {
+        sl += w[(size_t)(2 * k) * P.N + i];
+        sr += w[(size_t)(2 * k + 1) * P.N + i];
+      }
+      // fp32 sum of x*2^-15 terms is exact for K <= 256; the divide is the reference's float32 divide by K
+      const float kf = (float)P.K;
+      return make_float2(((float)sl * (1.0f / 32768.0f)) / kf, ((float)sr * (1.0f / 32768.0f)) / kf);
+    }
+    const int k = sig - 1;
+    return make_float2((float)w[(size_t)(2 * k) * P.N + i] * (1.0f / 32768.0f),
+                       (float)w[(size_t)(2 * k + 1) * P.N + i] * (1.0f / 32768.0f));
+  }
+  const float* f = P.fwave + (size_t)b * P.fwave_channels * P.N;
+  return make_float2(f[i], P.fwave_channels > 1 ? f[P.N + i] : 0.f);
+}
+
+#ifndef M2H_HOST_EMU
+M2H_DEV float stft_log1p_f16(float mag) {    // np.log1p on a float16 array: computed in fp32, rounded to fp16
+  return __half2float(__float2half_rn(log1pf(__half2float(__float2half_rn(mag)))));
+}
+M2H_DEV void stft_store(void* base, size_t idx, float v, bool f16) {
+  if (f16) ((__half*)base)[idx] = __float2half_rn(v); else ((float*)base)[idx] = v;
+}
+#else
+float m2h_emu_round_f16(float v);            // provided by the emulation harness (numpy-free fp16 rounding)
+M2H_DEV float stft_log1p_f16(float mag) { return m2h_emu_round_f16(log1pf(m2h_emu_round_f16(mag))); }
+void m2h_emu_store(void* base, size_t idx, float v, bool f16);
+M2H_DEV void stft_store(void* base, size_t idx, float v, bool f16) { m2h_emu_store(base, idx, v, f16); }
+#endif
+
+M2H_DEV void stft_emit(const StftParams& P, int b, int sig, int k, int t, float2 xl, float2 xr) {
+  const bool f16 = (P.flags & M2H_OUT_F16) != 0;
+  const float ml = sqrtf(xl.x * xl.x + xl.y * xl.y), mr = sqrtf(xr.x * xr.x + xr.y * xr.y);
+  const size_t bin = (size_t)k * P.T + t;
+  if (!P.waves) {
+    const int C = P.fwave_channels;
+    const size_t o = ((size_t)b * M2H_NBINS * P.T + bin) * C;
+    ((float*)P.f_mag)[o] = ml;
+    if (C > 1) ((float*)P.f_mag)[o + 1] = mr;
+    if (P.f_phase) {
+      ((float*)P.f_phase)[o] = atan2f(xl.y, xl.x);
+      if (C > 1) ((float*)P.f_phase)[o + 1] = atan2f(xr.y, xr.x);
+    }
+    return;
+  }
+  if (sig == 0) {
+    const size_t o = ((size_t)b * M2H_NBINS * P.T + bin) * 2;
+    if (P.mix_mag) {
+      float vl = ml, vr = mr;
+      if (P.flags & M2H_OUT_MIX_LOG1P) {
+        vl = f16 ? stft_log1p_f16(ml) : log1pf(ml);
+        vr = f16 ? stft_log1p_f16(mr) : log1pf(mr);
+      }
+      stft_store(P.mix_mag, o, vl, f16);
+      stft_store(P.mix_mag, o + 1, vr, f16);
+    }
+    if (P.mix_phase) {
+      stft_store(P.mix_phase, o, atan2f(xl.y, xl.x), f16);
+      stft_store(P.mix_phase, o + 1, atan2f(xr.y, xr.x), f16);
+    }
+  } else if (P.gt_mag) {
+    const int g = sig - 1;
+    if (P.gt_interleaved_phase) {
+      const size_t o = (((size_t)b * P.n_gt + g) * M2H_NBINS * P.T + bin) * 4;
+      stft_store(P.gt_mag, o, ml, f16);
+      stft_store(P.gt_mag, o + 1, atan2f(xl.y, xl.x), f16);
+      stft_store(P.gt_mag, o + 2, mr, f16);
+      stft_store(P.gt_mag, o + 3, atan2f(xr.y, xr.x), f16);
+    } else {
+      const size_t o = (((size_t)b * P.n_gt + g) * M2H_NBINS * P.T + bin) * 2;
+      stft_store(P.gt_mag, o, ml, f16);
+      stft_store(P.gt_mag, o + 1, mr, f16);
+    }
+  }
+}
+
+// ---- phases (per thread; grp = tid >> 7 owns frame t, lt = tid & 127) ------------------------------
+// P1: load 8 x 128 samples of the frame pair, window * conj(chirp), radix-16 pass along n1 (upper 8 inputs are the
+//     zero padding of the 2048-point transform), twiddle W_2048^(r*k1).
+M2H_DEV void stft_p1(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int b, int sig, int t0) {
+  const int grp = tid >> 7, r = tid & 127, t = t0 + grp;
+  if (t >= P.T) return;
+  float2 v[16];
+  M2H_UNROLL for (int n1 = 0; n1 < 8; ++n1) {
+    const int n = n1 * 128 + r;
+    float2 a = make_float2(0.f, 0.f);
+    if (n < M2H_NFFT) {
+      const float2 x = stft_sample(P, b, sig, stft_reflect(M2H_HOP * t - (M2H_NFFT / 2) + n, P.N));
+      a = c_mul(x, gt->wc[n]);
+    }
+    v[n1] = a;
+  }
+  M2H_UNROLL for (int n1 = 8; n1 < 16; ++n1) v[n1] = make_float2(0.f, 0.f);
+  fft_reg<16, false>(v);
+  float2* p = s.buf[grp] + (r >> 3) * M2H_STFT_S2 + (r & 7);
+  M2H_UNROLL for (int k1 = 0; k1 < 16; ++k1)
+    p[k1 * M2H_STFT_S1] = k1 == 0 ? v[0] : c_mul(v[bitrev<4>(k1)], s.t2048[r * k1]);
+}
+// P2: radix-16 pass along n2, twiddle W_128^(n3*k2) = W_2048^(16*n3*k2)
+M2H_DEV void stft_p2(const StftParams& P, StftSmem& s, int tid, int t0) {
+  const int grp = tid >> 7, lt = tid & 127;
+  if (t0 + grp >= P.T) return;
+  const int k1 = lt >> 3, n3 = lt & 7;
+  float2* p = s.buf[grp] + k1 * M2H_STFT_S1 + n3;
+  float2 v[16];
+  M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[j * M2H_STFT_S2];
+  fft_reg<16, false>(v);
+  M2H_UNROLL for (int k2 = 0; k2 < 16; ++k2)
+    p[k2 * M2H_STFT_S2] = k2 == 0 ? v[0] : c_mul(v[bitrev<4>(k2)], s.t2048[16 * n3 * k2]);
+}
+// P3: radix-8 pass along n3, multiply by the chirp spectrum, inverse radix-8 pass, twiddle conj(W_128^(n3*k2))
+M2H_DEV void stft_p3(const StftParams& P, StftSmem& s, int tid, int t0) {
+  const int grp = tid >> 7, lt = tid & 127;
+  if (t0 + grp >= P.T) return;
+  M2H_UNROLL for (int h = 0; h < 2; ++h) {
+    const int q = lt + h * 128;                 // q = k1*16 + k2
+    const int k2 = q & 15;
+    float2* p = s.buf[grp] + (q >> 4) * M2H_STFT_S1 + k2 * M2H_STFT_S2;
+    float2 v[8], u[8];
+    M2H_UNROLL for (int j = 0; j < 8; ++j) v[j] = p[j];
+    fft_reg<8, false>(v);
+    M2H_UNROLL for (int k3 = 0; k3 < 8; ++k3) u[k3] = c_mul(v[bitrev<3>(k3)], s.bf[q * 8 + k3]);
+    fft_reg<8, true>(u);
+    M2H_UNROLL for (int n3 = 0; n3 < 8; ++n3)
+      p[n3] = n3 == 0 ? u[0] : c_mulc(u[bitrev<3>(n3)], s.t2048[16 * n3 * k2]);
+  }
+}
+// P4: inverse radix-16 pass along k2 -> n2, twiddle conj(W_2048^((8*n2+n3)*k1))
+M2H_DEV void stft_p4(const StftParams& P, StftSmem& s, int tid, int t0) {
+  const int grp = tid >> 7, lt = tid & 127;
+  if (t0 + grp >= P.T) return;
+  const int k1 = lt >> 3, n3 = lt & 7;
+  float2* p = s.buf[grp] + k1 * M2H_STFT_S1 + n3;
+  float2 v[16];
+  M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[j * M2H_STFT_S2];
+  fft_reg<16, true>(v);
+  M2H_UNROLL for (int n2 = 0; n2 < 16; ++n2)
+    p[n2 * M2H_STFT_S2] = c_mulc(v[bitrev<4>(n2)], s.t2048[(8 * n2 + n3) * k1]);
+}
+// P5: inverse radix-16 pass along k1 -> n1 (only m = n1*128 + r < 1023 is needed), times conj(chirp)/4096
+M2H_DEV void stft_p5(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int t0) {
+  const int grp = tid >> 7, r = tid & 127;
+  if (t0 + grp >= P.T) return;
+  float2* p = s.buf[grp] + (r >> 3) * M2H_STFT_S2 + (r & 7);
+  float2 v[16];
+  M2H_UNROLL for (int k1 = 0; k1 < 16; ++k1) v[k1] = p[k1 * M2H_STFT_S1];
+  fft_reg<16, true>(v);
+  M2H_UNROLL for (int n1 = 0; n1 < 8; ++n1)
+    p[n1 * M2H_STFT_S1] = c_mul(v[bitrev<4>(n1)], gt->cc[n1 * 128 + r]);
+}
+M2H_DEV int stft_pos(int m) { return (m >> 7) * M2H_STFT_S1 + ((m >> 3) & 15) * M2H_STFT_S2 + (m & 7); }
+// P6: separate the ears (X_l = (X[k] + conj X[N-k]) / 2, X_r = (X[k] - conj X[N-k]) / 2i; the 1/2 lives in cc) and emit
+M2H_DEV void stft_p6(const StftParams& P, StftSmem& s, int tid, int b, int sig, int t0) {
+  const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
+  if (t >= P.T) return;
+  for (int k = lt; k < M2H_NBINS; k += 128) {
+    const float2 a = s.buf[grp][stft_pos(k)];
+    const float2 c = s.buf[grp][stft_pos(k == 0 ? 0 : M2H_NFFT - k)];
+    const float2 xl = make_float2(a.x + c.x, a.y - c.y);
+    const float2 xr = make_float2(a.y + c.y, c.x - a.x);
+    stft_emit(P, b, sig, k, t, xl, xr);
+  }
+}
+
+M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int cta, int n_ctas) {
+  M2H_FOR_THREADS(tid, M2H_STFT_THREADS) {
+    for (int i = tid; i < 2048; i += M2H_STFT_THREADS) { s.t2048[i] = gt->t2048[i]; s.bf[i] = gt->bf[i]; }
+  }
+  M2H_SYNC();
+  const int n_items = P.B * P.n_signals;
+  for (int item = cta; item < n_items; item += n_ctas) {
+    const int b = item / P.n_signals, sig = item % P.n_signals;
+    for (int t0 = 0; t0 < P.T; t0 += M2H_STFT_GROUPS) {
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p1(P, s, gt, tid, b, sig, t0);
+      M2H_SYNC();
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p2(P, s, tid, t0);
+      M2H_SYNC();
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p3(P, s, tid, t0);
+      M2H_SYNC();
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p4(P, s, tid, t0);
+      M2H_SYNC();
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p5(P, s, gt, tid, t0);
+      M2H_SYNC();
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p6(P, s, tid, b, sig, t0);
+      M2H_SYNC();
+    }
+  }
+}

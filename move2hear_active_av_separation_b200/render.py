@@ -1,0 +1,243 @@
+"""Host side of the mixture render: batched device API + drop-in shims for the reference's call sites.
+
+Mirrors (same names, argument meaning, return values, side effects, error behaviour):
+
+* ``HabitatSimAudioEnabledTrain.get_current_mixed_bin_audio_mag_spec``
+  (habitat_audio/simulator_train.py:386-486; eval twin simulator_eval.py:396-500), and
+* ``PassiveDataset.compute_audiospects`` (audio_separation/pretrain/datasets/dataset.py:162-228).
+
+All arithmetic runs in ``libm2h_b200.so`` (csrc/render_conv.cuh, csrc/render_stft.cuh) through the C ABI of
+``include/m2h.h``; torch is used only for device memory and streams.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+N_FFT = 1023
+HOP_LENGTH = 512
+N_BINS = 512
+SAMPLE_RATE = 16000
+FLAG_F16_OBS = 1
+FLAG_RAW_MAG = 2
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.M2HError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.M2HError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+class AudioRenderer:
+    """Owns the per-device workspace and launches the render kernels on the current torch stream."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.M2HError("no CUDA device: the B200 render path has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.m2h_init(self.device.index), "m2h_init")
+            nbytes = self.lib.m2h_render_workspace_bytes(self.device.index)
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    # ---- device-level API -------------------------------------------------------------------
+    def rir_convolve(self, mono: torch.Tensor, rir: torch.Tensor, rir_len: torch.Tensor,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int16 ``[B,K,N]`` (*) fp32 ``[B,K,2,Lmax]`` -> rounded int16 waves ``[B,K,2,N]``."""
+        mono = _need_cuda(mono, "mono", torch.int16)
+        rir = _need_cuda(rir, "rir", torch.float32)
+        rir_len = _need_cuda(rir_len, "rir_len", torch.int32)
+        B, K, N = mono.shape
+        if rir.shape[:3] != (B, K, 2) or rir_len.shape != (B, K):
+            raise _lib.M2HError(f"shape mismatch: mono {tuple(mono.shape)} rir {tuple(rir.shape)} rir_len {tuple(rir_len.shape)}")
+        Lmax = rir.shape[3]
+        waves = out if out is not None else torch.empty((B, K, 2, N), dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.m2h_rir_convolve(mono.data_ptr(), rir.data_ptr(), rir_len.data_ptr(), B, K, N, Lmax,
+                                           waves.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(),
+                                           _stream_ptr(self.device))
+        _lib.check(rc, "m2h_rir_convolve")
+        return waves
+
+    def stft_waves(self, waves: torch.Tensor, n_gt: int = 0, sim_dtypes: bool = False, want_phase: bool = False,
+                   raw_mag: bool = False):
+        """STFT of the mixture (and of the first ``n_gt`` sources).  Returns ``(mix_mag, mix_phase|None, gt|None)``."""
+        waves = _need_cuda(waves, "waves", torch.int16)
+        B, K, _, N = waves.shape
+        T = 1 + N // HOP_LENGTH
+        dt = torch.float16 if sim_dtypes else torch.float32
+        mix = torch.empty((B, N_BINS, T, 2), dtype=dt, device=self.device)
+        phase = torch.empty((B, N_BINS, T, 2), dtype=dt, device=self.device) if want_phase else None
+        gt = None
+        if n_gt > 0:
+            gt = torch.empty((B, n_gt, N_BINS, T, 4 if want_phase else 2), dtype=dt, device=self.device)
+        flags = (FLAG_F16_OBS if sim_dtypes else 0) | (FLAG_RAW_MAG if raw_mag else 0)
+        with torch.cuda.device(self.device):
+            rc = self.lib.m2h_stft_waves(waves.data_ptr(), B, K, N, n_gt, 1 if want_phase else 0, flags,
+                                         mix.data_ptr(), phase.data_ptr() if phase is not None else None,
+                                         gt.data_ptr() if gt is not None else None, _stream_ptr(self.device))
+        _lib.check(rc, "m2h_stft_waves")
+        return mix, phase, gt
+
+    def render(self, mono, rir, rir_len, n_gt: int = 0, sim_dtypes: bool = False, want_phase: bool = False,
+               raw_mag: bool = False):
+        """conv + quantise + mix + STFT.  Returns dict(mix_mag, mix_phase, gt, waves)."""
+        waves = self.rir_convolve(mono, rir, rir_len)
+        mix, phase, gt = self.stft_waves(waves, n_gt, sim_dtypes, want_phase, raw_mag)
+        return {"mix_mag": mix, "mix_phase": phase, "gt": gt, "waves": waves}
+
+    def stft_f32(self, wave: torch.Tensor, want_phase: bool = False):
+        """fp32 ``[B,C,N]`` -> (``|STFT|`` ``[B,512,T,C]``, phase or None)."""
+        wave = _need_cuda(wave, "wave", torch.float32)
+        B, C, N = wave.shape
+        T = 1 + N // HOP_LENGTH
+        mag = torch.empty((B, N_BINS, T, C), dtype=torch.float32, device=self.device)
+        ph = torch.empty_like(mag) if want_phase else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.m2h_stft_f32(wave.data_ptr(), B, C, N, mag.data_ptr(),
+                                       ph.data_ptr() if ph is not None else None, _stream_ptr(self.device))
+        _lib.check(rc, "m2h_stft_f32")
+        return mag, ph
+
+    # ---- host-array convenience (what the shims use) -------------------------------------------------
+    def pack_sources(self, monos: Sequence[np.ndarray], rirs: Sequence[np.ndarray]):
+        """K int16 ``[N]`` clips + K wav-layout ``[L_k, 2]`` RIRs -> device tensors for a batch of one."""
+        K = len(monos)
+        N = len(monos[0])
+        Lmax = max(1, max(len(r) for r in rirs))
+        mono = np.stack([np.asarray(m, dtype=np.int16) for m in monos])[None]
+        rir = np.zeros((1, K, 2, Lmax), dtype=np.float32)
+        lens = np.zeros((1, K), dtype=np.int32)
+        for k, r in enumerate(rirs):
+            r = np.asarray(r)
+            lens[0, k] = len(r)
+            if len(r):
+                rir[0, k, :, :len(r)] = np.asarray(r, dtype=np.float32).T
+        dev = self.device
+        return (torch.from_numpy(mono).to(dev), torch.from_numpy(rir).to(dev), torch.from_numpy(lens).to(dev)), N
+
+    def mono_gt_spec(self, mono: np.ndarray, gt_mono_mag_norm: float, want_phase: bool):
+        """Cached-per-sound monaural GT spectrogram (simulator_train.py:443-459, dataset.py:201-212)."""
+        wave = torch.from_numpy(np.asarray(mono).astype("float32") / 32768).to(self.device)[None, None]
+        mag, ph = self.stft_f32(wave, want_phase)
+        mag = mag[0, :, :, 0]
+        rms = torch.sqrt(torch.mean(mag * mag))
+        if gt_mono_mag_norm != 0.0 and float(rms) != 0.0:
+            mag = mag * gt_mono_mag_norm / rms
+        mag = mag.cpu().numpy()
+        return (mag, ph[0, :, :, 0].cpu().numpy()) if want_phase else (mag, None)
+
+
+_renderers = {}
+
+
+def get_renderer(device=None) -> AudioRenderer:
+    """Process-wide renderer per device, created lazily (safe with the reference's forkserver workers)."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    key = (os.getpid(), idx)
+    if key not in _renderers:
+        _renderers[key] = AudioRenderer(torch.device("cuda", idx))
+    return _renderers[key]
+
+
+# ================================================================================================
+# Drop-in replacements for the reference's methods (bind with `Class.method = function`)
+# ================================================================================================
+
+def _read_rir(path, sampling_rate):
+    """wavfile.read with the reference's error convention (simulator_train.py:407-415, dataset.py:170-176)."""
+    from scipy.io import wavfile
+    try:
+        sr, rir = wavfile.read(path)
+        assert sr == sampling_rate, "RIR doesn't have sampling frequency of RIR_SAMPLING_RATE kHz"
+    except ValueError:
+        logging.warning("{} file is not readable".format(path))
+        rir = np.zeros((sampling_rate, 2)).astype(np.float32)
+    if len(rir) == 0:
+        logging.debug("Empty RIR file at {}".format(path))
+        rir = np.zeros((sampling_rate, 2)).astype(np.float32)
+    return rir
+
+
+def get_current_mixed_bin_audio_mag_spec(self):
+    r"""Drop-in for ``HabitatSimAudioEnabledTrain/Eval.get_current_mixed_bin_audio_mag_spec``.
+
+    Same file reads, caches (``_cached_mono_waveforms``, ``_cached_mono_specs``), side effects
+    (``_gt_bin_audio_components``, ``_gt_mono_audio_components``, ``_mixed_bin_audio_phase``) and return value
+    (``np.float16 [512, 32, 2]`` = log1p of the fp16 magnitude); the arithmetic runs on the GPU.
+    """
+    from scipy.io import wavfile
+    cfg = self.config.AUDIO
+    rend = get_renderer()
+    self._gt_bin_audio_components = []
+    self._gt_mono_audio_components = []
+    monos, rirs = [], []
+    for indx, source_position_index in enumerate(self._source_position_indices):
+        name = self._current_sound_names[indx]
+        if name not in self._cached_mono_waveforms:
+            _, wav = wavfile.read(os.path.join(cfg.MONO_DIR, name + ".wav"))
+            self._cached_mono_waveforms[name] = wav
+        monos.append(self._cached_mono_waveforms[name])
+        rir_file = os.path.join(cfg.RIR_DIR, self.current_scene_name, str(self.azimuth_angle),
+                                str(self._receiver_position_index) + "_" + str(source_position_index) + ".wav")
+        rirs.append(_read_rir(rir_file, cfg.RIR_SAMPLING_RATE))
+    return render_sim_arrays(self, monos, rirs, list(self._current_sound_names), cfg.GT_MONO_MAG_NORM, rend)
+
+
+def render_sim_arrays(self, monos, rirs, names, gt_mono_mag_norm, rend=None):
+    """Array-level body of the simulator shim (also what the tests drive): sets the side-effect fields on ``self``."""
+    rend = rend or get_renderer()
+    K = len(monos)
+    (mono_d, rir_d, len_d), _ = rend.pack_sources(monos, rirs)
+    out = rend.render(mono_d, rir_d, len_d, n_gt=K, sim_dtypes=True, want_phase=True)
+    gt = out["gt"][0].cpu().numpy()                       # [K,512,T,4] fp16
+    self._gt_bin_audio_components = [gt[k] for k in range(K)]
+    self._gt_mono_audio_components = []
+    for k, name in enumerate(names):
+        if name not in self._cached_mono_specs:
+            if gt_mono_mag_norm != 0.0:
+                assert getattr(getattr(self, "config", None), "AUDIO", None) is None or self.config.AUDIO.NORM_TYPE == "l2"
+            mag, ph = rend.mono_gt_spec(monos[k], gt_mono_mag_norm, want_phase=True)
+            self._cached_mono_specs[name] = np.stack([mag, ph], axis=-1)
+        self._gt_mono_audio_components.append(self._cached_mono_specs[name].astype(np.float16))
+    self._mixed_bin_audio_phase = out["mix_phase"][0].cpu().numpy()
+    return out["mix_mag"][0].cpu().numpy()
+
+
+def compute_audiospects(self, rirs_audio, target_class):
+    r"""Drop-in for ``PassiveDataset.compute_audiospects`` (dataset.py:162-228).
+
+    Returns ``(log1p(mixed_mag) f32 [512,32,2], [gt_bin_mag f32 [512,32,2]], [gt_mono_mag f32 [512,32,1]],
+    np.int64 [1])``; keeps ``self._gt_mono_mag_cache`` and the zero-RIR fallback.
+    """
+    monos, rirs, names = [], [], []
+    for rir_audio in rirs_audio:
+        rirs.append(_read_rir(os.path.join(self.binaural_rir_dir, rir_audio[0]), self.rir_sampling_rate))
+        monos.append(self.file2audio_dict[rir_audio[1]])
+        names.append(rir_audio[1])
+    return compute_audiospects_arrays(self, monos, rirs, names, target_class, self.audio_cfg.GT_MONO_MAG_NORM)
+
+
+def compute_audiospects_arrays(self, monos, rirs, names, target_class, gt_mono_mag_norm, rend=None):
+    rend = rend or get_renderer()
+    (mono_d, rir_d, len_d), _ = rend.pack_sources(monos, rirs)
+    out = rend.render(mono_d, rir_d, len_d, n_gt=1, sim_dtypes=False, want_phase=False)
+    gt_bin_mag = [out["gt"][0, 0].cpu().numpy()]
+    if names[0] not in self._gt_mono_mag_cache:
+        mag, _ = rend.mono_gt_spec(monos[0], gt_mono_mag_norm if gt_mono_mag_norm else 0.0, want_phase=False)
+        self._gt_mono_mag_cache[names[0]] = mag
+    gt_mono_mag = [np.expand_dims(self._gt_mono_mag_cache[names[0]], axis=2).astype("float32")]
+    return out["mix_mag"][0].cpu().numpy(), gt_bin_mag, gt_mono_mag, np.array([target_class]).astype("int64")

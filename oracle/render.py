@@ -69,6 +69,19 @@ def magphase_librosa(D: np.ndarray):
     return mag, phase
 
 
+def log1p_f16(x16: np.ndarray) -> np.ndarray:
+    """``np.log1p`` of a float16 array with the reference's pinned numpy semantics.
+
+    numpy 1.19.5 (requirements.txt) evaluates half-precision ufuncs as
+    ``float -> log1pf -> half``.  numpy >= 2 on AVX512-FP16 hosts dispatches to an
+    SVML half kernel that is a few fp16 ulp off (41 % of inputs differ in this
+    container), which would make the oracle depend on the host CPU - so the
+    float32 route is spelled out.
+    """
+    assert x16.dtype == np.float16
+    return np.log1p(x16.astype(np.float32)).astype(np.float16)
+
+
 def convolve_quantise(mono: np.ndarray, rir: np.ndarray) -> np.ndarray:
     """simulator_train.py:417-423 / dataset.py:178-185.
 
@@ -139,7 +152,7 @@ def render_sim(monos, rirs, gt_mono_mag_norm: float = 1.2):
     mixed_mag32 = np.stack(mags, axis=-1)
     mixed_mag = mixed_mag32.astype(np.float16)
     return {
-        "mixed_bin_audio_mag": np.log1p(mixed_mag),                          # float16 [512,T,2]
+        "mixed_bin_audio_mag": log1p_f16(mixed_mag),                         # float16 [512,T,2]
         "mixed_bin_audio_phase": np.stack(phases, axis=-1).astype(np.float16),
         "gt_bin_audio_components": gt_bin,
         "gt_mono_audio_components": gt_mono,
