@@ -104,10 +104,11 @@ def test_full_size_properties(rend):
         rl = [R.rir_wav_layout(rirs[b, k], int(lens[b, k])) for k in range(K)]
         ds = R.render_dataset(list(monos[b]), rl, 0)
         assert rel_l2(mix[B - 8 + b].cpu().numpy(), ds[0]) < 1e-4
-    # (3) swapping the ears of the RIR swaps the ears of the output exactly
+    # (3) swapping the ears of the RIR swaps the ears: exactly for the quantised waves (ears are convolved
+    #     independently), to fp32 rounding for the spectrogram (the ears share one complex transform)
     out2 = rend.render(mono_d[:16], rir_d[:16].flip(2), len_d[:16])
     assert torch.equal(out2["waves"], waves[:16].flip(2))
-    assert torch.equal(out2["mix_mag"], mix[:16].flip(3))
+    assert rel_l2(out2["mix_mag"].cpu().numpy(), mix[:16].flip(3).cpu().numpy()) < 1e-5
     # (4) permuting the sources leaves the mixture unchanged (integer sum before the divide)
     out3 = rend.render(mono_d[:16].flip(1), rir_d[:16].flip(1), len_d[:16].flip(1))
     assert torch.equal(out3["mix_mag"], mix[:16])
