@@ -98,6 +98,64 @@ int m2h_render_mixture(const int16_t* mono, const float* rir, const int32_t* rir
  */
 int m2h_stft_f32(const float* wave, int B, int C, int N, float* mag, float* phase, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Passive-separator U-Net, inference statistics (eval-mode BatchNorm).
+ * Replaces PassiveSepEncCNN.forward / PassiveSepDecCNN.forward
+ * (audio_separation/rl/models/separator_cnn.py:70-108, 153-170) as composed by Policy.get_binSepMasks /
+ * convert_bin2mono (audio_separation/pretrain/passive/policy.py:61-71, audio_separation/rl/ppo/policy.py:183-193).
+ * Conv / transposed-conv layers run as bf16 implicit GEMMs on tcgen05 with fp32 accumulation; BatchNorm,
+ * (Leaky)ReLU, the target-class plane, the skip concatenations and the 1x1 head are fused into them.
+ * The spectrogram must be [512, 32] (N = 16000 samples).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* fp32 DEVICE pointers to the reference module's own parameters/buffers (state_dict layouts). */
+typedef struct m2h_unet_enc_params {
+  const float* conv_w[5];    /* cnn.{i}.0.weight  [Cout, Cin, 4, 4]  (Cin = 33 for layer 0 of the binaural separator) */
+  const float* bn_w[5];      /* cnn.{i}.1.weight */
+  const float* bn_b[5];      /* cnn.{i}.1.bias */
+  const float* bn_mean[5];   /* cnn.{i}.1.running_mean */
+  const float* bn_var[5];    /* cnn.{i}.1.running_var */
+} m2h_unet_enc_params;
+
+typedef struct m2h_unet_dec_params {
+  const float* deconv_w[5];  /* cnn.{i}.0.weight  [Cin, Cout, 4, 4] (ConvTranspose2d) */
+  const float* bn_w[5];
+  const float* bn_b[5];
+  const float* bn_mean[5];
+  const float* bn_var[5];
+  const float* head_w;       /* cnn.5.0.weight [C, C, 1, 1], C = 32 (binaural) or 16 (bin2mono) */
+  const float* head_b;       /* cnn.5.0.bias   [C] */
+} m2h_unet_dec_params;
+
+size_t m2h_unet_enc_packed_bytes(int convert_bin2mono);
+size_t m2h_unet_dec_packed_bytes(int convert_bin2mono);
+/* Fold BatchNorm into per-channel scale/bias and re-lay the weights as bf16 GEMM operands into `packed`. */
+int m2h_unet_pack_encoder(const m2h_unet_enc_params* p, int convert_bin2mono, float bn_eps, void* packed, void* stream);
+int m2h_unet_pack_decoder(const m2h_unet_dec_params* p, int convert_bin2mono, float bn_eps, void* packed, void* stream);
+
+/* Activation workspace shared by one encoder/decoder pair (bf16 NHWC feature maps; the skip connections live in
+ * the second half of the decoder's concat buffers).  offsets[7] = byte offsets of
+ * {x0 [B,32,32,32], cat1 [B,16,16,128], cat2 [B,8,8,256], cat3 [B,4,4,512], cat4 [B,2,2,1024], bottleneck [B,512],
+ *  d4 [B,32,32,32]}. */
+size_t m2h_unet_workspace_bytes(int B);
+int m2h_unet_workspace_layout(int B, size_t offsets[7]);
+
+/*
+ * Encoder.  obs: fp32 [B, 512, 32, 2] log1p magnitudes (observations["mixed_bin_audio_mag"], or `mixed_audio`
+ * when convert_bin2mono).  target_class_plus1: fp32 [B] = target_class + 1 (binaural separator only).
+ * masks (+ element strides of its [B, 512, 32, 2] view): predicted ratio masks, convert_bin2mono only; the encoder
+ * input is then log1p(clamp(masks * (exp(obs) - 1), 0)) (separator_cnn.py:73-79).
+ * bottleneck_f32: optional fp32 [B, 512] copy of the bottleneck features.
+ */
+int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2mono, const float* obs,
+                             const float* target_class_plus1, const float* masks, const int64_t* mask_strides,
+                             int B, void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream);
+/* Decoder.  mask_out: fp32 [B, C, 512, 32] (C = 2 or 1) - the memory layout behind the reference's permuted
+ * [B, 512, 32, C] return value (separator_cnn.py:163-170). */
+int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2mono, int B, void* workspace,
+                             size_t workspace_bytes, float* mask_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
