@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Headline benchmark: separated mixtures / second through (RIR conv + quantise + mix + STFT + U-Net).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic mixtures: BASELINE.json configs[1]
+(B = 1024 mixtures per GPU, K = 2 sources x 1 s @ 16 kHz, 16000-tap binaural RIRs, seeded as SURVEY.md 8d) rendered
+to log1p-magnitude spectrograms, then the binaural passive-separator U-Net (random init, eval-mode BN) predicting
+the ratio masks.  Work shards by mixture across GPUs (no data-path collective, weak scaling).  Prints ONE JSON line.
+
+``--impl reference`` times the reference's own CPU arithmetic (scipy fftconvolve + librosa-faithful STFT + the
+torch-fp32 U-Net restated in oracle/) on the box's host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "separated mixtures/sec (RIR conv+STFT+U-Net)"
+UNIT = "mixtures/s"
+B_PER_GPU = 1024
+K_SRC = 2
+N_SAMPLES = 16000
+L_TAPS = 16000
+N_DISTINCT = 64               # distinct seeded mixtures, tiled to the batch (identical for every arm)
+
+# algorithmic bytes per mixture: every input read once, every output written once
+BYTES_CONV = 2 * K_SRC * N_SAMPLES + 8 * K_SRC * L_TAPS + 2 * K_SRC * 2 * N_SAMPLES        # mono + RIR in, int16 waves out
+BYTES_STFT = 2 * K_SRC * 2 * N_SAMPLES + 4 * 512 * 32 * 2                                   # int16 waves in, fp32 log-mag out
+BYTES_RENDER = 2 * K_SRC * N_SAMPLES + 8 * K_SRC * L_TAPS + 4 * 512 * 32 * 2                # 451,072 B
+FLOPS_UNET = 220.7e6                                                                         # binSep fwd, nominal 2*MACs
+
+
+def workload_config(extra=None):
+    cfg = {"workload": "configs[1] render (B=1024/GPU, K=2, N=16000, L=16000, seeds 0/1) + binSep U-Net fwd (eval BN)",
+           "batch_per_gpu": B_PER_GPU, "sources": K_SRC, "samples": N_SAMPLES, "rir_taps": L_TAPS,
+           "l2": "inputs+intermediates per step (0.9 GB) exceed the 126 MB L2; no artificial flush"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+def synth_host_inputs():
+    import numpy as np
+    from oracle import render as R
+    monos = R.synth_monos(N_DISTINCT, K_SRC, N_SAMPLES, seed=0)
+    rirs, lens = R.synth_rirs(N_DISTINCT, K_SRC, L_TAPS, seed=1)
+    tc = (np.arange(N_DISTINCT) % 11).astype(np.int64).reshape(-1, 1)
+    return monos, rirs, lens, tc
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference path (oracle) - the checker doubling as the timed "reference arm"
+# ------------------------------------------------------------------------------------------------
+def _pool_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+
+
+def _cpu_render_one(args):
+    from oracle import render as R
+    monos, rirs, lens = args
+    rl = [R.rir_wav_layout(rirs[k], int(lens[k])) for k in range(len(monos))]
+    return R.render_dataset(list(monos), rl, 0)[0]
+
+
+class CpuReference:
+    """scipy/numpy render on a process pool (one mixture per task, like the reference's env / DataLoader workers)
+    followed by the torch-fp32 U-Net on all host threads."""
+
+    def __init__(self):
+        import multiprocessing as mp
+        import torch
+        from oracle import unet as U
+        self.cores = len(os.sched_getaffinity(0))
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_pool_init)
+        torch.set_num_threads(self.cores)
+        self.enc_sd, self.dec_sd = U.init_state(False, seed=3)
+        self.U = U
+        self.pool.map(_cpu_render_one, [])          # spin the workers up
+
+    def step(self, monos, rirs, lens, tc):
+        import numpy as np
+        import torch
+        obs = self.pool.map(_cpu_render_one, [(monos[i], rirs[i], lens[i]) for i in range(len(monos))])
+        obs = torch.from_numpy(np.stack(obs))
+        with torch.no_grad():
+            mask = self.U.separator_forward(self.enc_sd, self.dec_sd, obs, torch.from_numpy(tc))
+        return mask
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_sample_size(cores):
+    """Mixtures per CPU step: a few tasks per worker, bounded so that a step stays around a second."""
+    return max(16, min(256, 4 * cores))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    monos, rirs, lens, tc = synth_host_inputs()
+    ref = CpuReference()
+    sample = cpu_sample_size(ref.cores)
+    sl = [i % N_DISTINCT for i in range(sample)]
+    for _ in range(max(args.warmup, 1)):
+        ref.step(monos[sl], rirs[sl], lens[sl], tc[sl])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.step(monos[sl], rirs[sl], lens[sl], tc[sl])
+    dt = time.perf_counter() - t0
+    ref.close()
+    value = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
+            "config": workload_config({"sample_per_step": sample}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                             "sample": f"{sample} mixtures/step of the same seeded workload, scipy.fftconvolve + restated librosa STFT on a {ref.cores}-process pool, then torch-fp32 U-Net on {ref.cores} threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    monos, rirs, lens, tc = synth_host_inputs()
+
+    # CPU baseline first (rank 0, N = 1 only), before CUDA is touched: bounded sample of the same workload
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference()
+        sample = cpu_sample_size(ref.cores)
+        sl = [i % N_DISTINCT for i in range(sample)]
+        ref.step(monos[sl], rirs[sl], lens[sl], tc[sl])
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 12.0 and reps < 50):
+            cpu_mask = ref.step(monos[sl], rirs[sl], lens[sl], tc[sl])
+            reps += 1
+        dt = time.perf_counter() - t0
+        ref.close()
+        cpu_baseline = {"value": sample * reps / dt, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                        "sample": f"{reps} x {sample} mixtures of the same seeded workload ({dt:.1f} s): scipy.fftconvolve + restated librosa STFT on a {ref.cores}-process pool, torch-fp32 U-Net on {ref.cores} threads"}
+    else:
+        cpu_mask, sample = None, 0
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from move2hear_active_av_separation_b200.render import AudioRenderer
+    from move2hear_active_av_separation_b200.separator_cnn import PassiveSepDecCNN, PassiveSepEncCNN
+    from oracle import unet as U
+
+    rend = AudioRenderer(dev)
+    enc_sd, dec_sd = U.init_state(False, seed=3)
+    enc, dec = PassiveSepEncCNN().to(dev).eval(), PassiveSepDecCNN().to(dev).eval()
+    enc.load_state_dict(enc_sd)
+    dec.load_state_dict(dec_sd)
+
+    B = B_PER_GPU
+    rep = B // N_DISTINCT
+    # each rank renders its own shard: roll the distinct set by rank so shards differ
+    roll = (rank * 7) % N_DISTINCT
+    h_mono = torch.from_numpy(np.roll(monos, roll, 0)).repeat(rep, 1, 1).pin_memory()
+    h_rir = torch.from_numpy(np.roll(rirs, roll, 0)).repeat(rep, 1, 1, 1).pin_memory()
+    h_len = torch.from_numpy(np.roll(lens, roll, 0)).repeat(rep, 1).pin_memory()
+    h_tc = torch.from_numpy(np.roll(tc, roll, 0)).repeat(rep, 1).pin_memory()
+    d_mono, d_rir, d_len, d_tc = (t.to(dev) for t in (h_mono, h_rir, h_len, h_tc))
+
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device(timers=None):
+        if timers is not None:
+            timers[0].record(stream)
+        waves = rend.rir_convolve(d_mono, d_rir, d_len)
+        if timers is not None:
+            timers[1].record(stream)
+        mix, _, _ = rend.stft_waves(waves)
+        if timers is not None:
+            timers[2].record(stream)
+        with torch.no_grad():
+            mask = dec(*enc({"mixed_bin_audio_mag": mix, "target_class": d_tc}))
+        if timers is not None:
+            timers[3].record(stream)
+        return mask
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # parity spot-check of this very configuration against the CPU oracle (not timed)
+    mask = step_device()
+    if cpu_mask is not None:
+        assert roll == 0
+        got = mask[[i % N_DISTINCT for i in range(sample)]].float().cpu()
+        err = float((got - cpu_mask).norm() / cpu_mask.norm())
+        assert err < 2e-2, f"bench parity check failed: mask rel-L2 {err}"
+
+    for _ in range(max(args.warmup - 1, 0)):
+        step_device()
+    timers = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(timers[i])
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    t_conv = sum(t[0].elapsed_time(t[1]) for t in timers) / args.steps
+    t_stft = sum(t[1].elapsed_time(t[2]) for t in timers) / args.steps
+    t_unet = sum(t[2].elapsed_time(t[3]) for t in timers) / args.steps
+
+    # ---- end to end: pinned host inputs -> H2D -> render -> U-Net -> D2H of the masks, every step ----
+    h_out = torch.empty((B, 2, 512, 32), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        m, r, l, c = (t.to(dev, non_blocking=True) for t in (h_mono, h_rir, h_len, h_tc))
+        waves = rend.rir_convolve(m, r, l)
+        mix, _, _ = rend.stft_waves(waves)
+        with torch.no_grad():
+            mask = dec(*enc({"mixed_bin_audio_mag": mix, "target_class": c}))
+        h_out.copy_(mask.permute(0, 3, 1, 2), non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, args.steps // 2)
+    f0.record(stream)
+    for _ in range(e2e_steps):
+        step_e2e()
+    f1.record(stream)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(times[0]), float(times[1])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    pk = peaks()
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in (h_mono, h_rir, h_len, h_tc))
+    d2h = h_out.numel() * h_out.element_size()
+    conv_gbs = BYTES_CONV * B / (t_conv * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("m2h_rir_conv_kernel", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (render) / bf16 operands + f32 accumulate (U-Net)", "data": "synthetic",
+        "config": workload_config({"global_batch": world * B, "parallelism": f"shard-by-mixture x{world}, no data-path collective"}),
+        "roofline": {"kernel": "m2h_rir_conv_kernel", "bound": "hbm", "achieved": conv_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": conv_gbs / pk["hbm_gbs"], "traffic": traffic, "peak_src": pk["src"],
+                     "algorithmic_bytes_per_launch": BYTES_CONV * B, "ms_per_launch": t_conv,
+                     "note": "compute/shared-memory bound fp32 FFT (25 MFLOP per mixture): see DESIGN.md section 4"},
+        "roofline_other": [
+            {"kernel": "m2h_stft_kernel", "bound": "hbm", "achieved": BYTES_STFT * B / (t_stft * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+             "frac": BYTES_STFT * B / (t_stft * 1e-3) / 1e9 / pk["hbm_gbs"], "ms_per_launch": t_stft},
+            {"kernel": "render chain (conv + stft) vs SURVEY 8d bytes", "bound": "hbm", "achieved": BYTES_RENDER * B / ((t_conv + t_stft) * 1e-3) / 1e9,
+             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": BYTES_RENDER * B / ((t_conv + t_stft) * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": t_conv + t_stft},
+            {"kernel": "unet_gemm_kernel x11 (+pack)", "bound": "tensor", "achieved": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
+             "unit": "TFLOP/s", "frac": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], "ms": t_unet},
+        ],
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": 15 * args.steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
