@@ -360,7 +360,7 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps},
-        "gpu_launches": 15 * args.steps,
+        "gpu_launches": 14 * args.steps,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

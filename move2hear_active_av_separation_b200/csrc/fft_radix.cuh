@@ -61,3 +61,49 @@ M2H_HD constexpr int bitrev(int k) {
   for (int i = 0; i < BITS; ++i) r |= ((k >> i) & 1) << (BITS - 1 - i);
   return r;
 }
+
+// out(k, v[bitrev(k)] * w1^k)  (times conj(w1)^k when CONJ) for k = 0..R-1.
+// The powers form a geometric sequence with a thread-constant base, so they are generated in registers
+// (two-level: k = Q*a + b, depth <= 5 multiplies) instead of being fetched from a shared-memory table:
+// table lookups with power-of-two lane strides were 40-67 % bank conflicts in the first ncu captures.
+//
+// Both anchors w1 and wq = w1^Q come correctly rounded from a table (computing wq from the rounded w1 would amplify
+// w1's rounding error by Q): the worst amplification of a table rounding error is (Q - 1) + (R/Q - 1).
+#define M2H_TW_Q(R) ((R) == 32 ? 8 : 4)
+template <int R, int BITS, bool CONJ, typename Out>
+M2H_DEV void twiddle_powers_out(const float2 (&v)[R], float2 w1, float2 wq, Out out) {
+  constexpr int Q = M2H_TW_Q(R);
+  float2 wb[Q];
+  wb[0] = make_float2(1.f, 0.f);
+  wb[1] = w1;
+  M2H_UNROLL for (int b = 2; b < Q; ++b) wb[b] = c_mul(wb[b >> 1], wb[(b + 1) >> 1]);
+  float2 wa = make_float2(1.f, 0.f);
+  M2H_UNROLL for (int a = 0; a < R / Q; ++a) {
+    M2H_UNROLL for (int b = 0; b < Q; ++b) {
+      const int k = a * Q + b;
+      if (k == 0) { out(0, v[0]); continue; }
+      const float2 t = a == 0 ? wb[b] : (b == 0 ? wa : c_mul(wa, wb[b]));
+      out(k, c_mul_sel<CONJ>(v[bitrev<BITS>(k)], t));
+    }
+    if (a + 1 < R / Q) wa = a == 0 ? wq : (a == 1 ? c_mul(wq, wq) : c_mul(wa, wq));
+  }
+}
+// in-place variant for twiddles applied on load: v[k] *= w1^k (natural order)
+template <int R, bool CONJ>
+M2H_DEV void twiddle_powers_inplace(float2 (&v)[R], float2 w1, float2 wq) {
+  constexpr int Q = M2H_TW_Q(R);
+  float2 wb[Q];
+  wb[0] = make_float2(1.f, 0.f);
+  wb[1] = w1;
+  M2H_UNROLL for (int b = 2; b < Q; ++b) wb[b] = c_mul(wb[b >> 1], wb[(b + 1) >> 1]);
+  float2 wa = make_float2(1.f, 0.f);
+  M2H_UNROLL for (int a = 0; a < R / Q; ++a) {
+    M2H_UNROLL for (int b = 0; b < Q; ++b) {
+      const int k = a * Q + b;
+      if (k == 0) continue;
+      const float2 t = a == 0 ? wb[b] : (b == 0 ? wa : c_mul(wa, wb[b]));
+      v[k] = c_mul_sel<CONJ>(v[k], t);
+    }
+    if (a + 1 < R / Q) wa = a == 0 ? wq : (a == 1 ? c_mul(wq, wq) : c_mul(wa, wq));
+  }
+}

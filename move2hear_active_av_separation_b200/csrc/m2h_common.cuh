@@ -25,6 +25,7 @@
   #define M2H_RESTRICT
   M2H_DEV float m2h_rintf(float v) { return nearbyintf(v); }
   M2H_DEV float m2h_ldg(const float* p) { return *p; }
+  M2H_DEV float2 m2h_ldg2(const float2* p) { return *p; }
 #else
   #include <cuda_runtime.h>
   #include <cuda_fp16.h>
@@ -36,6 +37,7 @@
   #define M2H_RESTRICT __restrict__
   M2H_DEV float m2h_rintf(float v) { return rintf(v); }
   M2H_DEV float m2h_ldg(const float* p) { return __ldg(p); }
+  M2H_DEV float2 m2h_ldg2(const float2* p) { return __ldg(p); }
 #endif
 
 // ---- complex arithmetic on float2 ---------------------------------------------------------
@@ -60,13 +62,18 @@ template <bool CONJ> M2H_DEV float2 c_mul_sel(float2 a, float2 w) { return CONJ 
 #define M2H_MAX_SAMPLES 16384
 
 // twiddle tables living in device global memory (copied to shared memory by each CTA)
+// Per-thread twiddle anchors of the conv kernel (512 threads), correctly rounded from double:
+//   thr[0][t] = W_16384^t        thr[1][t] = W_16384^(8t)            passes A / A'   (radix 32, Q = 8)
+//   thr[2][t] = W_512^(t&15)     thr[3][t] = W_512^(8*(t&15))        pass B          (radix 32)
+//   thr[4][t] = W_512^(t&31)     thr[5][t] = W_512^(4*(t&31))        pass C'         (radix 16, Q = 4)
+//   thr[6][t] = W_32768^f0(t), f0(t) = (t>>8) + 32*((t>>3)&31) + 1024*(t&7)   untangle twiddle of the thread's first pair
 struct M2hConvTables {
-  float2 tA[256];     // W_256^x     = exp(-2 pi i x / 256)       (= W_32768^(128 x))
-  float2 tB[128];     // W_32768^y
-  float2 t512[512];   // W_512^e
+  float2 thr[7][512];
 };
+// thr[0][l] = W_2048^l, thr[1][l] = W_2048^(4l)  (P1/P5);  thr[2][l] = W_128^(l&7), thr[3][l] = W_128^(4*(l&7))  (P2);
+// thr[4][l] = W_128^(l&15), thr[5][l] = W_128^(4*(l&15))  (P3)      -- l = thread id within its 128-thread group
 struct M2hStftTables {
-  float2 t2048[2048];   // W_2048^e
+  float2 thr[6][128];
   float2 bf[2048];      // FFT_2048 of the Bluestein chirp, stored in (k1,k2,k3) order: index (k1*16+k2)*8+k3 <-> f = k1+16*k2+256*k3
   float2 wc[1024];      // hann[n] * conj(chirp[n]), n < 1023 (entry 1023 = 0)
   float2 cc[1024];      // conj(chirp[m]) / 4096   (1/2048 inverse-FFT scale, 1/2 ear-untangle scale)

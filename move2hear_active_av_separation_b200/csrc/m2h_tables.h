@@ -11,14 +11,28 @@ static float2 cis(double turns_neg) {     // exp(-2 pi i * turns)
 }
 
 static void build_conv_tables(M2hConvTables& t) {
-  for (int i = 0; i < 256; ++i) t.tA[i] = cis((double)i / 256.0);
-  for (int i = 0; i < 128; ++i) t.tB[i] = cis((double)i / 32768.0);
-  for (int i = 0; i < 512; ++i) t.t512[i] = cis((double)i / 512.0);
+  for (int i = 0; i < 512; ++i) {
+    t.thr[0][i] = cis((double)i / 16384.0);
+    t.thr[1][i] = cis((double)(8 * i) / 16384.0);
+    t.thr[2][i] = cis((double)(i & 15) / 512.0);
+    t.thr[3][i] = cis((double)(8 * (i & 15)) / 512.0);
+    t.thr[4][i] = cis((double)(i & 31) / 512.0);
+    t.thr[5][i] = cis((double)(4 * (i & 31)) / 512.0);
+    const int f0 = (i >> 8) + 32 * ((i >> 3) & 31) + 1024 * (i & 7);
+    t.thr[6][i] = cis((double)f0 / 32768.0);
+  }
 }
 
 static void build_stft_tables(M2hStftTables& t) {
   const int N = M2H_NFFT, F = 2048;
-  for (int i = 0; i < F; ++i) t.t2048[i] = cis((double)i / F);
+  for (int i = 0; i < 128; ++i) {
+    t.thr[0][i] = cis((double)i / 2048.0);
+    t.thr[1][i] = cis((double)(4 * i) / 2048.0);
+    t.thr[2][i] = cis((double)(i & 7) / 128.0);
+    t.thr[3][i] = cis((double)(4 * (i & 7)) / 128.0);
+    t.thr[4][i] = cis((double)(i & 15) / 128.0);
+    t.thr[5][i] = cis((double)(4 * (i & 15)) / 128.0);
+  }
   std::vector<double> cr(N), ci(N);
   for (int n = 0; n < N; ++n) {          // chirp c[n] = exp(+i pi n^2 / N), phase reduced exactly in integers
     const long long m = ((long long)n * n) % (2 * N);

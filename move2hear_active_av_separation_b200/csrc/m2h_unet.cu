@@ -23,7 +23,7 @@ struct EncLayout {
   size_t w[5], scale[5], bias[5], cls_w, total;
 };
 struct DecLayout {
-  size_t w[5], scale[5], bias[5], head_w, head_b, total;
+  size_t w[5], scale[5], bias[5], head_w, head_wf, head_b, total;
 };
 
 static EncLayout enc_layout() {
@@ -42,6 +42,7 @@ static DecLayout dec_layout() {
   for (int i = 0; i < 5; ++i) { L.w[i] = o; o = align256(o + (size_t)4 * kDecCoutBase[i] * (i == 0 ? 1 : 4) * kDecCin[i] * 2); }
   for (int i = 0; i < 5; ++i) { L.scale[i] = o; o = align256(o + kDecCoutBase[i] * 4); L.bias[i] = o; o = align256(o + kDecCoutBase[i] * 4); }
   L.head_w = o; o = align256(o + 32 * 64 * 2);
+  L.head_wf = o; o = align256(o + 32 * 32 * 4);
   L.head_b = o; o = align256(o + 32 * 4);
   L.total = o;
   return L;
@@ -120,11 +121,12 @@ __global__ void pack_deconv0_w_kernel(const float* __restrict__ w, __nv_bfloat16
   }
 }
 // head Conv2d 1x1 [C][C] -> bf16 [32][64] zero padded; bias -> fp32 [32]
-__global__ void pack_head_kernel(const float* __restrict__ w, const float* __restrict__ b, __nv_bfloat16* __restrict__ wo, float* __restrict__ bo, int C) {
+__global__ void pack_head_kernel(const float* __restrict__ w, const float* __restrict__ b, __nv_bfloat16* __restrict__ wo, float* __restrict__ wf, float* __restrict__ bo, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 32 * 64) {
     const int n = i / 64, c = i % 64;
     wo[i] = __float2bfloat16_rn(n < C && c < C ? w[n * C + c] : 0.f);
+    if (c < 32) wf[n * 32 + c] = __bfloat162float(wo[i]);       // bf16-rounded copy for the fused (epilogue) head
   }
   if (i < 32) bo[i] = i < C ? b[i] : 0.f;
 }
@@ -176,6 +178,9 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 // launches
 // ------------------------------------------------------------------------------------------------
 static bool g_unet_attr_set[M2H_MAX_DEVICES];
+#ifndef M2H_UNFUSED_HEAD
+#define M2H_UNFUSED_HEAD 0      // 1: run the 1x1 head as its own GEMM launch (kept for A/B testing)
+#endif
 
 template <int BN>
 static int launch_bn(const UGLayer& L, cudaStream_t st) {
@@ -201,6 +206,10 @@ static int unet_prepare_device() {
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<32>::kSmemBytes));
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<64>::kSmemBytes));
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<128>::kSmemBytes));
+    // the default carve-out left room for one CTA per SM (first ncu capture: 100 KB config, 5 warps/SM): ask for the maximum
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     g_unet_attr_set[dev] = true;
   }
   return M2H_OK;
@@ -242,7 +251,7 @@ extern "C" int m2h_unet_pack_decoder(const m2h_unet_dec_params* p, int convert_b
     fold_bn_kernel<<<(kDecCoutBase[i] + 127) / 128, 128, 0, st>>>(p->bn_w[i], p->bn_b[i], p->bn_mean[i], p->bn_var[i], bn_eps,
                                                                  (float*)(base + L.scale[i]), (float*)(base + L.bias[i]), cout_real, kDecCoutBase[i]);
   }
-  pack_head_kernel<<<(32 * 64 + 127) / 128, 128, 0, st>>>(p->head_w, p->head_b, (__nv_bfloat16*)(base + L.head_w), (float*)(base + L.head_b), c_last);
+  pack_head_kernel<<<(32 * 64 + 127) / 128, 128, 0, st>>>(p->head_w, p->head_b, (__nv_bfloat16*)(base + L.head_w), (float*)(base + L.head_wf), (float*)(base + L.head_b), c_last);
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }
@@ -353,10 +362,14 @@ extern "C" int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2
     g.w = (const __nv_bfloat16*)(pk + PL.w[i]); g.Cout = kDecCoutBase[i]; g.Kvalid = g.Kpad = 4 * kDecCin[i];
     g.scale = (const float*)(pk + PL.scale[i]); g.bias = (const float*)(pk + PL.bias[i]); g.n_mod = kDecCoutBase[i]; g.slope = 0.f;
     g.out = out_ptr[i]; g.Hout = g.Wout = 2 * hin[i]; g.out_stride = 2; g.out_ld = out_ld[i]; g.n_valid = g.Cout;
+    if (i == 4 && !M2H_UNFUSED_HEAD) {   // last up-conv + BN + ReLU + 1x1 head + bias -> fp32 [B, C, 512, 32] in one kernel
+      g.out = mask_out; g.out_mode = UG_OUT_HEAD_NCHW_F32; g.n_valid = convert_bin2mono ? 16 : 32;
+      g.head_w = (const float*)(pk + PL.head_wf); g.head_b = (const float*)(pk + PL.head_b);
+    }
     rc = launch_layer(g, bn[i], st);
     if (rc != M2H_OK) return rc;
   }
-  {  // 1x1 head + bias -> fp32 NCHW = [B, C, 512, 32] (channel = ear*16 + slice, row = freq % 32)
+  if (M2H_UNFUSED_HEAD) {  // 1x1 head + bias -> fp32 NCHW = [B, C, 512, 32] (channel = ear*16 + slice, row = freq % 32)
     UGLayer g;
     layer_defaults(g);
     g.in = d4; g.Hin = g.Win = 32; g.Cin = 32; g.cin_shift = 5; g.in_ld = 32;

@@ -38,28 +38,29 @@ struct ConvParams {
 
 struct ConvSmem {
   float2 buf[M2H_CONV_BUF];
-  M2hConvTables tab;
 };
+
+// Every inter-pass twiddle set is a geometric sequence whose base depends only on the thread id: each pass fetches
+// its two correctly-rounded anchors (base, base^Q) with one coalesced, L1-resident global load and generates the other
+// powers in registers (fft_radix.cuh) - no shared-memory twiddle tables, hence no table bank conflicts.
+#define M2H_CONV_TW(t, which, tid) m2h_ldg2(&(t)->thr[which][tid])
+M2H_HD constexpr float conv_w16384_cos(int i) { return i == 0 ? 1.0f : i == 1 ? 0.9999999264657179f : i == 2 ? 0.9999997058628822f : i == 3 ? 0.9999993381915255f : i == 4 ? 0.9999988234517019f : i == 5 ? 0.999998161643487f : i == 6 ? 0.9999973527669782f : i == 7 ? 0.9999963968222944f : i == 8 ? 0.9999952938095762f : i == 9 ? 0.9999940437289858f : i == 10 ? 0.9999926465807072f : i == 11 ? 0.9999911023649456f : i == 12 ? 0.9999894110819284f : i == 13 ? 0.9999875727319041f : i == 14 ? 0.9999855873151432f : 0.9999834548319377f; }
+M2H_HD constexpr float conv_w16384_sin(int i) { return i == 0 ? -0.0f : i == 1 ? -0.00038349518757139556f : i == 2 ? -0.0007669903187427045f : i == 3 ? -0.0011504853371138485f : i == 4 ? -0.0015339801862847655f : i == 5 ? -0.001917474809855419f : i == 6 ? -0.002300969151425805f : i == 7 ? -0.0026844631545959617f : i == 8 ? -0.003067956762965976f : i == 9 ? -0.003451449920135994f : i == 10 ? -0.0038349425697062275f : i == 11 ? -0.004218434655276963f : i == 12 ? -0.0046019261204485705f : i == 13 ? -0.0049854169088215106f : i == 14 ? -0.0053689069639963425f : -0.005752396229573736f; }
 
 M2H_DEV int conv_pos(int f) {            // position of spectrum index f = k1 + 32*k2 + 1024*k3
   return (f & 31) * M2H_CONV_S1 + ((f >> 5) & 31) * M2H_CONV_S2 + (f >> 10);
 }
-M2H_DEV float2 conv_twF(const M2hConvTables& t, int f) {     // W_32768^f, 0 <= f < 32768
-  return c_mul(t.tA[f >> 7], t.tB[f & 127]);
-}
-M2H_DEV float2 conv_twM(const M2hConvTables& t, int e) {     // W_16384^e, 0 <= e < 16384
-  return c_mul(t.tA[e >> 6], t.tB[(e & 63) << 1]);
-}
+// pair index -> spectrum index f in [0, 8192): k3 fastest so that half-warps touch consecutive positions
+M2H_DEV int conv_pair_f(int idx) { return (idx >> 8) + 32 * ((idx >> 3) & 31) + 1024 * (idx & 7); }
 
 // ---- forward FFT passes B and C (pass A is fused with the loads) ----------------------------
-M2H_DEV void conv_fwd_pass_b(ConvSmem& s, int tid) {
+M2H_DEV void conv_fwd_pass_b(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t) {
   const int k1 = tid >> 4, n3 = tid & 15;
   float2* p = s.buf + k1 * M2H_CONV_S1 + n3;
   float2 v[32];
   M2H_UNROLL for (int j = 0; j < 32; ++j) v[j] = p[j * M2H_CONV_S2];
   fft_reg<32, false>(v);
-  M2H_UNROLL for (int k2 = 0; k2 < 32; ++k2)
-    p[k2 * M2H_CONV_S2] = k2 == 0 ? v[0] : c_mul(v[bitrev<5>(k2)], s.tab.t512[n3 * k2]);
+  twiddle_powers_out<32, 5, false>(v, M2H_CONV_TW(t, 2, tid), M2H_CONV_TW(t, 3, tid), [&](int k2, float2 x) { p[k2 * M2H_CONV_S2] = x; });   // W_512^(n3*k2)
 }
 M2H_DEV void conv_fwd_pass_c(ConvSmem& s, int tid) {
   M2H_UNROLL for (int h = 0; h < 2; ++h) {
@@ -72,7 +73,7 @@ M2H_DEV void conv_fwd_pass_c(ConvSmem& s, int tid) {
   }
 }
 // ---- inverse FFT passes C' and B' (pass A' is fused with the output) ---------------------------
-M2H_DEV void conv_inv_pass_c(ConvSmem& s, int tid) {
+M2H_DEV void conv_inv_pass_c(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t) {
   M2H_UNROLL for (int h = 0; h < 2; ++h) {
     const int q = tid + h * M2H_CONV_THREADS;
     const int k2 = q & 31;
@@ -80,25 +81,24 @@ M2H_DEV void conv_inv_pass_c(ConvSmem& s, int tid) {
     float2 v[16];
     M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[j];
     fft_reg<16, true>(v);
-    M2H_UNROLL for (int n3 = 0; n3 < 16; ++n3)
-      p[n3] = n3 == 0 ? v[0] : c_mulc(v[bitrev<4>(n3)], s.tab.t512[n3 * k2]);
+    twiddle_powers_out<16, 4, true>(v, M2H_CONV_TW(t, 4, tid), M2H_CONV_TW(t, 5, tid), [&](int n3, float2 x) { p[n3] = x; });                 // conj W_512^(n3*k2)
   }
 }
+// pass B' stores untwiddled; conj W_16384^((16*n2+n3)*k1) = conj(W_16384^r)^k1 is applied by pass A' on load
 M2H_DEV void conv_inv_pass_b(ConvSmem& s, int tid) {
   const int k1 = tid >> 4, n3 = tid & 15;
   float2* p = s.buf + k1 * M2H_CONV_S1 + n3;
   float2 v[32];
   M2H_UNROLL for (int j = 0; j < 32; ++j) v[j] = p[j * M2H_CONV_S2];
   fft_reg<32, true>(v);
-  M2H_UNROLL for (int n2 = 0; n2 < 32; ++n2)
-    p[n2 * M2H_CONV_S2] = c_mulc(v[bitrev<5>(n2)], conv_twM(s.tab, (16 * n2 + n3) * k1));
+  M2H_UNROLL for (int n2 = 0; n2 < 32; ++n2) p[n2 * M2H_CONV_S2] = v[bitrev<5>(n2)];
 }
 
 // Pass A of the forward transform with the global loads fused in.  Thread `tid` owns the residue
 // r = tid of the packed index j = n1*512 + r and reads packed samples (x[2j], x[2j+1]).
 //   SRC = 0: int16 mono, SRC = 1: float RIR taps.  `len` = number of valid real samples.
 template <int SRC>
-M2H_DEV void conv_fwd_pass_a(ConvSmem& s, int tid, const void* src, int len) {
+M2H_DEV void conv_fwd_pass_a(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const void* src, int len) {
   const int r = tid;
   float2 v[32];
   M2H_UNROLL for (int n1 = 0; n1 < 32; ++n1) {
@@ -117,12 +117,8 @@ M2H_DEV void conv_fwd_pass_a(ConvSmem& s, int tid, const void* src, int len) {
   }
   fft_reg<32, false>(v);
   float2* p = s.buf + (r >> 4) * M2H_CONV_S2 + (r & 15);
-  M2H_UNROLL for (int k1 = 0; k1 < 32; ++k1)
-    p[k1 * M2H_CONV_S1] = k1 == 0 ? v[0] : c_mul(v[bitrev<5>(k1)], conv_twM(s.tab, r * k1));
+  twiddle_powers_out<32, 5, false>(v, M2H_CONV_TW(t, 0, tid), M2H_CONV_TW(t, 1, tid), [&](int k1, float2 x) { p[k1 * M2H_CONV_S1] = x; });    // W_16384^(r*k1)
 }
-
-// pair index -> spectrum index f in [0, 8192): k3 fastest so that half-warps touch consecutive positions
-M2H_DEV int conv_pair_f(int idx) { return (idx >> 8) + 32 * ((idx >> 3) & 31) + 1024 * (idx & 7); }
 
 // Untangle the packed-real spectrum at (f, M-f):  returns 2*X[f] in xa and 2*X[M-f] in xb.
 M2H_DEV void conv_untangle(float2 za, float2 zb, float2 w, float2& xa, float2& xb) {
@@ -134,23 +130,28 @@ M2H_DEV void conv_untangle(float2 za, float2 zb, float2 w, float2& xa, float2& x
 }
 
 // Phase: spectrum of the mono signal -> per-CTA scratch (float4 = {2X[f], 2X[M-f]}).
-M2H_DEV void conv_store_mono_spectrum(ConvSmem& s, int tid, float4* g) {
-  for (int idx = tid; idx < 8192; idx += M2H_CONV_THREADS) {
+M2H_DEV void conv_store_mono_spectrum(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, float4* g) {
+  const float2 wU = M2H_CONV_TW(t, 6, tid);
+  M2H_UNROLL for (int i = 0; i < 8192 / M2H_CONV_THREADS; ++i) {
+    const int idx = tid + i * M2H_CONV_THREADS;
     if (idx == 0) {
       const float2 z0 = s.buf[0], zh = s.buf[conv_pos(8192)];
       g[0] = make_float4(2.f * (z0.x + z0.y), 2.f * (z0.x - z0.y), 2.f * zh.x, -2.f * zh.y);   // X[0], X[M] (real), X[M/2]
     } else {
       const int f = conv_pair_f(idx);
       float2 xa, xb;
-      conv_untangle(s.buf[conv_pos(f)], s.buf[conv_pos(16384 - f)], conv_twF(s.tab, f), xa, xb);
+      const float2 w = c_mul(wU, make_float2(conv_w16384_cos(i), conv_w16384_sin(i)));   // W_32768^(f0 + 2i)
+      conv_untangle(s.buf[conv_pos(f)], s.buf[conv_pos(16384 - f)], w, xa, xb);
       g[idx] = make_float4(xa.x, xa.y, xb.x, xb.y);
     }
   }
 }
 
 // Phase: untangle H, multiply by X, re-tangle for the inverse transform (in place).
-M2H_DEV void conv_multiply_spectrum(ConvSmem& s, int tid, const float4* g) {
-  for (int idx = tid; idx < 8192; idx += M2H_CONV_THREADS) {
+M2H_DEV void conv_multiply_spectrum(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const float4* g) {
+  const float2 wU = M2H_CONV_TW(t, 6, tid);
+  M2H_UNROLL for (int i = 0; i < 8192 / M2H_CONV_THREADS; ++i) {
+    const int idx = tid + i * M2H_CONV_THREADS;
     const float4 x = g[idx];
     if (idx == 0) {
       const int ph = conv_pos(8192);
@@ -163,7 +164,7 @@ M2H_DEV void conv_multiply_spectrum(ConvSmem& s, int tid, const float4* g) {
     } else {
       const int f = conv_pair_f(idx);
       const int pa = conv_pos(f), pb = conv_pos(16384 - f);
-      const float2 w = conv_twF(s.tab, f);
+      const float2 w = c_mul(wU, make_float2(conv_w16384_cos(i), conv_w16384_sin(i)));
       float2 ha, hb;
       conv_untangle(s.buf[pa], s.buf[pb], w, ha, hb);
       const float2 ya = c_mul(make_float2(x.x, x.y), ha);
@@ -186,11 +187,12 @@ M2H_DEV int16_t conv_quantise(float v) {
 }
 
 // Pass A' of the inverse transform fused with scale / round / window / store.
-M2H_DEV void conv_inv_pass_a_store(ConvSmem& s, int tid, int16_t* out, int N, int c_off) {
+M2H_DEV void conv_inv_pass_a_store(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, int16_t* out, int N, int c_off) {
   const int r = tid;
   const float2* p = s.buf + (r >> 4) * M2H_CONV_S2 + (r & 15);
   float2 v[32];
   M2H_UNROLL for (int k1 = 0; k1 < 32; ++k1) v[k1] = p[k1 * M2H_CONV_S1];
+  twiddle_powers_inplace<32, true>(v, M2H_CONV_TW(t, 0, tid), M2H_CONV_TW(t, 1, tid));                                                        // conj W_16384^(r*k1)
   fft_reg<32, true>(v);
   const float scale = 1.0f / (8.0f * 16384.0f);      // 1/M inverse scale, 2*2*2 from the untangle/re-tangle steps
   M2H_UNROLL for (int n1 = 0; n1 < 32; ++n1) {
@@ -203,12 +205,6 @@ M2H_DEV void conv_inv_pass_a_store(ConvSmem& s, int tid, int16_t* out, int N, in
 
 // The whole per-CTA loop.  `cta`/`n_ctas` = blockIdx.x / gridDim.x.
 M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables* M2H_RESTRICT gtab, int cta, int n_ctas) {
-  M2H_FOR_THREADS(tid, M2H_CONV_THREADS) {
-    const float2* src = (const float2*)gtab;
-    float2* dst = (float2*)&s.tab;
-    for (int i = tid; i < (int)(sizeof(M2hConvTables) / sizeof(float2)); i += M2H_CONV_THREADS) dst[i] = src[i];
-  }
-  M2H_SYNC();
   float4* g = P.scratch + (size_t)cta * M2H_CONV_SCRATCH_F4;
   for (int item = cta; item < P.n_items; item += n_ctas) {
     const int N = P.N;
@@ -226,30 +222,30 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
       }
       continue;
     }
-    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_a<0>(s, tid, P.mono + (size_t)item * N, N);
+    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_a<0>(s, tid, gtab, P.mono + (size_t)item * N, N);
     M2H_SYNC();
-    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid);
+    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid, gtab);
     M2H_SYNC();
     M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_c(s, tid);
     M2H_SYNC();
-    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_store_mono_spectrum(s, tid, g);
+    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_store_mono_spectrum(s, tid, gtab, g);
     M2H_SYNC();
     for (int ear = 0; ear < 2; ++ear) {
       const float* h = P.rir + ((size_t)item * 2 + ear) * P.Lmax + jmin;
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_a<1>(s, tid, h, Leff);
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_a<1>(s, tid, gtab, h, Leff);
       M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid);
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid, gtab);
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_c(s, tid);
       M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_multiply_spectrum(s, tid, g);
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_multiply_spectrum(s, tid, gtab, g);
       M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_inv_pass_c(s, tid);
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_inv_pass_c(s, tid, gtab);
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_inv_pass_b(s, tid);
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS)
-        conv_inv_pass_a_store(s, tid, P.waves + ((size_t)item * 2 + ear) * N, N, c_off);
+        conv_inv_pass_a_store(s, tid, gtab, P.waves + ((size_t)item * 2 + ear) * N, N, c_off);
       M2H_SYNC();
     }
   }

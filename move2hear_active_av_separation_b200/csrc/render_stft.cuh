@@ -8,7 +8,7 @@
 // identity as a 2048-point circular convolution.  The two ears of a frame ride together as one complex signal
 // (left + i*right) and are separated by conjugate symmetry afterwards, so one frame pair costs two complex
 // FFT-2048s.  A CTA of 512 threads = 4 groups of 128 threads; each group transforms one frame pair at a time in
-// a padded [16][16][8] shared buffer (position(i1,i2,i3) = i1*152 + i2*9 + i3, conflict-free for all passes).
+// a padded [16][16][8] shared buffer (position(i1,i2,i3) = i1*136 + i2*8 + (i2>>1) + i3, conflict-free for all passes).
 //
 // Signals: s = 0 is the mixture ((sum_k wave_k) * 2^-15 / K, exactly the fp32 arithmetic of
 // simulator_train.py:469-471), s >= 1 is source s-1 alone (wave * 2^-15).  A generic fp32 input mode serves the
@@ -18,9 +18,11 @@
 
 #define M2H_STFT_THREADS 512
 #define M2H_STFT_GROUPS 4
-#define M2H_STFT_S1 152
-#define M2H_STFT_S2 9
+// padded [16][16][8] layout: position(i1,i2,i3) = i1*136 + i2*8 + (i2 >> 1) + i3  (one pad slot per 16 elements and
+// 8 per i1 block): every pass's half-warp touches 16 distinct bank pairs
+#define M2H_STFT_S1 136
 #define M2H_STFT_BUF (16 * M2H_STFT_S1)
+#define M2H_STFT_POS2(i2) ((i2) * 8 + ((i2) >> 1))
 
 enum {
   M2H_OUT_MIX_LOG1P = 1,   // mixture magnitude is written as log1p(mag)
@@ -48,9 +50,9 @@ struct StftParams {
 
 struct StftSmem {
   float2 buf[M2H_STFT_GROUPS][M2H_STFT_BUF];
-  float2 t2048[2048];
-  float2 bf[2048];
+  float2 bf[2048];          // chirp spectrum, [k3][k1*16+k2] so that consecutive threads read consecutive entries
 };
+#define M2H_STFT_TW(t, which, tid) m2h_ldg2(&(t)->thr[which][(tid) & 127])
 
 M2H_DEV int stft_reflect(int i, int N) { return i < 0 ? -i : (i >= N ? 2 * (N - 1) - i : i); }
 
@@ -154,63 +156,60 @@ M2H_DEV void stft_p1(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_
   }
   M2H_UNROLL for (int n1 = 8; n1 < 16; ++n1) v[n1] = make_float2(0.f, 0.f);
   fft_reg<16, false>(v);
-  float2* p = s.buf[grp] + (r >> 3) * M2H_STFT_S2 + (r & 7);
-  M2H_UNROLL for (int k1 = 0; k1 < 16; ++k1)
-    p[k1 * M2H_STFT_S1] = k1 == 0 ? v[0] : c_mul(v[bitrev<4>(k1)], s.t2048[r * k1]);
+  float2* p = s.buf[grp] + M2H_STFT_POS2(r >> 3) + (r & 7);
+  twiddle_powers_out<16, 4, false>(v, M2H_STFT_TW(gt, 0, tid), M2H_STFT_TW(gt, 1, tid), [&](int k1, float2 x) { p[k1 * M2H_STFT_S1] = x; });     // W_2048^(r*k1)
 }
 // P2: radix-16 pass along n2, twiddle W_128^(n3*k2) = W_2048^(16*n3*k2)
-M2H_DEV void stft_p2(const StftParams& P, StftSmem& s, int tid, int t0) {
+M2H_DEV void stft_p2(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int t0) {
   const int grp = tid >> 7, lt = tid & 127;
   if (t0 + grp >= P.T) return;
   const int k1 = lt >> 3, n3 = lt & 7;
   float2* p = s.buf[grp] + k1 * M2H_STFT_S1 + n3;
   float2 v[16];
-  M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[j * M2H_STFT_S2];
+  M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[M2H_STFT_POS2(j)];
   fft_reg<16, false>(v);
-  M2H_UNROLL for (int k2 = 0; k2 < 16; ++k2)
-    p[k2 * M2H_STFT_S2] = k2 == 0 ? v[0] : c_mul(v[bitrev<4>(k2)], s.t2048[16 * n3 * k2]);
+  twiddle_powers_out<16, 4, false>(v, M2H_STFT_TW(gt, 2, tid), M2H_STFT_TW(gt, 3, tid), [&](int k2, float2 x) { p[M2H_STFT_POS2(k2)] = x; });    // W_128^(n3*k2)
 }
 // P3: radix-8 pass along n3, multiply by the chirp spectrum, inverse radix-8 pass, twiddle conj(W_128^(n3*k2))
-M2H_DEV void stft_p3(const StftParams& P, StftSmem& s, int tid, int t0) {
+M2H_DEV void stft_p3(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int t0) {
   const int grp = tid >> 7, lt = tid & 127;
   if (t0 + grp >= P.T) return;
   M2H_UNROLL for (int h = 0; h < 2; ++h) {
     const int q = lt + h * 128;                 // q = k1*16 + k2
     const int k2 = q & 15;
-    float2* p = s.buf[grp] + (q >> 4) * M2H_STFT_S1 + k2 * M2H_STFT_S2;
+    float2* p = s.buf[grp] + (q >> 4) * M2H_STFT_S1 + M2H_STFT_POS2(k2);
     float2 v[8], u[8];
     M2H_UNROLL for (int j = 0; j < 8; ++j) v[j] = p[j];
     fft_reg<8, false>(v);
-    M2H_UNROLL for (int k3 = 0; k3 < 8; ++k3) u[k3] = c_mul(v[bitrev<3>(k3)], s.bf[q * 8 + k3]);
+    M2H_UNROLL for (int k3 = 0; k3 < 8; ++k3) u[k3] = c_mul(v[bitrev<3>(k3)], s.bf[k3 * 256 + q]);
     fft_reg<8, true>(u);
-    M2H_UNROLL for (int n3 = 0; n3 < 8; ++n3)
-      p[n3] = n3 == 0 ? u[0] : c_mulc(u[bitrev<3>(n3)], s.t2048[16 * n3 * k2]);
+    twiddle_powers_out<8, 3, true>(u, M2H_STFT_TW(gt, 4, tid), M2H_STFT_TW(gt, 5, tid), [&](int n3, float2 x) { p[n3] = x; });                   // conj W_128^(n3*k2)
   }
 }
-// P4: inverse radix-16 pass along k2 -> n2, twiddle conj(W_2048^((8*n2+n3)*k1))
+// P4: inverse radix-16 pass along k2 -> n2 (its twiddle conj(W_2048^(r*k1)), r = 8*n2+n3, is applied by P5)
 M2H_DEV void stft_p4(const StftParams& P, StftSmem& s, int tid, int t0) {
   const int grp = tid >> 7, lt = tid & 127;
   if (t0 + grp >= P.T) return;
   const int k1 = lt >> 3, n3 = lt & 7;
   float2* p = s.buf[grp] + k1 * M2H_STFT_S1 + n3;
   float2 v[16];
-  M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[j * M2H_STFT_S2];
+  M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[M2H_STFT_POS2(j)];
   fft_reg<16, true>(v);
-  M2H_UNROLL for (int n2 = 0; n2 < 16; ++n2)
-    p[n2 * M2H_STFT_S2] = c_mulc(v[bitrev<4>(n2)], s.t2048[(8 * n2 + n3) * k1]);
+  M2H_UNROLL for (int n2 = 0; n2 < 16; ++n2) p[M2H_STFT_POS2(n2)] = v[bitrev<4>(n2)];     // twiddle applied by P5 on load
 }
 // P5: inverse radix-16 pass along k1 -> n1 (only m = n1*128 + r < 1023 is needed), times conj(chirp)/4096
 M2H_DEV void stft_p5(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int t0) {
   const int grp = tid >> 7, r = tid & 127;
   if (t0 + grp >= P.T) return;
-  float2* p = s.buf[grp] + (r >> 3) * M2H_STFT_S2 + (r & 7);
+  float2* p = s.buf[grp] + M2H_STFT_POS2(r >> 3) + (r & 7);
   float2 v[16];
   M2H_UNROLL for (int k1 = 0; k1 < 16; ++k1) v[k1] = p[k1 * M2H_STFT_S1];
+  twiddle_powers_inplace<16, true>(v, M2H_STFT_TW(gt, 0, tid), M2H_STFT_TW(gt, 1, tid));                                                          // conj W_2048^(r*k1)
   fft_reg<16, true>(v);
   M2H_UNROLL for (int n1 = 0; n1 < 8; ++n1)
     p[n1 * M2H_STFT_S1] = c_mul(v[bitrev<4>(n1)], gt->cc[n1 * 128 + r]);
 }
-M2H_DEV int stft_pos(int m) { return (m >> 7) * M2H_STFT_S1 + ((m >> 3) & 15) * M2H_STFT_S2 + (m & 7); }
+M2H_DEV int stft_pos(int m) { return (m >> 7) * M2H_STFT_S1 + M2H_STFT_POS2((m >> 3) & 15) + (m & 7); }
 // P6: separate the ears (X_l = (X[k] + conj X[N-k]) / 2, X_r = (X[k] - conj X[N-k]) / 2i; the 1/2 lives in cc) and emit
 M2H_DEV void stft_p6(const StftParams& P, StftSmem& s, int tid, int b, int sig, int t0) {
   const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
@@ -226,7 +225,7 @@ M2H_DEV void stft_p6(const StftParams& P, StftSmem& s, int tid, int b, int sig, 
 
 M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int cta, int n_ctas) {
   M2H_FOR_THREADS(tid, M2H_STFT_THREADS) {
-    for (int i = tid; i < 2048; i += M2H_STFT_THREADS) { s.t2048[i] = gt->t2048[i]; s.bf[i] = gt->bf[i]; }
+    for (int i = tid; i < 2048; i += M2H_STFT_THREADS) s.bf[(i & 7) * 256 + (i >> 3)] = gt->bf[i];
   }
   M2H_SYNC();
   const int n_items = P.B * P.n_signals;
@@ -235,9 +234,9 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
     for (int t0 = 0; t0 < P.T; t0 += M2H_STFT_GROUPS) {
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p1(P, s, gt, tid, b, sig, t0);
       M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p2(P, s, tid, t0);
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p2(P, s, gt, tid, t0);
       M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p3(P, s, tid, t0);
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p3(P, s, gt, tid, t0);
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p4(P, s, tid, t0);
       M2H_SYNC();

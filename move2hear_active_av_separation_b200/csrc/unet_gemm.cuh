@@ -27,7 +27,7 @@
 #define UG_MAX_TAPS 16
 #define UG_LOOKAHEAD 2
 
-enum { UG_OUT_NHWC_BF16 = 0, UG_OUT_NCHW_F32 = 1 };
+enum { UG_OUT_NHWC_BF16 = 0, UG_OUT_NCHW_F32 = 1, UG_OUT_HEAD_NCHW_F32 = 2 };
 
 struct UGLayer {
   // input activation, NHWC bf16: element (b, y, x, c) at in[((b*Hin + y)*Win + x)*in_ld + c]
@@ -50,7 +50,11 @@ struct UGLayer {
   // output: pixel (qy*out_stride + py, qx*out_stride + px); column n -> (n / n_split)*n_split_ld + n % n_split
   void* out;
   int out_mode, Hout, Wout, out_stride, out_ld, n_split, n_split_ld;
-  int n_valid;             // NCHW mode: channels >= n_valid are padding and are not stored; Cout_real = n_valid
+  int n_valid;             // NCHW modes: channels >= n_valid are padding and are not stored; Cout_real = n_valid
+  // UG_OUT_HEAD_NCHW_F32 (BN = 32 only): the activated 32-channel pixel goes through the 1x1 head conv in the epilogue
+  //   z[n] = head_b[n] + sum_c head_w[n][c] * y[c]   (separator_cnn.py:135) and z is stored as fp32 NCHW
+  const float* head_w;     // fp32 [32][32] (zero padded)
+  const float* head_b;     // fp32 [32]
 };
 
 namespace ug {
@@ -122,18 +126,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 template <int BN> struct Cfg {
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int kStages = 3;
+  static constexpr int kMinBlocks = BN >= 128 ? 2 : 3;
   static constexpr int kABytes = UG_BM * UG_BK * 2;          // 16 KB
   static constexpr int kBBytes = BN * UG_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + (BN == 32 ? 4224 : 0) /*head weights*/;
 };
 
 }  // namespace ug
 
 template <int BN>
-__global__ void __launch_bounds__(UG_THREADS, 1) unet_gemm_kernel(const UGLayer L) {
+__global__ void __launch_bounds__(UG_THREADS, ug::Cfg<BN>::kMinBlocks) unet_gemm_kernel(const UGLayer L) {
   using C = ug::Cfg<BN>;
   extern __shared__ unsigned char ug_smem_raw[];
   const uint32_t raw = ug::smem_u32(ug_smem_raw);
@@ -153,6 +158,10 @@ __global__ void __launch_bounds__(UG_THREADS, 1) unet_gemm_kernel(const UGLayer 
     for (int s = 0; s < C::kStages; ++s) { ug::mbar_init(full_bar(s), UG_PRODUCER_THREADS); ug::mbar_init(empty_bar(s), 1); }
     ug::mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  float* head_smem = reinterpret_cast<float*>(tiles_ptr + C::kStages * C::kStageBytes + 256);
+  if (BN == 32 && L.out_mode == UG_OUT_HEAD_NCHW_F32) {
+    for (int i = tid; i < 32 * 32 + 32; i += UG_THREADS) head_smem[i] = i < 1024 ? L.head_w[i] : L.head_b[i - 1024];
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ug::smem_u32(tmem_slot)), "r"((uint32_t)C::kTmemCols) : "memory");
@@ -178,15 +187,28 @@ __global__ void __launch_bounds__(UG_THREADS, 1) unet_gemm_kernel(const UGLayer 
       const int s = kb % C::kStages;
       if (kb >= C::kStages) ug::mbar_wait(empty_bar(s), (uint32_t)((kb / C::kStages - 1) & 1));
       const uint32_t a_st = tiles + s * C::kStageBytes, b_st = a_st + C::kABytes;
-      // A: 8 chunks of 8 channels
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kk = kb * UG_BK + j * 8;
+      // A: 8 chunks of 8 channels.  With Cin >= 64 a k-block lies inside one tap: one address / bounds computation.
+      if (L.Cin >= UG_BK) {
+        const int kk = kb * UG_BK;
         const int tap = kk >> L.cin_shift, c = kk & (L.Cin - 1);
         const int iy = by + L.dy[phase][tap & (UG_MAX_TAPS - 1)], ix = bx + L.dx[phase][tap & (UG_MAX_TAPS - 1)];
         const bool ok = row_ok && kk < L.Kvalid && iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
         const __nv_bfloat16* src = ok ? in_b + ((size_t)iy * L.Win + ix) * L.in_ld + c : L.in;
-        ug::cp_async16(a_st + a_row + (((uint32_t)j ^ sw) << 4), src, ok ? 16u : 0u);
+        const uint32_t nb = ok ? 16u : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ug::cp_async16(a_st + a_row + (((uint32_t)j ^ sw) << 4), ok ? src + j * 8 : src, nb);
+      } else {   // Cin == 32: two taps per k-block
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int kk = kb * UG_BK + h * 32;
+          const int tap = kk >> L.cin_shift;
+          const int iy = by + L.dy[phase][tap & (UG_MAX_TAPS - 1)], ix = bx + L.dx[phase][tap & (UG_MAX_TAPS - 1)];
+          const bool ok = row_ok && kk < L.Kvalid && iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
+          const __nv_bfloat16* src = ok ? in_b + ((size_t)iy * L.Win + ix) * L.in_ld : L.in;
+          const uint32_t nb = ok ? 16u : 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ug::cp_async16(a_st + a_row + (((uint32_t)(h * 4 + j) ^ sw) << 4), ok ? src + j * 8 : src, nb);
+        }
       }
       // B: BN rows x 8 chunks, 128 threads
 #pragma unroll
@@ -245,6 +267,27 @@ __global__ void __launch_bounds__(UG_THREADS, 1) unet_gemm_kernel(const UGLayer 
           pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
           pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
           *reinterpret_cast<uint4*>(o + i) = pk;
+        }
+      } else if (BN == 32 && L.out_mode == UG_OUT_HEAD_NCHW_F32) {
+        // 1x1 head on the activated pixel (operands rounded to bf16 like the unfused layer pair), fp32 NCHW store
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = __bfloat162float(__float2bfloat16_rn(y[i]));
+        float* o = reinterpret_cast<float*>(L.out) + ((size_t)b * L.n_valid * L.Hout + oy) * L.Wout + ox;
+#pragma unroll 1
+        for (int n8 = 0; n8 < L.n_valid; n8 += 8) {
+          float z[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) z[u] = head_smem[1024 + n8 + u];
+#pragma unroll
+          for (int c4 = 0; c4 < 32; c4 += 4) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 w4 = *reinterpret_cast<const float4*>(head_smem + (n8 + u) * 32 + c4);
+              z[u] = fmaf(w4.x, y[c4], fmaf(w4.y, y[c4 + 1], fmaf(w4.z, y[c4 + 2], fmaf(w4.w, y[c4 + 3], z[u]))));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) o[(size_t)(n8 + u) * L.Hout * L.Wout] = z[u];
         }
       } else {   // fp32 NCHW: out[((b*Cout + n)*Hout + oy)*Wout + ox]
         float* o = reinterpret_cast<float*>(L.out) + (((size_t)b * L.n_valid + nn) * L.Hout + oy) * L.Wout + ox;
