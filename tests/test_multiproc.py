@@ -1,0 +1,60 @@
+"""CPU, world_size 2, gloo: the host-side sharding / max-over-ranks logic bench.py uses for N > 1."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, %r)
+    import numpy as np, torch, torch.distributed as dist
+    from oracle import render as R
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    N_DISTINCT = 8
+    monos = R.synth_monos(N_DISTINCT, 2, seed=0)
+    # same sharding rule as bench.py: every rank rolls the seeded set by 7*rank
+    roll = (rank * 7) %% N_DISTINCT
+    mine = np.roll(monos, roll, 0)
+    digest = torch.tensor([float(np.abs(mine[0]).sum())], dtype=torch.float64)
+    gathered = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(gathered, digest)
+    t = torch.tensor([10.0 + rank, 3.0 - rank], dtype=torch.float64)      # per-rank (value, e2e) step times
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps({"world": world, "digests": [float(g) for g in gathered], "max": t.tolist()}))
+    dist.destroy_process_group()
+""") % ROOT
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_gloo_sharding_and_max_reduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["world"] == 2 and d["max"] == [11.0, 3.0]
+    assert d["digests"][0] != d["digests"][1]          # the two ranks render different shards
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
