@@ -293,16 +293,14 @@ def run_ours(args):
     t_stft = sum(t[1].elapsed_time(t[2]) for t in timers) / args.steps
     t_unet = sum(t[2].elapsed_time(t[3]) for t in timers) / args.steps
 
-    # ---- end to end: pinned host inputs -> H2D -> render -> U-Net -> D2H of the masks, every step ----
+    # ---- end to end: pinned host inputs -> H2D -> render -> U-Net -> D2H of the masks, every step, through the
+    # package's host-buffer entry (pipeline.SeparationPipeline: chunks in flight on 3 streams so copies overlap kernels)
+    from move2hear_active_av_separation_b200.pipeline import SeparationPipeline
     h_out = torch.empty((B, 2, 512, 32), dtype=torch.float32).pin_memory()
+    pipe = SeparationPipeline(enc, dec, dev, K_SRC, N_SAMPLES, L_TAPS)
 
     def step_e2e():
-        m, r, l, c = (t.to(dev, non_blocking=True) for t in (h_mono, h_rir, h_len, h_tc))
-        waves = rend.rir_convolve(m, r, l)
-        mix, _, _ = rend.stft_waves(waves)
-        with torch.no_grad():
-            mask = dec(*enc({"mixed_bin_audio_mag": mix, "target_class": c}))
-        h_out.copy_(mask.permute(0, 3, 1, 2), non_blocking=True)
+        pipe(h_mono, h_rir, h_len, h_tc, h_out)
 
     for _ in range(2):
         step_e2e()

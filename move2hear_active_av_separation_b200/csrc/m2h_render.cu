@@ -56,7 +56,8 @@ m2h_rir_conv_kernel(const ConvParams P, const M2hConvTables* __restrict__ tab) {
   conv_cta_body(P, s, tab, blockIdx.x, gridDim.x);
 }
 
-__global__ void __launch_bounds__(M2H_STFT_THREADS, 1)
+// 64 registers / thread (no spills): two 512-thread CTAs per SM, 2 x 86 KB of shared memory
+__global__ void __launch_bounds__(M2H_STFT_THREADS, 2)
 m2h_stft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
@@ -82,6 +83,9 @@ extern "C" int m2h_init(int device) {
   M2H_CUDA_CHECK(cudaMemcpy(d.stft, &hs, sizeof(hs), cudaMemcpyHostToDevice));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
+  // the driver's default carve-out (102 KB, ncu r1b) left room for ONE STFT CTA per SM: ask for the maximum
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaSetDevice(prev));
   d.ready = true;
   return M2H_OK;
