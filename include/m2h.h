@@ -134,12 +134,16 @@ size_t m2h_unet_dec_packed_bytes(int convert_bin2mono);
 int m2h_unet_pack_encoder(const m2h_unet_enc_params* p, int convert_bin2mono, float bn_eps, void* packed, void* stream);
 int m2h_unet_pack_decoder(const m2h_unet_dec_params* p, int convert_bin2mono, float bn_eps, void* packed, void* stream);
 
-/* Activation workspace shared by one encoder/decoder pair (bf16 NHWC feature maps; the skip connections live in
- * the second half of the decoder's concat buffers).  offsets[7] = byte offsets of
- * {x0 [B,32,32,32], cat1 [B,16,16,128], cat2 [B,8,8,256], cat3 [B,4,4,512], cat4 [B,2,2,1024], bottleneck [B,512],
- *  d4 [B,32,32,32]}. */
+/* Activation workspace shared by one encoder/decoder pair: bf16 NHWC feature maps, each stored with a zero border of one
+ * pixel ("haloed": [B, H+2, W+2, C]) so that conv padding and tap shifts need no bounds logic; the skip connections
+ * live in the upper channel half of the decoder's concat buffers.  offsets[7] = byte offsets of
+ * {x0 [B,18,18,128] (network input, space-to-depth: cell (h/2, w/2), channel ((h&1)*2 + (w&1))*32 + c),
+ *  cat1 [B,18,18,128], cat2 [B,10,10,256], cat3 [B,6,6,512], cat4 [B,4,4,1024], bottleneck [B,512], (unused)}. */
 size_t m2h_unet_workspace_bytes(int B);
 int m2h_unet_workspace_layout(int B, size_t offsets[7]);
+/* Zero the borders of the feature maps.  m2h_unet_encoder_forward does this itself; a caller that fills the skip /
+ * bottleneck slots by hand before m2h_unet_decoder_forward calls it once on a fresh workspace. */
+int m2h_unet_workspace_clear_halos(int B, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Encoder.  obs: fp32 [B, 512, 32, 2] log1p magnitudes (observations["mixed_bin_audio_mag"], or `mixed_audio`

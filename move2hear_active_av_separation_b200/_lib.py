@@ -95,6 +95,7 @@ SIGNATURES = {
     "m2h_unet_pack_decoder": (_i, [_vp, _i, ctypes.c_float, _vp, _vp]),
     "m2h_unet_workspace_bytes": (_sz, [_i]),
     "m2h_unet_workspace_layout": (_i, [_i, _vp]),
+    "m2h_unet_workspace_clear_halos": (_i, [_i, _vp, _sz, _vp]),
     "m2h_unet_encoder_forward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp, _vp]),
     "m2h_unet_decoder_forward": (_i, [_vp, _i, _i, _vp, _sz, _vp, _vp]),
 }

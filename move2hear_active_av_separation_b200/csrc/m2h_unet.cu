@@ -2,11 +2,13 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/m2h.h"
 #include "m2h_internal.h"
 #include "unet_gemm.cuh"
+#include "unet_slab.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // static network description (separator_cnn.py:44-50, 128-135)
@@ -29,7 +31,8 @@ struct DecLayout {
 static EncLayout enc_layout() {
   EncLayout L;
   size_t o = 0;
-  for (int i = 0; i < 5; ++i) { L.w[i] = o; o = align256(o + (size_t)kEncCout[i] * kEncTaps[i] * kEncCin[i] * 2); }
+  // layer 0 runs on the slab kernel: 12 weight tiles of [64 co][64 k] (unet_slab.cuh)
+  for (int i = 0; i < 5; ++i) { L.w[i] = o; o = align256(o + (i == 0 ? (size_t)12 * 64 * 64 * 2 : (size_t)kEncCout[i] * kEncTaps[i] * kEncCin[i] * 2)); }
   for (int i = 0; i < 5; ++i) { L.scale[i] = o; o = align256(o + kEncCout[i] * 4); L.bias[i] = o; o = align256(o + kEncCout[i] * 4); }
   L.cls_w = o; o = align256(o + 9 * 64 * 4);
   L.total = o;
@@ -52,7 +55,10 @@ extern "C" size_t m2h_unet_enc_packed_bytes(int) { return enc_layout().total; }
 extern "C" size_t m2h_unet_dec_packed_bytes(int) { return dec_layout().total; }
 
 // workspace (bf16 elements per sample)
-static const size_t kWsElems[7] = {32 * 32 * 32, 16 * 16 * 128, 8 * 8 * 256, 4 * 4 * 512, 2 * 2 * 1024, 512, 32 * 32 * 32};
+// every feature map carries a zero border of one pixel ("haloed" NHWC); x0 is stored space-to-depth (16x16 cells of 2x2 pixels)
+static const int kWsHp[5] = {18, 18, 10, 6, 4};
+static const int kWsLd[5] = {128, 128, 256, 512, 1024};
+static const size_t kWsElems[7] = {18 * 18 * 128, 18 * 18 * 128, 10 * 10 * 256, 6 * 6 * 512, 4 * 4 * 1024, 512, 0};
 extern "C" int m2h_unet_workspace_layout(int B, size_t offsets[7]) {
   if (B < 0 || !offsets) { m2h_set_error("m2h_unet_workspace_layout: bad arguments"); return M2H_ERR_ARG; }
   size_t o = 0;
@@ -142,7 +148,111 @@ __global__ void fold_bn_kernel(const float* __restrict__ g, const float* __restr
   } else { scale[i] = 0.f; bias[i] = 0.f; }
 }
 
-// obs fp32 [B,512,32,2] -> x0 bf16 NHWC [B,32,32,32], channel = ear*16 + slice, row = freq % 32 (separator_cnn.py:84-90);
+// ------------------------------------------------------------------------------------------------
+// slab-kernel weight tiles (unet_slab.cuh): bf16 [rows][64 k], rows in the order the kernel's items consume them
+// ------------------------------------------------------------------------------------------------
+struct SlabPackBlock { int16_t kh, kw, kw2, chunk; };      // one block of Cout rows
+struct SlabPackDesc { int n_blocks, Cout, CoutReal, CinFull; SlabPackBlock blk[64]; };
+// ConvTranspose2d weight [Cin][CoutReal][4][4]: row block = (phase, tap) -> kernel position (kh, kw); k = channel inside the chunk
+__host__ __device__ inline float slab_deconv_w_value(const float* w, const SlabPackDesc& D, size_t i) {
+  const int k = (int)(i & 63);
+  const int row = (int)(i >> 6);
+  const int n = row % D.Cout;
+  const SlabPackBlock b = D.blk[row / D.Cout];
+  const int c = b.chunk * 64 + k;
+  return n < D.CoutReal ? w[(((size_t)c * D.CoutReal + n) * 4 + b.kh) * 4 + b.kw] : 0.f;
+}
+__global__ void pack_slab_deconv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, const SlabPackDesc D) {
+  const size_t total = (size_t)D.n_blocks * D.Cout * 64;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(slab_deconv_w_value(w, D, i));
+}
+// Conv2d weight [Cout][CinFull][4][4], Cin = 32, space-to-depth input: k < 32 -> kernel column kw, k >= 32 -> kw2 (or zero)
+__host__ __device__ inline float slab_conv_w_value(const float* w, const SlabPackDesc& D, size_t i) {
+  const int k = (int)(i & 63);
+  const int row = (int)(i >> 6);
+  const int n = row % D.Cout;
+  const SlabPackBlock b = D.blk[row / D.Cout];
+  const int kw = k < 32 ? b.kw : b.kw2;
+  return kw >= 0 ? w[(((size_t)n * D.CinFull + (k & 31)) * 4 + b.kh) * 4 + kw] : 0.f;
+}
+__global__ void pack_slab_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, const SlabPackDesc D) {
+  const size_t total = (size_t)D.n_blocks * D.Cout * 64;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(slab_conv_w_value(w, D, i));
+}
+
+// Items of a transposed-conv layer: per 64-channel chunk, one weight tile per distinct tap shift (dy, dx); the phases that
+// use the shift are stacked along N.  Fills the kernel's item list and the matching packing descriptor.
+static void build_deconv_items(int Cin, int Cout, int CoutReal, int Wp, USLayer& L, SlabPackDesc& D) {
+  static const int order[9][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {-1, 1}, {1, -1}, {1, 1}};
+  L.n_items = 0; L.n_chunks = Cin / 64; L.n_phase = 4; L.Cout = Cout;
+  D.n_blocks = 0; D.Cout = Cout; D.CoutReal = CoutReal; D.CinFull = 0;
+  bool written[4] = {false, false, false, false};
+  for (int c = 0; c < L.n_chunks; ++c) {
+    for (int s = 0; s < 9; ++s) {
+      const int dy = order[s][0], dx = order[s][1];
+      int ph[4], n_ph = 0;
+      for (int py = 0; py < 2; ++py) {
+        if (!(dy == 0 || dy == (py == 0 ? -1 : 1))) continue;
+        for (int px = 0; px < 2; ++px)
+          if (dx == 0 || dx == (px == 0 ? -1 : 1)) ph[n_ph++] = py * 2 + px;
+      }
+      int p = 0;
+      while (p < n_ph) {               // split into items of <= 128 weight rows and <= 2 runs of consecutive phases
+        USItem& it = L.items[L.n_items++];
+        memset(&it, 0, sizeof(it));
+        it.a_shift = (int16_t)((Wp + 1) + dy * Wp + dx); it.chunk = (int8_t)c; it.a_k16 = 0; it.n_k16 = 4;
+        int rows = 0;
+        while (p < n_ph && rows + Cout <= 128) {
+          const bool extend = it.n_parts > 0 && ph[p] == ph[p - 1] + 1 && written[ph[p]] == written[ph[p - 1]] &&
+                              it.part[it.n_parts - 1].b_row + it.part[it.n_parts - 1].n == rows;
+          if (!extend) {
+            if (it.n_parts == 2) break;
+            USPart& pt = it.part[it.n_parts++];
+            pt.b_row = (int16_t)rows; pt.n = 0; pt.tmem_col = (int16_t)(ph[p] * Cout); pt.init = written[ph[p]] ? 0 : 1;
+          }
+          it.part[it.n_parts - 1].n = (int16_t)(it.part[it.n_parts - 1].n + Cout);
+          SlabPackBlock& b = D.blk[D.n_blocks++];
+          b.kh = (int16_t)deconv_k(ph[p] >> 1, dy == 0 ? 0 : 1); b.kw = (int16_t)deconv_k(ph[p] & 1, dx == 0 ? 0 : 1); b.kw2 = -1; b.chunk = (int16_t)c;
+          rows += Cout;
+          ++p;
+        }
+        it.b_rows = (int16_t)rows;
+        for (int q = 0; q < it.n_parts; ++q)
+          for (int col = it.part[q].tmem_col; col < it.part[q].tmem_col + it.part[q].n; col += Cout) written[col / Cout] = true;
+      }
+    }
+  }
+}
+// Items of encoder layer 0 (Conv2d k4 s2 p1, Cin = 32) on the space-to-depth input: chunk = row parity py,
+// channel inside the chunk = px*32 + c.  Kernel rows kh with that parity: py = 0 -> kh = 1 (dy 0), 3 (dy +1); py = 1 -> kh = 0 (dy -1), 2 (dy 0).
+static void build_conv0_items(int Wp, int CinFull, USLayer& L, SlabPackDesc& D) {
+  L.n_items = 0; L.n_chunks = 2; L.n_phase = 1; L.Cout = 64;
+  D.n_blocks = 0; D.Cout = 64; D.CoutReal = 64; D.CinFull = CinFull;
+  bool first = true;
+  for (int py = 0; py < 2; ++py) {
+    for (int j = 0; j < 2; ++j) {
+      const int kh = py == 0 ? (j == 0 ? 1 : 3) : (j == 0 ? 0 : 2);
+      const int dy = py == 0 ? (j == 0 ? 0 : 1) : (j == 0 ? -1 : 0);
+      // (kw = 1 | kw = 2): dx = 0, both column parities = the whole 64-channel chunk; kw = 0: px = 1, dx = -1; kw = 3: px = 0, dx = +1
+      const int dxs[3] = {0, -1, 1}, ak[3] = {0, 2, 0}, nk[3] = {4, 2, 2}, kw1[3] = {1, 0, 3}, kw2[3] = {2, -1, -1};
+      for (int t = 0; t < 3; ++t) {
+        USItem& it = L.items[L.n_items++];
+        memset(&it, 0, sizeof(it));
+        it.a_shift = (int16_t)((Wp + 1) + dy * Wp + dxs[t]); it.chunk = (int8_t)py; it.a_k16 = (int8_t)ak[t]; it.n_k16 = (int8_t)nk[t];
+        it.n_parts = 1; it.b_rows = 64;
+        it.part[0].b_row = 0; it.part[0].n = 64; it.part[0].tmem_col = 0; it.part[0].init = first ? 1 : 0;
+        first = false;
+        SlabPackBlock& b = D.blk[D.n_blocks++];
+        b.kh = (int16_t)kh; b.kw = (int16_t)kw1[t]; b.kw2 = (int16_t)kw2[t]; b.chunk = (int16_t)py;
+      }
+    }
+  }
+}
+
+// obs fp32 [B,512,32,2] -> x0 bf16, space-to-depth + halo: [B][18][18][128], cell (h/2+1, w/2+1), channel = ((h&1)*2 + (w&1))*32 + ear*16 + slice,
+// where h = freq % 32, slice = freq / 32 (separator_cnn.py:84-90);
 // bin2mono: x = log1p(max(mask * (exp(obs) - 1), 0)) first (separator_cnn.py:73-79)
 struct PackInParams {
   const float* obs; const float* masks; long long ms[4]; __nv_bfloat16* x0; int B;
@@ -165,7 +275,7 @@ __global__ void pack_input_kernel(const PackInParams P) {
     v[s] = __float2bfloat16_rn(l);
     v[16 + s] = __float2bfloat16_rn(r);
   }
-  uint4* dst = reinterpret_cast<uint4*>(P.x0 + (size_t)i * 32);
+  uint4* dst = reinterpret_cast<uint4*>(P.x0 + (((size_t)b * 18 + (h >> 1) + 1) * 18 + (w >> 1) + 1) * 128 + ((h & 1) * 2 + (w & 1)) * 32);
   const uint4* src = reinterpret_cast<const uint4*>(v);
 #pragma unroll
   for (int k = 0; k < 4; ++k) dst[k] = src[k];
@@ -173,14 +283,34 @@ __global__ void pack_input_kernel(const PackInParams P) {
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = __bfloat162float(in[i]);
 }
+// zero the one-pixel border of the five haloed feature maps (the kernels only ever write interiors): one thread per
+// (border position, 16-byte chunk)
+struct HaloParams { __nv_bfloat16* buf[5]; int Hp[5], ld8[5]; long long start[6]; };
+__global__ void clear_halo_kernel(const HaloParams P) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P.start[5]; i += (long long)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (i >= P.start[t + 1]) ++t;
+    const long long j = i - P.start[t];
+    const int hp = P.Hp[t], ld8 = P.ld8[t], hc = 4 * hp - 4;
+    const int ch = (int)(j % ld8);
+    const long long bh = j / ld8;
+    const int h = (int)(bh % hc);
+    const long long b = bh / hc;
+    int y, x;
+    if (h < hp) { y = 0; x = h; }
+    else if (h < 2 * hp) { y = hp - 1; x = h - hp; }
+    else { const int k = h - 2 * hp; y = 1 + (k >> 1); x = (k & 1) ? hp - 1 : 0; }
+    reinterpret_cast<uint4*>(P.buf[t])[((b * hp + y) * hp + x) * ld8 + ch] = make_uint4(0, 0, 0, 0);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
 static bool g_unet_attr_set[M2H_MAX_DEVICES];
-#ifndef M2H_UNFUSED_HEAD
-#define M2H_UNFUSED_HEAD 0      // 1: run the 1x1 head as its own GEMM launch (kept for A/B testing)
-#endif
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
 
 template <int BN>
 static int launch_bn(const UGLayer& L, cudaStream_t st) {
@@ -198,6 +328,7 @@ static int launch_layer(const UGLayer& L, int bn, cudaStream_t st) {
     default: m2h_set_error("unet layer: no kernel for BN=%d", bn); return M2H_ERR_ARG;
   }
 }
+static const int kSlabMaxSmem = 227 * 1024;
 static int unet_prepare_device() {
   int dev;
   int rc = m2h_current_device_checked(&dev);
@@ -206,15 +337,103 @@ static int unet_prepare_device() {
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<32>::kSmemBytes));
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<64>::kSmemBytes));
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<128>::kSmemBytes));
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlabMaxSmem));
     // the default carve-out left room for one CTA per SM (first ncu capture: 100 KB config, 5 warps/SM): ask for the maximum
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_slab_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     g_unet_attr_set[dev] = true;
+  }
+  if (!g_encode_tiled) {
+    // the driver's tensor-map encoder, resolved through the runtime (libcuda is not linked)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    M2H_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { m2h_set_error("cuTensorMapEncodeTiled is not available from this driver"); return M2H_ERR_CUDA; }
+    g_encode_tiled = (EncodeTiledFn)fn;
   }
   return M2H_OK;
 }
 static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+// 2D bf16 tensor map [rows][cols] (cols contiguous, row pitch ld elements), box = [box_rows][64], 128-byte swizzle
+static int make_tmap(CUtensorMap* tm, const void* base, size_t rows, int cols, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { m2h_set_error("cuTensorMapEncodeTiled failed (%d): rows=%zu cols=%d ld=%d box_rows=%d", (int)r, rows, cols, ld, box_rows); return M2H_ERR_CUDA; }
+  return M2H_OK;
+}
+// geometry + tensor maps + launch of one slab layer; items / epilogue fields of L are filled by the caller
+static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, int B, const __nv_bfloat16* w, cudaStream_t st) {
+  L.Hp = L.Wp = Hp; L.PI = Hp * Hp; L.B = B;
+  {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("M2H_SLAB_BASE_OFFSET"); mode = e ? atoi(e) : 0; }
+    L.desc_base_offset = mode;
+  }
+  L.slab_rows = 128 + 2 * (Hp + 1);
+  L.slab_bytes = (L.slab_rows * 128 + 1023) & ~1023;
+  L.tile_cols = L.n_phase * L.Cout;
+  L.tmem_cols = 32;
+  while (L.tmem_cols < 2 * L.tile_cols) L.tmem_cols *= 2;
+  int w_rows = 0;
+  for (int i = 0; i < L.n_items; ++i) { L.items[i].w_row = (int16_t)w_rows; w_rows += L.items[i].b_rows; }
+  L.w_rows = w_rows;
+  L.w_box_rows = L.Cout < 128 ? L.Cout : 128;
+  const size_t positions = (size_t)B * L.PI;
+  L.n_tiles = (int)((positions + 127) / 128);
+  // weights stay resident in shared memory when they fit next to >= 2 tiles' worth of slab chunks, else they stream through a ring
+  const int budget = kSlabMaxSmem - 1024 - 512 - US_AUX_BYTES;
+  if (w_rows * 128 + 2 * L.n_chunks * L.slab_bytes <= budget) {
+    L.n_b_stages = 0;
+    L.n_slab_stages = (budget - w_rows * 128) / L.slab_bytes;
+  } else {
+    L.n_b_stages = 6;
+    L.n_slab_stages = (budget - L.n_b_stages * US_B_STAGE_BYTES) / L.slab_bytes;
+  }
+  if (L.n_slab_stages > US_MAX_STAGES) L.n_slab_stages = US_MAX_STAGES;
+  // flatten items -> parts -> K16 steps into the MMA list the issuing thread walks
+  L.n_mmas = 0;
+  for (int i = 0; i < L.n_items; ++i) {
+    const USItem& it = L.items[i];
+    const bool first_of_chunk = i == 0 || L.items[i - 1].chunk != it.chunk;
+    const bool last_of_chunk = i + 1 == L.n_items || L.items[i + 1].chunk != it.chunk;
+    for (int p = 0; p < it.n_parts; ++p) {
+      for (int k = 0; k < it.n_k16; ++k) {
+        if (L.n_mmas >= US_MAX_MMAS) { m2h_set_error("slab layer: too many MMAs"); return M2H_ERR_ARG; }
+        USMma& m = L.mmas[L.n_mmas++];
+        const bool first = p == 0 && k == 0, last = p + 1 == it.n_parts && k + 1 == it.n_k16;
+        static int dbg_align = -1;      // timing experiment only: round tap shifts down to whole 8-row swizzle atoms (wrong results)
+        if (dbg_align < 0) { const char* e = getenv("M2H_SLAB_DEBUG_ALIGN"); dbg_align = e ? atoi(e) : 0; }
+        m.a_off16 = (uint32_t)((dbg_align ? (it.a_shift & ~7) : it.a_shift) * 128 + (it.a_k16 + k) * 32) >> 4;
+        m.b_off16 = (uint32_t)(((L.n_b_stages ? 0 : it.w_row) + it.part[p].b_row) * 128 + k * 32) >> 4;
+        m.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(it.part[p].n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        m.tmem_col = (uint16_t)it.part[p].tmem_col;
+        m.flags = (uint16_t)(((!it.part[p].init || k) ? US_F_ACC : 0) | (first && first_of_chunk ? US_F_WAIT_SLAB : 0) |
+                             (first && L.n_b_stages ? US_F_WAIT_B : 0) | (last && L.n_b_stages ? US_F_COMMIT_B : 0) |
+                             (last && last_of_chunk ? US_F_COMMIT_SLAB : 0));
+      }
+    }
+  }
+  if (L.n_items > US_MAX_ITEMS || L.slab_rows > 256 || L.n_slab_stages < 2 || L.tmem_cols > 512 || w_rows > 32767) { m2h_set_error("slab layer: unsupported geometry"); return M2H_ERR_ARG; }
+  alignas(64) CUtensorMap tm_in, tm_w;
+  int rc = make_tmap(&tm_in, in, positions, in_ld, in_ld, L.slab_rows);
+  if (rc != M2H_OK) return rc;
+  rc = make_tmap(&tm_w, w, (size_t)w_rows, 64, 64, L.w_box_rows);
+  if (rc != M2H_OK) return rc;
+  int dev = 0, sms = 0;
+  M2H_CUDA_CHECK(cudaGetDevice(&dev));
+  M2H_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = (unsigned)(L.n_tiles < sms ? L.n_tiles : sms);
+  unet_slab_kernel<<<grid, US_THREADS, us::smem_bytes(L.slab_bytes, L.n_slab_stages, L.n_b_stages, w_rows), st>>>(tm_in, tm_w, L);
+  M2H_CUDA_CHECK(cudaGetLastError());
+  return M2H_OK;
+}
 
 extern "C" int m2h_unet_pack_encoder(const m2h_unet_enc_params* p, int convert_bin2mono, float bn_eps, void* packed, void* stream) {
   if (!p || !packed) { m2h_set_error("m2h_unet_pack_encoder: null pointer"); return M2H_ERR_ARG; }
@@ -226,7 +445,13 @@ extern "C" int m2h_unet_pack_encoder(const m2h_unet_enc_params* p, int convert_b
   for (int i = 0; i < 5; ++i) {
     if (!p->conv_w[i] || !p->bn_w[i] || !p->bn_b[i] || !p->bn_mean[i] || !p->bn_var[i]) { m2h_set_error("m2h_unet_pack_encoder: null parameter for layer %d", i); return M2H_ERR_ARG; }
     const int cin_full = i == 0 ? (convert_bin2mono ? 32 : 33) : kEncCin[i];
-    pack_conv_w_kernel<<<256, 256, 0, st>>>(p->conv_w[i], (__nv_bfloat16*)(base + L.w[i]), kEncCout[i], cin_full, kEncCin[i], kEncTaps[i]);
+    if (i == 0) {
+      USLayer sl; SlabPackDesc pd;
+      build_conv0_items(18, cin_full, sl, pd);
+      pack_slab_conv_w_kernel<<<96, 256, 0, st>>>(p->conv_w[0], (__nv_bfloat16*)(base + L.w[0]), pd);
+    } else {
+      pack_conv_w_kernel<<<256, 256, 0, st>>>(p->conv_w[i], (__nv_bfloat16*)(base + L.w[i]), kEncCout[i], cin_full, kEncCin[i], kEncTaps[i]);
+    }
     fold_bn_kernel<<<(kEncCout[i] + 127) / 128, 128, 0, st>>>(p->bn_w[i], p->bn_b[i], p->bn_mean[i], p->bn_var[i], bn_eps,
                                                              (float*)(base + L.scale[i]), (float*)(base + L.bias[i]), kEncCout[i], kEncCout[i]);
   }
@@ -246,8 +471,15 @@ extern "C" int m2h_unet_pack_decoder(const m2h_unet_dec_params* p, int convert_b
   for (int i = 0; i < 5; ++i) {
     if (!p->deconv_w[i] || !p->bn_w[i] || !p->bn_b[i] || !p->bn_mean[i] || !p->bn_var[i]) { m2h_set_error("m2h_unet_pack_decoder: null parameter for layer %d", i); return M2H_ERR_ARG; }
     const int cout_real = i == 4 ? c_last : kDecCoutBase[i];
-    if (i == 0) pack_deconv0_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[0], (__nv_bfloat16*)(base + L.w[0]), 512, 512);
-    else pack_deconv_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[i], (__nv_bfloat16*)(base + L.w[i]), kDecCin[i], cout_real, kDecCoutBase[i]);
+    if (i == 0) {
+      pack_deconv0_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[0], (__nv_bfloat16*)(base + L.w[0]), 512, 512);
+    } else if (i >= 3) {     // slab layers
+      USLayer sl; SlabPackDesc pd;
+      build_deconv_items(kDecCin[i], kDecCoutBase[i], cout_real, i == 3 ? 10 : 18, sl, pd);
+      pack_slab_deconv_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[i], (__nv_bfloat16*)(base + L.w[i]), pd);
+    } else {
+      pack_deconv_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[i], (__nv_bfloat16*)(base + L.w[i]), kDecCin[i], cout_real, kDecCoutBase[i]);
+    }
     fold_bn_kernel<<<(kDecCoutBase[i] + 127) / 128, 128, 0, st>>>(p->bn_w[i], p->bn_b[i], p->bn_mean[i], p->bn_var[i], bn_eps,
                                                                  (float*)(base + L.scale[i]), (float*)(base + L.bias[i]), cout_real, kDecCoutBase[i]);
   }
@@ -258,8 +490,41 @@ extern "C" int m2h_unet_pack_decoder(const m2h_unet_dec_params* p, int convert_b
 
 static void layer_defaults(UGLayer& g) {
   memset(&g, 0, sizeof(g));
-  g.n_phase = 1; g.in_stride = 1; g.out_stride = 1; g.slope = 1.f; g.n_split = 1 << 30; g.n_split_ld = 0;
+  g.n_phase = 1; g.in_stride = 1; g.out_stride = 1; g.slope = 1.f; g.n_split = 1 << 30;
   g.out_mode = UG_OUT_NHWC_BF16;
+}
+
+struct WsPtrs { __nv_bfloat16* x0; __nv_bfloat16* cat[5]; __nv_bfloat16* bott; };
+static WsPtrs ws_ptrs(void* workspace, int B) {
+  size_t off[7];
+  m2h_unet_workspace_layout(B, off);
+  char* ws = (char*)workspace;
+  WsPtrs P;
+  P.x0 = (__nv_bfloat16*)(ws + off[0]);
+  P.cat[0] = nullptr;
+  for (int i = 1; i < 5; ++i) P.cat[i] = (__nv_bfloat16*)(ws + off[i]);
+  P.bott = (__nv_bfloat16*)(ws + off[5]);
+  return P;
+}
+
+extern "C" int m2h_unet_workspace_clear_halos(int B, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0) { m2h_set_error("m2h_unet_workspace_clear_halos: B < 0"); return M2H_ERR_ARG; }
+  if (B == 0) return M2H_OK;
+  if (!workspace) { m2h_set_error("m2h_unet_workspace_clear_halos: null pointer"); return M2H_ERR_ARG; }
+  if (workspace_bytes < m2h_unet_workspace_bytes(B)) { m2h_set_error("m2h_unet_workspace_clear_halos: workspace too small"); return M2H_ERR_WORKSPACE; }
+  int dev;
+  int rc = m2h_current_device_checked(&dev);
+  if (rc != M2H_OK) return rc;
+  const WsPtrs W = ws_ptrs(workspace, B);
+  HaloParams P;
+  P.buf[0] = W.x0;
+  for (int i = 1; i < 5; ++i) P.buf[i] = W.cat[i];
+  P.start[0] = 0;
+  for (int i = 0; i < 5; ++i) { P.Hp[i] = kWsHp[i]; P.ld8[i] = kWsLd[i] / 8; P.start[i + 1] = P.start[i] + (long long)B * (4 * kWsHp[i] - 4) * P.ld8[i]; }
+  const long long blocks = (P.start[5] + 255) / 256;
+  clear_halo_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(P);
+  M2H_CUDA_CHECK(cudaGetLastError());
+  return M2H_OK;
 }
 
 extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2mono, const float* obs,
@@ -273,32 +538,39 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
   int rc = unet_prepare_device();
   if (rc != M2H_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  size_t off[7];
-  m2h_unet_workspace_layout(B, off);
-  char* ws = (char*)workspace;
-  __nv_bfloat16* x0 = (__nv_bfloat16*)(ws + off[0]);
-  __nv_bfloat16* cat[5] = {nullptr, (__nv_bfloat16*)(ws + off[1]), (__nv_bfloat16*)(ws + off[2]), (__nv_bfloat16*)(ws + off[3]), (__nv_bfloat16*)(ws + off[4])};
-  __nv_bfloat16* bott = (__nv_bfloat16*)(ws + off[5]);
+  const WsPtrs W = ws_ptrs(workspace, B);
   const EncLayout PL = enc_layout();
   const char* pk = (const char*)packed_enc;
 
+  rc = m2h_unet_workspace_clear_halos(B, workspace, workspace_bytes, stream);
+  if (rc != M2H_OK) return rc;
   PackInParams pp;
-  pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = x0; pp.B = B;
+  pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.x0; pp.B = B;
   for (int i = 0; i < 4; ++i) pp.ms[i] = convert_bin2mono ? (long long)mask_strides[i] : 0;
   pack_input_kernel<<<(B * 1024 + 255) / 256, 256, 0, st>>>(pp);
   M2H_CUDA_CHECK(cudaGetLastError());
 
-  // inputs / outputs of the five layers; skips are written into the upper channel half of the concat buffers
-  const __nv_bfloat16* in_ptr[5] = {x0, cat[1] + 64, cat[2] + 128, cat[3] + 256, cat[4] + 512};
-  const int in_ld[5] = {32, 128, 256, 512, 1024};
-  __nv_bfloat16* out_ptr[5] = {cat[1] + 64, cat[2] + 128, cat[3] + 256, cat[4] + 512, bott};
-  const int out_ld[5] = {128, 256, 512, 1024, 512};
+  {  // layer 0 on the slab kernel: x0 (space-to-depth, 18x18 cells x 128 ch) -> cat1[..., 64:128]
+    USLayer sl; SlabPackDesc pd;
+    memset(&sl, 0, sizeof(sl));
+    build_conv0_items(18, 0, sl, pd);
+    sl.in_coff = 0;
+    sl.scale = (const float*)(pk + PL.scale[0]); sl.bias = (const float*)(pk + PL.bias[0]); sl.slope = 0.2f;
+    if (!convert_bin2mono) { sl.cls = target_class_plus1; sl.cls_w = (const float*)(pk + PL.cls_w); }
+    sl.out = W.cat[1]; sl.out_mode = UG_OUT_NHWC_BF16; sl.out_stride = 1; sl.Hop = sl.Wop = 18; sl.out_ld = 128; sl.out_coff = 64;
+    rc = launch_slab(sl, W.x0, 128, 18, B, (const __nv_bfloat16*)(pk + PL.w[0]), st);
+    if (rc != M2H_OK) return rc;
+  }
+  // layers 1-4 (implicit-GEMM gather kernel); skips are written into the upper channel half of the concat buffers
+  const __nv_bfloat16* in_ptr[5] = {nullptr, W.cat[1] + 64, W.cat[2] + 128, W.cat[3] + 256, W.cat[4] + 512};
+  const int in_ld[5] = {0, 128, 256, 512, 1024};
+  __nv_bfloat16* out_ptr[5] = {nullptr, W.cat[2] + 128, W.cat[3] + 256, W.cat[4] + 512, W.bott};
+  const int out_ld[5] = {0, 256, 512, 1024, 512};
   const int hin[5] = {32, 16, 8, 4, 2};
-  const int bn[5] = {64, 128, 128, 128, 128};
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 1; i < 5; ++i) {
     UGLayer g;
     layer_defaults(g);
-    g.in = in_ptr[i]; g.Hin = g.Win = hin[i]; g.Cin = kEncCin[i]; g.cin_shift = ilog2(kEncCin[i]); g.in_ld = in_ld[i];
+    g.in = in_ptr[i]; g.Hin = g.Win = hin[i]; g.Cin = kEncCin[i]; g.cin_shift = ilog2(kEncCin[i]); g.in_ld = in_ld[i]; g.in_pad = 1;
     g.Hq = g.Wq = hin[i] / 2; g.M = B * g.Hq * g.Wq; g.in_stride = 2; g.n_taps = kEncTaps[i];
     for (int t = 0; t < kEncTaps[i]; ++t) {
       const int kh = kEncTaps[i] == 16 ? t >> 2 : 1 + (t >> 1), kw = kEncTaps[i] == 16 ? t & 3 : 1 + (t & 1);
@@ -306,13 +578,12 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
     }
     g.w = (const __nv_bfloat16*)(pk + PL.w[i]); g.Cout = kEncCout[i]; g.Kvalid = g.Kpad = kEncTaps[i] * kEncCin[i];
     g.scale = (const float*)(pk + PL.scale[i]); g.bias = (const float*)(pk + PL.bias[i]); g.n_mod = kEncCout[i]; g.slope = 0.2f;
-    if (i == 0 && !convert_bin2mono) { g.cls = target_class_plus1; g.cls_w = (const float*)(pk + PL.cls_w); }
-    g.out = out_ptr[i]; g.Hout = g.Wout = g.Hq; g.out_ld = out_ld[i]; g.n_valid = g.Cout;
-    rc = launch_layer(g, bn[i], st);
+    g.out = out_ptr[i]; g.Hout = g.Wout = g.Hq; g.out_ld = out_ld[i]; g.out_pad = i == 4 ? 0 : 1; g.n_valid = g.Cout;
+    rc = launch_layer(g, 128, st);
     if (rc != M2H_OK) return rc;
   }
   if (bottleneck_f32) {
-    bf16_to_f32_kernel<<<(B * 512 + 255) / 256, 256, 0, st>>>(bott, bottleneck_f32, (size_t)B * 512);
+    bf16_to_f32_kernel<<<(B * 512 + 255) / 256, 256, 0, st>>>(W.bott, bottleneck_f32, (size_t)B * 512);
     M2H_CUDA_CHECK(cudaGetLastError());
   }
   return M2H_OK;
@@ -327,57 +598,53 @@ extern "C" int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2
   int rc = unet_prepare_device();
   if (rc != M2H_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  size_t off[7];
-  m2h_unet_workspace_layout(B, off);
-  char* ws = (char*)workspace;
-  __nv_bfloat16* cat[5] = {nullptr, (__nv_bfloat16*)(ws + off[1]), (__nv_bfloat16*)(ws + off[2]), (__nv_bfloat16*)(ws + off[3]), (__nv_bfloat16*)(ws + off[4])};
-  __nv_bfloat16* bott = (__nv_bfloat16*)(ws + off[5]);
-  __nv_bfloat16* d4 = (__nv_bfloat16*)(ws + off[6]);
+  const WsPtrs W = ws_ptrs(workspace, B);
   const DecLayout PL = dec_layout();
   const char* pk = (const char*)packed_dec;
 
-  {  // layer 0: 1x1 -> 2x2, a plain GEMM [B, 512] x [2048, 512]^T whose column blocks are the 4 output pixels
+  {  // layer 0: 1x1 -> 2x2, a plain GEMM [B, 512] x [2048, 512]^T whose column blocks are the 4 output pixels (cat4 is a haloed 4x4 grid)
     UGLayer g;
     layer_defaults(g);
-    g.in = bott; g.Hin = g.Win = 1; g.Cin = 512; g.cin_shift = 9; g.in_ld = 512;
+    g.in = W.bott; g.Hin = g.Win = 1; g.Cin = 512; g.cin_shift = 9; g.in_ld = 512;
     g.Hq = g.Wq = 1; g.M = B; g.n_taps = 1;
     g.w = (const __nv_bfloat16*)(pk + PL.w[0]); g.Cout = 2048; g.Kvalid = g.Kpad = 512;
     g.scale = (const float*)(pk + PL.scale[0]); g.bias = (const float*)(pk + PL.bias[0]); g.n_mod = 512; g.slope = 0.f;
-    g.out = cat[4]; g.Hout = g.Wout = 1; g.out_ld = 4 * 1024; g.n_split = 512; g.n_split_ld = 1024; g.n_valid = 2048;
+    g.out = W.cat[4]; g.Hout = g.Wout = 1; g.out_ld = 16 * 1024; g.n_split = 512; g.n_valid = 2048;
+    for (int pix = 0; pix < 4; ++pix) g.pix_off[pix] = (((pix >> 1) + 1) * 4 + (pix & 1) + 1) * 1024;
     rc = launch_layer(g, 128, st);
     if (rc != M2H_OK) return rc;
   }
-  const __nv_bfloat16* in_ptr[5] = {nullptr, cat[4], cat[3], cat[2], cat[1]};
-  __nv_bfloat16* out_ptr[5] = {nullptr, cat[3], cat[2], cat[1], d4};
-  const int out_ld[5] = {0, 512, 256, 128, 32};
+  const __nv_bfloat16* in_ptr[5] = {nullptr, W.cat[4], W.cat[3], W.cat[2], W.cat[1]};
+  __nv_bfloat16* out_ptr[5] = {nullptr, W.cat[3], W.cat[2], W.cat[1], nullptr};
+  const int out_ld[5] = {0, 512, 256, 128, 0};
   const int hin[5] = {1, 2, 4, 8, 16};
-  const int bn[5] = {0, 128, 128, 64, 32};
-  for (int i = 1; i < 5; ++i) {
+  for (int i = 1; i < 3; ++i) {   // layers 1, 2: gather kernel, 4 sub-pixel phases
     UGLayer g;
     layer_defaults(g);
-    g.in = in_ptr[i]; g.Hin = g.Win = hin[i]; g.Cin = kDecCin[i]; g.cin_shift = ilog2(kDecCin[i]); g.in_ld = kDecCin[i];
+    g.in = in_ptr[i]; g.Hin = g.Win = hin[i]; g.Cin = kDecCin[i]; g.cin_shift = ilog2(kDecCin[i]); g.in_ld = kDecCin[i]; g.in_pad = 1;
     g.Hq = g.Wq = hin[i]; g.M = B * hin[i] * hin[i]; g.n_taps = 4; g.n_phase = 4;
     for (int ph = 0; ph < 4; ++ph)
       for (int t = 0; t < 4; ++t) { g.dy[ph][t] = (int8_t)deconv_d(ph >> 1, t >> 1); g.dx[ph][t] = (int8_t)deconv_d(ph & 1, t & 1); }
     g.w = (const __nv_bfloat16*)(pk + PL.w[i]); g.Cout = kDecCoutBase[i]; g.Kvalid = g.Kpad = 4 * kDecCin[i];
     g.scale = (const float*)(pk + PL.scale[i]); g.bias = (const float*)(pk + PL.bias[i]); g.n_mod = kDecCoutBase[i]; g.slope = 0.f;
-    g.out = out_ptr[i]; g.Hout = g.Wout = 2 * hin[i]; g.out_stride = 2; g.out_ld = out_ld[i]; g.n_valid = g.Cout;
-    if (i == 4 && !M2H_UNFUSED_HEAD) {   // last up-conv + BN + ReLU + 1x1 head + bias -> fp32 [B, C, 512, 32] in one kernel
-      g.out = mask_out; g.out_mode = UG_OUT_HEAD_NCHW_F32; g.n_valid = convert_bin2mono ? 16 : 32;
-      g.head_w = (const float*)(pk + PL.head_wf); g.head_b = (const float*)(pk + PL.head_b);
-    }
-    rc = launch_layer(g, bn[i], st);
+    g.out = out_ptr[i]; g.Hout = g.Wout = 2 * hin[i]; g.out_stride = 2; g.out_ld = out_ld[i]; g.out_pad = 1; g.n_valid = g.Cout;
+    rc = launch_layer(g, 128, st);
     if (rc != M2H_OK) return rc;
   }
-  if (M2H_UNFUSED_HEAD) {  // 1x1 head + bias -> fp32 NCHW = [B, C, 512, 32] (channel = ear*16 + slice, row = freq % 32)
-    UGLayer g;
-    layer_defaults(g);
-    g.in = d4; g.Hin = g.Win = 32; g.Cin = 32; g.cin_shift = 5; g.in_ld = 32;
-    g.Hq = g.Wq = 32; g.M = B * 1024; g.n_taps = 1;
-    g.w = (const __nv_bfloat16*)(pk + PL.head_w); g.Cout = 32; g.Kvalid = 32; g.Kpad = 64;
-    g.bias = (const float*)(pk + PL.head_b); g.n_mod = 32; g.slope = 1.f;
-    g.out = mask_out; g.out_mode = UG_OUT_NCHW_F32; g.Hout = g.Wout = 32; g.n_valid = convert_bin2mono ? 16 : 32;
-    rc = launch_layer(g, 32, st);
+  for (int i = 3; i < 5; ++i) {   // layers 3, 4: slab kernel; layer 4 carries the 1x1 head and writes fp32 [B, C, 512, 32]
+    USLayer sl; SlabPackDesc pd;
+    memset(&sl, 0, sizeof(sl));
+    const int hp = hin[i] + 2;
+    build_deconv_items(kDecCin[i], kDecCoutBase[i], kDecCoutBase[i], hp, sl, pd);
+    sl.in_coff = 0;
+    sl.scale = (const float*)(pk + PL.scale[i]); sl.bias = (const float*)(pk + PL.bias[i]); sl.slope = 0.f;
+    if (i == 3) {
+      sl.out = out_ptr[3]; sl.out_mode = UG_OUT_NHWC_BF16; sl.out_stride = 2; sl.Hop = sl.Wop = 18; sl.out_ld = out_ld[3]; sl.out_coff = 0;
+    } else {
+      sl.out = mask_out; sl.out_mode = UG_OUT_HEAD_NCHW_F32; sl.n_valid = convert_bin2mono ? 16 : 32;
+      sl.head_w = (const float*)(pk + PL.head_wf); sl.head_b = (const float*)(pk + PL.head_b);
+    }
+    rc = launch_slab(sl, in_ptr[i], kDecCin[i], hp, B, (const __nv_bfloat16*)(pk + PL.w[i]), st);
     if (rc != M2H_OK) return rc;
   }
   return M2H_OK;

@@ -30,9 +30,10 @@
 enum { UG_OUT_NHWC_BF16 = 0, UG_OUT_NCHW_F32 = 1, UG_OUT_HEAD_NCHW_F32 = 2 };
 
 struct UGLayer {
-  // input activation, NHWC bf16: element (b, y, x, c) at in[((b*Hin + y)*Win + x)*in_ld + c]
+  // input activation, NHWC bf16 with a zero border of in_pad pixels:
+  // element (b, y, x, c) at in[((b*(Hin+2p) + y+p)*(Win+2p) + x+p)*in_ld + c]
   const __nv_bfloat16* in;
-  int Hin, Win, Cin, cin_shift, in_ld;
+  int Hin, Win, Cin, cin_shift, in_ld, in_pad;
   // GEMM rows: m = (b*Hq + qy)*Wq + qx ; input pixel = (qy*in_stride + dy[tap], qx*in_stride + dx[tap])
   int M, Hq, Wq, in_stride;
   int n_taps;
@@ -47,9 +48,10 @@ struct UGLayer {
   float slope;             // y = v > 0 ? v : v*slope   (1 = identity, 0 = ReLU, 0.2 = LeakyReLU)
   const float* cls;        // [B] (target_class + 1) or null
   const float* cls_w;      // [3][3][Cout] sums of the class-plane weights over the valid taps, or null
-  // output: pixel (qy*out_stride + py, qx*out_stride + px); column n -> (n / n_split)*n_split_ld + n % n_split
+  // output: pixel (qy*out_stride + py, qx*out_stride + px) of a grid with a border of out_pad pixels;
+  // column n -> pix_off[n / n_split] + n % n_split (the 1x1-input decoder layer spreads column blocks over 4 pixels)
   void* out;
-  int out_mode, Hout, Wout, out_stride, out_ld, n_split, n_split_ld;
+  int out_mode, Hout, Wout, out_stride, out_ld, out_pad, n_split, pix_off[4];
   int n_valid;             // NCHW modes: channels >= n_valid are padding and are not stored; Cout_real = n_valid
   // UG_OUT_HEAD_NCHW_F32 (BN = 32 only): the activated 32-channel pixel goes through the 1x1 head conv in the epilogue
   //   z[n] = head_b[n] + sum_c head_w[n][c] * y[c]   (separator_cnn.py:135) and z is stored as fp32 NCHW
@@ -179,7 +181,8 @@ __global__ void __launch_bounds__(UG_THREADS, ug::Cfg<BN>::kMinBlocks) unet_gemm
     int b = 0, qy = 0, qx = 0;
     if (row_ok) { qx = m % L.Wq; const int t = m / L.Wq; qy = t % L.Hq; b = t / L.Hq; }
     const int by = qy * L.in_stride, bx = qx * L.in_stride;
-    const __nv_bfloat16* in_b = L.in + (size_t)b * L.Hin * L.Win * L.in_ld;
+    const int ip = L.in_pad, Wpi = L.Win + 2 * ip;
+    const __nv_bfloat16* in_b = L.in + ((size_t)b * (L.Hin + 2 * ip) * Wpi + (size_t)ip * Wpi + ip) * L.in_ld;
     const __nv_bfloat16* w_tile = L.w + ((size_t)phase * L.Cout + n0) * L.Kpad;
     const uint32_t a_row = (uint32_t)tid * 128u;
     const uint32_t sw = (uint32_t)(tid & 7);
@@ -192,8 +195,8 @@ __global__ void __launch_bounds__(UG_THREADS, ug::Cfg<BN>::kMinBlocks) unet_gemm
         const int kk = kb * UG_BK;
         const int tap = kk >> L.cin_shift, c = kk & (L.Cin - 1);
         const int iy = by + L.dy[phase][tap & (UG_MAX_TAPS - 1)], ix = bx + L.dx[phase][tap & (UG_MAX_TAPS - 1)];
-        const bool ok = row_ok && kk < L.Kvalid && iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
-        const __nv_bfloat16* src = ok ? in_b + ((size_t)iy * L.Win + ix) * L.in_ld + c : L.in;
+        const bool ok = row_ok && kk < L.Kvalid && (ip || (iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win));
+        const __nv_bfloat16* src = ok ? in_b + ((ptrdiff_t)iy * Wpi + ix) * L.in_ld + c : L.in;
         const uint32_t nb = ok ? 16u : 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) ug::cp_async16(a_st + a_row + (((uint32_t)j ^ sw) << 4), ok ? src + j * 8 : src, nb);
@@ -203,8 +206,8 @@ __global__ void __launch_bounds__(UG_THREADS, ug::Cfg<BN>::kMinBlocks) unet_gemm
           const int kk = kb * UG_BK + h * 32;
           const int tap = kk >> L.cin_shift;
           const int iy = by + L.dy[phase][tap & (UG_MAX_TAPS - 1)], ix = bx + L.dx[phase][tap & (UG_MAX_TAPS - 1)];
-          const bool ok = row_ok && kk < L.Kvalid && iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win;
-          const __nv_bfloat16* src = ok ? in_b + ((size_t)iy * L.Win + ix) * L.in_ld : L.in;
+          const bool ok = row_ok && kk < L.Kvalid && (ip || (iy >= 0 && iy < L.Hin && ix >= 0 && ix < L.Win));
+          const __nv_bfloat16* src = ok ? in_b + ((ptrdiff_t)iy * Wpi + ix) * L.in_ld : L.in;
           const uint32_t nb = ok ? 16u : 0u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) ug::cp_async16(a_st + a_row + (((uint32_t)(h * 4 + j) ^ sw) << 4), ok ? src + j * 8 : src, nb);
@@ -256,9 +259,10 @@ __global__ void __launch_bounds__(UG_THREADS, ug::Cfg<BN>::kMinBlocks) unet_gemm
         y[i] = a > 0.f ? a : a * L.slope;
       }
       const int nn = n0 + cb;
-      const size_t col = (size_t)(nn / L.n_split) * L.n_split_ld + (nn % L.n_split);
+      const size_t col = (size_t)L.pix_off[nn / L.n_split] + (nn % L.n_split);
       if (L.out_mode == UG_OUT_NHWC_BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.out) + (((size_t)b * L.Hout + oy) * L.Wout + ox) * L.out_ld + col;
+        const int op = L.out_pad;
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.out) + (((size_t)b * (L.Hout + 2 * op) + oy + op) * (L.Wout + 2 * op) + ox + op) * L.out_ld + col;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 pk;

@@ -1,0 +1,346 @@
+// "Slab" implicit-GEMM kernel for the high-resolution conv / transposed-conv layers of the passive-separator U-Net.
+//
+// Replaces nn.Conv2d(k4,s2,p1) (first encoder layer) and nn.ConvTranspose2d(k4,s2,p1) (last decoder layers) + BatchNorm2d
+// (inference statistics) + LeakyReLU / ReLU (+ the 1x1 head) of audio_separation/rl/models/separator_cnn.py:5-24, 44-50,
+// 128-135 for the layers whose im2col gather is bound by L2 -> shared-memory traffic (small Cout, many pixels).
+//
+// Activations live in HBM as *haloed* NHWC bf16: [B][H+2][W+2][C] with a zero border, i.e. one flat list of
+// "positions" q = (b*(H+2) + y)*(W+2) + x.  With the zero border, a tap (dy, dx) of a stride-1 window is a plain
+// shift of the position index by dy*(W+2) + dx, so ONE shared-memory copy of the positions [q0-(W+3), q0+128+(W+3))
+// (the slab, fetched by a single TMA box per 64-channel chunk) serves every tap and every sub-pixel phase:
+//   D[phase][m, n] = sum_{tap, c} slab[m + shift(phase, tap), c] * W[phase][n, tap, c]
+// Each tap is a tcgen05.mma whose A descriptor is the slab's base address plus shift*128 B (K-major, 128B-swizzled rows;
+// the swizzle is a function of the absolute shared-memory address - measured: parity holds with the descriptor's
+// base-offset field left 0 - so row-shifted start addresses stay consistent with what TMA wrote).  Phases that share a
+// shift are multiplied in one MMA (N = phases x Cout).  The stride-2 encoder layer uses the space-to-depth form of its
+// input ([B][H/2+2][W/2+2][4*C], channel = (y parity, x parity, c)), where every kernel tap is again a unit shift plus a
+// channel sub-block.  Rows of the 128-position tile that fall on the border are computed and discarded (79 % useful at 16x16).
+//
+// Persistent: one CTA per SM walks the tiles.  Weight tiles are either resident in shared memory (loaded once per CTA)
+// or stream through a TMA ring; slab chunks stream through their own ring, prefetched across tiles; the accumulators
+// are double-buffered in TMEM so that the epilogue of tile i (two groups of 4 warps alternate) overlaps the MMAs of tile i+1.
+// Warp roles: 0-7 epilogue (BatchNorm scale/bias, activation, class-plane term, 1x1 head, stores), 8 MMA issuer,
+// 9 weight loader, 10 slab loader.
+#pragma once
+#include <cuda.h>
+#include "unet_gemm.cuh"
+
+#define US_THREADS 352
+#define US_MAX_ITEMS 40
+#define US_B_STAGE_BYTES 16384        // up to 128 weight rows x 64 k (bf16)
+#define US_MAX_STAGES 8
+#define US_AUX_BYTES 12288            // head weights (4224 B) | scale, bias | class-plane sums | MMA list
+
+struct USPart { int16_t b_row, n, tmem_col, init; };   // init: first MMA writing these accumulator columns
+struct USItem {                       // one weight tile and the MMAs that consume it
+  int16_t a_shift;                    // slab row of output row 0 for this tap: (Wp+1) + dy*Wp + dx
+  int8_t chunk;                       // 64-channel chunk of the slab (items are ordered by chunk)
+  int8_t a_k16, n_k16;                // first 16-channel step inside the chunk, number of steps
+  int8_t n_parts;
+  int16_t b_rows;                     // weight rows of this tile (multiple of box rows)
+  int16_t w_row;                      // first row of the tile in the packed weight tensor
+  USPart part[2];
+};
+
+// One tcgen05.mma, flattened on the host so that the issuing thread only adds bases (a single thread issues every MMA:
+// anything it has to look up or derive per instruction shows up as idle tensor cycles).
+#define US_MAX_MMAS 208
+enum { US_F_ACC = 1, US_F_WAIT_SLAB = 2, US_F_WAIT_B = 4, US_F_COMMIT_B = 8, US_F_COMMIT_SLAB = 16 };
+struct USMma {
+  uint32_t a_off16;                   // (a_shift*128 + k16*32) >> 4, relative to the slab stage
+  uint32_t b_off16;                   // byte offset >> 4 inside the resident weight block / the ring stage
+  uint32_t idesc;                     // instruction descriptor (N of this part)
+  uint16_t tmem_col, flags;
+};
+
+struct USLayer {
+  int n_items, n_chunks, n_tiles, n_mmas;
+  int slab_rows;                      // 128 + 2*(Wp+1)
+  int slab_bytes;                     // slab_rows*128 rounded up to 1024
+  int n_slab_stages, n_b_stages;      // ring depths; n_b_stages == 0: weights resident (w_rows*128 B)
+  int w_rows;
+  int Hp, Wp, PI, B;                  // padded geometry of the input grid, positions per image, batch
+  int in_coff;                        // first input channel inside the position's channel vector
+  int w_box_rows;                     // rows per weight TMA box
+  int tile_cols, tmem_cols;           // accumulator columns per tile (n_phase*Cout), allocation (power of two >= 2*tile_cols)
+  int n_phase, Cout;
+  // epilogue
+  const float* scale; const float* bias; float slope;
+  const float* cls; const float* cls_w;           // class-plane term (encoder layer 0)
+  void* out; int out_mode;                          // UG_OUT_NHWC_BF16 | UG_OUT_HEAD_NCHW_F32
+  int out_stride, Hop, Wop, out_ld, out_coff;       // output pixel (y-1)*out_stride + py + 1 in a haloed [Hop][Wop] grid
+  int n_valid; const float* head_w; const float* head_b;
+  int desc_base_offset;               // debug: 1 = put (start address >> 7) & 7 into the A descriptor's base-offset field
+  USItem items[US_MAX_ITEMS];
+  USMma mmas[US_MAX_MMAS];
+};
+
+namespace us {
+using namespace ug;
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t instr_desc_bf16_n(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// Whole-warp (convergent) variants: every lane holds the same operands, one elected lane issues.  Keeping the issuing
+// warp convergent lets the compiler keep descriptors in uniform registers instead of per-thread registers + R2UR loops.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar) : "memory");
+}
+__host__ __device__ constexpr int smem_bytes(int slab_bytes, int n_slab_stages, int n_b_stages, int w_rows) {
+  return n_slab_stages * slab_bytes + (n_b_stages ? n_b_stages * US_B_STAGE_BYTES : w_rows * 128) + 1024 /*align*/ + 512 /*barriers*/ + US_AUX_BYTES;
+}
+}  // namespace us
+
+__global__ void __launch_bounds__(US_THREADS, 1)
+unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ USLayer L) {
+  extern __shared__ unsigned char us_smem_raw[];
+  const uint32_t raw = ug::smem_u32(us_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* base_ptr = us_smem_raw + (base - raw);
+  const bool resident = L.n_b_stages == 0;
+  const uint32_t w_bytes = resident ? (uint32_t)L.w_rows * 128u : (uint32_t)L.n_b_stages * US_B_STAGE_BYTES;
+  const uint32_t b0 = base;                                   // weights (resident block or ring)
+  const uint32_t slab0 = base + w_bytes;
+  const uint32_t bars = slab0 + (uint32_t)L.n_slab_stages * L.slab_bytes;
+  unsigned char* bars_ptr = base_ptr + w_bytes + (size_t)L.n_slab_stages * L.slab_bytes;
+  auto s_full = [&](int s) { return bars + 8u * s; };
+  auto s_empty = [&](int s) { return bars + 8u * (US_MAX_STAGES + s); };
+  auto b_full = [&](int s) { return bars + 8u * (2 * US_MAX_STAGES + s); };      // slot 0 doubles as "resident weights landed"
+  auto b_empty = [&](int s) { return bars + 8u * (3 * US_MAX_STAGES + s); };
+  auto t_full = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + s); };
+  auto t_empty = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 2 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (4 * US_MAX_STAGES + 4));
+  float* head_smem = reinterpret_cast<float*>(bars_ptr + 512);           // [32][32] weights + [32] bias
+  float* sb_smem = head_smem + 1056;                                      // scale[Cout], bias[Cout]
+  float* cls_smem = sb_smem + 2 * 128;                                    // [9][Cout]
+  uint4* mma_smem = reinterpret_cast<uint4*>(bars_ptr + 512 + 8192);     // copy of L.mmas (constant-bank loads cost ~100+ cycles each)
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role code stays on the uniform datapath
+
+  if (tid == 0) {
+    for (int s = 0; s < US_MAX_STAGES; ++s) {
+      ug::mbar_init(s_full(s), 1); ug::mbar_init(s_empty(s), 1); ug::mbar_init(b_full(s), 1); ug::mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) { ug::mbar_init(t_full(s), 1); ug::mbar_init(t_empty(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (L.out_mode == UG_OUT_HEAD_NCHW_F32)
+    for (int i = tid; i < 32 * 32 + 32; i += US_THREADS) head_smem[i] = i < 1024 ? L.head_w[i] : L.head_b[i - 1024];
+  for (int i = tid; i < L.Cout; i += US_THREADS) { sb_smem[i] = L.scale[i]; sb_smem[128 + i] = L.bias[i]; }
+  if (L.cls != nullptr)
+    for (int i = tid; i < 9 * L.Cout; i += US_THREADS) cls_smem[i] = L.cls_w[i];
+  for (int i = tid; i < L.n_mmas; i += US_THREADS) mma_smem[i] = *reinterpret_cast<const uint4*>(&L.mmas[i]);
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ug::smem_u32(tmem_slot)), "r"((uint32_t)L.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  ug::tc_fence_before();
+  __syncthreads();
+  ug::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int NS = L.n_slab_stages, NB = L.n_b_stages;
+
+  if (warp == 10) {
+    // ------------------------------ slab loader: one TMA box per (tile, 64-channel chunk) ------------------------------
+    if (lane == 0) {
+      int cnt = 0;
+      for (int t = blockIdx.x; t < L.n_tiles; t += gridDim.x) {
+        for (int c = 0; c < L.n_chunks; ++c, ++cnt) {
+          const int s = cnt % NS;
+          if (cnt >= NS) ug::mbar_wait(s_empty(s), (uint32_t)((cnt / NS - 1) & 1));
+          us::mbar_expect_tx(s_full(s), (uint32_t)L.slab_rows * 128u);
+          us::tma_load_2d(slab0 + s * L.slab_bytes, &tm_in, L.in_coff + c * 64, t * 128 - (L.Wp + 1), s_full(s));
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------ weight loader ------------------------------
+    if (lane == 0) {
+      if (resident) {
+        us::mbar_expect_tx(b_full(0), w_bytes);
+        for (int r = 0; r < L.w_rows; r += L.w_box_rows) us::tma_load_2d(b0 + r * 128, &tm_w, 0, r, b_full(0));
+      } else {
+        int cnt = 0;
+        for (int t = blockIdx.x; t < L.n_tiles; t += gridDim.x) {
+          for (int i = 0; i < L.n_items; ++i, ++cnt) {
+            const int s = cnt % NB;
+            if (cnt >= NB) ug::mbar_wait(b_empty(s), (uint32_t)((cnt / NB - 1) & 1));
+            const int rows = L.items[i].b_rows, row = L.items[i].w_row;
+            us::mbar_expect_tx(b_full(s), (uint32_t)rows * 128u);
+            for (int r = 0; r < rows; r += L.w_box_rows)
+              us::tma_load_2d(b0 + s * US_B_STAGE_BYTES + r * 128, &tm_w, 0, row + r, b_full(s));
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------ MMA issuer (convergent warp, one elected lane issues) ------------------------------
+    if (resident) { ug::mbar_wait(b_full(0), 0); ug::tc_fence_after(); }
+    int ss = 0, bs = 0, iter = 0;                 // ring positions of the NEXT slab chunk / weight tile to consume
+    uint32_t s_par = 0, b_par = 0;
+    const uint64_t desc_hi = ug::smem_desc_sw128(0);
+    for (int t = blockIdx.x; t < L.n_tiles; t += gridDim.x, ++iter) {
+      const int buf = iter & 1;
+      if (iter >= 2) { ug::mbar_wait(t_empty(buf), (uint32_t)(((iter >> 1) - 1) & 1)); ug::tc_fence_after(); }
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * L.tile_cols);
+      uint32_t a_lo = 0, b_lo = (b0 >> 4);
+      int cs = 0, cb = 0;                           // stages in use by the current chunk / tile
+      uint4 e1 = mma_smem[0], e2 = mma_smem[1 < L.n_mmas ? 1 : 0];
+#pragma unroll 2
+      for (int j = 0; j < L.n_mmas; ++j) {
+        const uint4 e = e1;                          // entries are fetched two MMAs ahead of their use
+        e1 = e2;
+        e2 = mma_smem[j + 2 < L.n_mmas ? j + 2 : 0];
+        const uint32_t flags = e.w >> 16;
+        if (flags & (US_F_WAIT_SLAB | US_F_WAIT_B)) {
+          if (flags & US_F_WAIT_SLAB) {
+            ug::mbar_wait(s_full(ss), s_par);
+            cs = ss;
+            a_lo = (slab0 + ss * L.slab_bytes) >> 4;
+            if (++ss == NS) { ss = 0; s_par ^= 1u; }
+          }
+          if (flags & US_F_WAIT_B) {
+            ug::mbar_wait(b_full(bs), b_par);
+            cb = bs;
+            b_lo = (b0 + bs * US_B_STAGE_BYTES) >> 4;
+            if (++bs == NB) { bs = 0; b_par ^= 1u; }
+          }
+          ug::tc_fence_after();
+        }
+        us::umma_bf16_elect(tmem_d + (e.w & 0xFFFFu), desc_hi | (uint64_t)((a_lo + e.x) & 0x3FFFu), desc_hi | (uint64_t)((b_lo + e.y) & 0x3FFFu), e.z, flags & US_F_ACC);
+        if (flags & US_F_COMMIT_B) us::umma_commit_elect(b_empty(cb));
+        if (flags & US_F_COMMIT_SLAB) us::umma_commit_elect(s_empty(cs));
+      }
+      us::umma_commit_elect(t_full(buf));
+    }
+  } else {
+    // ------------------------------ epilogue: two groups of 4 warps alternate tiles / TMEM buffers ------------------------------
+    const int grp = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
+    for (int iter = grp;; iter += 2) {
+      const int t = blockIdx.x + iter * gridDim.x;
+      if (t >= L.n_tiles) break;
+      const int q = t * 128 + row;
+      const int b = q / L.PI, r = q - b * L.PI;
+      const int y = r / L.Wp, x = r - y * L.Wp;
+      const bool ok = b < L.B && y >= 1 && y <= L.Hp - 2 && x >= 1 && x <= L.Wp - 2;
+      ug::mbar_wait(t_full(grp), (uint32_t)((iter >> 1) & 1));
+      ug::tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * L.tile_cols);
+      if (L.out_mode == UG_OUT_NHWC_BF16) {
+        float clsv = 0.f;
+        const float* clsw = nullptr;
+        if (L.cls != nullptr && ok) {
+          clsv = L.cls[b];
+          const int cy = y == 1 ? 0 : (y == L.Hp - 2 ? 2 : 1), cx = x == 1 ? 0 : (x == L.Wp - 2 ? 2 : 1);
+          clsw = cls_smem + (cy * 3 + cx) * L.Cout;
+        }
+        for (int ph = 0; ph < L.n_phase; ++ph) {
+          const int oy = (y - 1) * L.out_stride + (ph >> 1) + 1, ox = (x - 1) * L.out_stride + (ph & 1) + 1;
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.out) + (((size_t)b * L.Hop + oy) * L.Wop + ox) * L.out_ld + L.out_coff;
+#pragma unroll 1
+          for (int cb = 0; cb < L.Cout; cb += 32) {
+            uint32_t v[32];
+            ug::tmem_ld32(trow + (uint32_t)(ph * L.Cout + cb), v);
+            if (!ok) continue;
+            float yv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float a = __uint_as_float(v[i]);
+              if (clsw) a = fmaf(clsv, clsw[cb + i], a);
+              a = fmaf(a, sb_smem[cb + i], sb_smem[128 + cb + i]);
+              yv[i] = a > 0.f ? a : a * L.slope;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(yv[i], yv[i + 1]), t1 = __floats2bfloat162_rn(yv[i + 2], yv[i + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(yv[i + 4], yv[i + 5]), t3 = __floats2bfloat162_rn(yv[i + 6], yv[i + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(o + cb + i) = pk;
+            }
+          }
+        }
+        ug::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ug::mbar_arrive(t_empty(grp));
+      } else {
+        // last up-conv (Cout = 32) + BN + ReLU, then the 1x1 head z = head_b + head_w y (separator_cnn.py:135) on the
+        // activated pixel (operands rounded to bf16 like the unfused layer pair); fp32 NCHW store [B][n_valid][Hm][Wm],
+        // the two x-phases of a pixel pair go out as one float2
+        const int Hm = (L.Hp - 2) * 2, Wm = (L.Wp - 2) * 2;
+        float yv[4][32];
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+          uint32_t v[32];
+          ug::tmem_ld32(trow + (uint32_t)(ph * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = fmaf(__uint_as_float(v[i]), sb_smem[i], sb_smem[128 + i]);
+            a = a > 0.f ? a : a * L.slope;
+            yv[ph][i] = __bfloat162float(__float2bfloat16_rn(a));
+          }
+        }
+        ug::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ug::mbar_arrive(t_empty(grp));       // accumulators are in registers: the MMA warp may reuse the buffer
+        if (ok) {
+          float* o = reinterpret_cast<float*>(L.out) + ((size_t)b * L.n_valid * Hm + (size_t)((y - 1) * 2)) * Wm + (x - 1) * 2;
+#pragma unroll 1
+          for (int n4 = 0; n4 < L.n_valid; n4 += 4) {
+            float z[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int ph = 0; ph < 4; ++ph) z[ph][u] = head_smem[1024 + n4 + u];
+#pragma unroll
+            for (int c4 = 0; c4 < 32; c4 += 4) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 w4 = *reinterpret_cast<const float4*>(head_smem + (n4 + u) * 32 + c4);
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph)
+                  z[ph][u] = fmaf(w4.x, yv[ph][c4], fmaf(w4.y, yv[ph][c4 + 1], fmaf(w4.z, yv[ph][c4 + 2], fmaf(w4.w, yv[ph][c4 + 3], z[ph][u]))));
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float* on = o + (size_t)(n4 + u) * Hm * Wm;
+              *reinterpret_cast<float2*>(on) = make_float2(z[0][u], z[1][u]);
+              *reinterpret_cast<float2*>(on + Wm) = make_float2(z[2][u], z[3][u]);
+            }
+          }
+        }
+      }
+    }
+  }
+  ug::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    ug::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L.tmem_cols) : "memory");
+  }
+}

@@ -75,10 +75,20 @@ class _Workspace:
         self.offsets = list(offs)
 
     def view(self, idx: int, shape):
+        """Logical (un-haloed) view of slot ``idx``: ``(B, H, W, C)`` feature map or the ``(B, 512)`` bottleneck."""
         n = 1
-        for s in shape:
+        full = tuple(shape) if len(shape) == 2 else (shape[0], shape[1] + 2, shape[2] + 2, shape[3])
+        for s in full:
             n *= s
-        return self.buf[self.offsets[idx]: self.offsets[idx] + 2 * n].view(torch.bfloat16).view(shape)
+        t = self.buf[self.offsets[idx]: self.offsets[idx] + 2 * n].view(torch.bfloat16).view(full)
+        return t if len(shape) == 2 else t[:, 1:-1, 1:-1, :]
+
+    def clear_halos(self):
+        lib = _lib.load()
+        with torch.cuda.device(self.buf.device):
+            rc = lib.m2h_unet_workspace_clear_halos(self.B, self.buf.data_ptr(), self.nbytes,
+                                                    torch.cuda.current_stream(self.buf.device).cuda_stream)
+        _lib.check(rc, "m2h_unet_workspace_clear_halos")
 
     def skips(self) -> List[torch.Tensor]:
         """NCHW-shaped views (bf16) of the encoder's skip features, deepest first like the reference."""
@@ -243,6 +253,7 @@ class PassiveSepDecCNN(_PackedModule):
         if ws is None or ws.B != B or ws.buf.device != device:
             # features did not come straight from the partner encoder: stage them (layout/dtype copies only)
             ws = _Workspace(B, device)
+            ws.clear_halos()
             ws.view(5, (B, 512)).copy_(bottleneck_feats.reshape(B, 512))
             for idx, feat, (hw, c) in zip((4, 3, 2, 1), lst_skip_feats, ((2, 512), (4, 256), (8, 128), (16, 64))):
                 ws.view(idx, (B, hw, hw, 2 * c))[..., c:].copy_(feat.permute(0, 2, 3, 1))

@@ -114,3 +114,18 @@ def test_emulated_conv_short_signal(emu):
         want = R.convolve_quantise(mono[0], np.ascontiguousarray(h[0].T)) * 32768
         d = waves[0, 0].astype(np.int32) - want.astype(np.int32)
         assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 3e-3 * d.size, (N, L)
+
+
+def test_unet_slab_schedule_host_emulation(tmp_path):
+    """Item tables + weight-tile packing of the slab U-Net kernel, replayed on the CPU against direct (de)convolutions."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "emu_unet_slab")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-w", "-I", os.path.join(root, "include"),
+                           "-o", exe, os.path.join(root, "tests", "emu", "emu_unet_slab.cu")])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
