@@ -160,6 +160,60 @@ int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2mono, const
 int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2mono, int B, void* workspace,
                              size_t workspace_bytes, float* mask_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Passive-separator U-Net, training (batch-statistics BatchNorm) forward + backward, and the pretraining loss.
+ * Replaces the .train()-mode forward/backward of PassiveSepEncCNN / PassiveSepDecCNN
+ * (audio_separation/rl/models/separator_cnn.py:27-170) under PassiveTrainer.train
+ * (audio_separation/pretrain/passive/passive_trainer.py:226-236) and the L1 losses of optimize_supervised_loss (:269-275).
+ * Convolutions, their data gradients (the forward kernels with re-packed weights) and weight gradients run as bf16
+ * tcgen05 GEMMs with fp32 accumulation; BatchNorm statistics are reduced in fp64.  One workspace holds the activations,
+ * the raw conv outputs, the gradients and the packed weights of one encoder/decoder pair between forward and backward.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct m2h_unet_enc_grads {
+  float* conv_w[5];   /* OUT, same layouts as the parameters */
+  float* bn_w[5];
+  float* bn_b[5];
+} m2h_unet_enc_grads;
+typedef struct m2h_unet_dec_grads {
+  float* deconv_w[5];
+  float* bn_w[5];
+  float* bn_b[5];
+  float* head_w;
+  float* head_b;
+} m2h_unet_dec_grads;
+
+size_t m2h_unet_train_workspace_bytes(int B);
+/* offsets[32]: byte offsets of the slots; 0-5 as m2h_unet_workspace_layout (activations), 7 a4 [B,34,34,32], 8 plain input copy,
+ * 9-12 raw conv outputs of the concat levels (overwritten by their gradients in backward), 13 z bottleneck, 14 z4,
+ * 15-18 gradients of the concat buffers [B,H+2,W+2,2C] (lower half: decoder activation, upper half: skip), 19 d bottleneck [B,512],
+ * 20 d a4, 21-24 encoder-side skip gradients, 25+ scratch.  offsets[31] = total bytes. */
+int m2h_unet_train_workspace_layout(int B, size_t offsets[32]);
+/* Zero a fresh workspace once (feature-map borders must be zero; the kernels only write interiors). */
+int m2h_unet_train_workspace_init(int B, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Train-mode forward.  The running_mean / running_var tensors behind p->bn_mean / p->bn_var are UPDATED in place
+ * (momentum, unbiased variance) and num_batches_tracked[i] (int64 device scalars, may be NULL) incremented,
+ * as nn.BatchNorm2d does.  Other arguments as m2h_unet_encoder_forward / m2h_unet_decoder_forward. */
+int m2h_unet_encoder_forward_train(const m2h_unet_enc_params* p, int64_t* const* num_batches_tracked, int convert_bin2mono,
+                                   float bn_eps, float bn_momentum, const float* obs, const float* target_class_plus1,
+                                   const float* masks, const int64_t* mask_strides, int B, void* workspace, size_t workspace_bytes,
+                                   float* bottleneck_f32, void* stream);
+int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int64_t* const* num_batches_tracked, int convert_bin2mono,
+                                   float bn_eps, float bn_momentum, int B, void* workspace, size_t workspace_bytes,
+                                   float* mask_out, void* stream);
+/* Backward of the decoder given dmask = dL/d(mask_out) (fp32 [B, C, 512, 32]): parameter gradients into `grads`,
+ * gradients of the bottleneck / skip features left in the workspace (slots 15-19) for m2h_unet_encoder_backward. */
+int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int convert_bin2mono, const float* dmask, int B, void* workspace,
+                              size_t workspace_bytes, const m2h_unet_dec_grads* grads, void* stream);
+int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int convert_bin2mono, const float* target_class_plus1, int B,
+                              void* workspace, size_t workspace_bytes, const m2h_unet_enc_grads* grads, void* stream);
+
+/* L1 loss of optimize_supervised_loss: use_mix = 1: pred = mask * (exp(obs) - 1) vs gt (binaural, C = 2);
+ * use_mix = 0: pred = mask vs gt (monaural, C = 1).  mask: fp32 [B, C, 512, 32]; obs: fp32 [B, 512, 32, 2]; gt: fp32 [B, 512, 32, C].
+ * loss_sum (device double) = sum |pred - gt|; dmask (may be NULL) = sign(pred - gt) * mix * grad_scale. */
+int m2h_l1_mask_loss(const float* mask, const float* obs, const float* gt, int B, int C, int use_mix, float grad_scale,
+                     double* loss_sum, float* dmask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,7 +82,7 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int t = (int)((i / Cin) % n_taps);
     const int n = (int)(i / ((size_t)Cin * n_taps));
     const int kh = n_taps == 16 ? t >> 2 : 1 + (t >> 1), kw = n_taps == 16 ? t & 3 : 1 + (t & 1);
-    out[i] = __float2bfloat16_rn(w[(((size_t)n * CinFull + c) * 4 + kh) * 4 + kw]);
+    out[i] = __float2bfloat16_rn(c < CinFull ? w[(((size_t)n * CinFull + c) * 4 + kh) * 4 + kw] : 0.f);
   }
 }
 // class plane of encoder layer 0: cls_w[cy][cx][n] = sum over taps that stay inside the image of w[n][32][kh][kw]
@@ -256,6 +256,7 @@ static void build_conv0_items(int Wp, int CinFull, USLayer& L, SlabPackDesc& D) 
 // bin2mono: x = log1p(max(mask * (exp(obs) - 1), 0)) first (separator_cnn.py:73-79)
 struct PackInParams {
   const float* obs; const float* masks; long long ms[4]; __nv_bfloat16* x0; int B;
+  __nv_bfloat16* x0_plain;     // optional second copy, plain haloed NHWC [B][34][34][32] (weight-gradient operand)
 };
 __global__ void pack_input_kernel(const PackInParams P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (b, h, w)
@@ -279,6 +280,11 @@ __global__ void pack_input_kernel(const PackInParams P) {
   const uint4* src = reinterpret_cast<const uint4*>(v);
 #pragma unroll
   for (int k = 0; k < 4; ++k) dst[k] = src[k];
+  if (P.x0_plain) {
+    uint4* d2 = reinterpret_cast<uint4*>(P.x0_plain + (((size_t)b * 34 + h + 1) * 34 + w + 1) * 32);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d2[k] = src[k];
+  }
 }
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = __bfloat162float(in[i]);
@@ -545,7 +551,7 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
   rc = m2h_unet_workspace_clear_halos(B, workspace, workspace_bytes, stream);
   if (rc != M2H_OK) return rc;
   PackInParams pp;
-  pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.x0; pp.B = B;
+  pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.x0; pp.B = B; pp.x0_plain = nullptr;
   for (int i = 0; i < 4; ++i) pp.ms[i] = convert_bin2mono ? (long long)mask_strides[i] : 0;
   pack_input_kernel<<<(B * 1024 + 255) / 256, 256, 0, st>>>(pp);
   M2H_CUDA_CHECK(cudaGetLastError());
@@ -649,3 +655,5 @@ extern "C" int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2
   }
   return M2H_OK;
 }
+
+#include "m2h_unet_train.inl"

@@ -148,7 +148,7 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   }
   if (L.out_mode == UG_OUT_HEAD_NCHW_F32)
     for (int i = tid; i < 32 * 32 + 32; i += US_THREADS) head_smem[i] = i < 1024 ? L.head_w[i] : L.head_b[i - 1024];
-  for (int i = tid; i < L.Cout; i += US_THREADS) { sb_smem[i] = L.scale[i]; sb_smem[128 + i] = L.bias[i]; }
+  for (int i = tid; i < L.Cout; i += US_THREADS) { sb_smem[i] = L.scale ? L.scale[i] : 1.f; sb_smem[128 + i] = L.bias ? L.bias[i] : 0.f; }
   if (L.cls != nullptr)
     for (int i = tid; i < 9 * L.Cout; i += US_THREADS) cls_smem[i] = L.cls_w[i];
   for (int i = tid; i < L.n_mmas; i += US_THREADS) mma_smem[i] = *reinterpret_cast<const uint4*>(&L.mmas[i]);

@@ -1,0 +1,101 @@
+"""Data-parallel gradient exchange for separator pretraining (BASELINE config 3; SURVEY 8e: the path's one collective).
+
+The reference pretrains on one GPU; data-parallel pretraining follows ``DistributedDataParallel`` semantics:
+every rank runs its own shard (per-rank BatchNorm statistics), parameter gradients are averaged across ranks once per
+step, running statistics follow rank 0.  ``GradientAllReducer`` packs the gradients into a few flat fp32 buckets in
+reverse parameter order (decoder first: the order backward produces them) and all-reduces a bucket on a side stream as
+soon as its last gradient has been accumulated, so that the NCCL transfers overlap the remaining backward kernels.
+Works with any ``torch.distributed`` backend (``gloo`` in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+class GradientAllReducer:
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # buckets in reverse registration order (gradients of late layers are ready first)
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._pending = [0] * len(self.buckets)
+        self._flat = [None] * len(self.buckets)
+        self._work = [None] * len(self.buckets)
+        self._stream = None
+        self._hooks = []
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self._reset()
+
+    def _reset(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._work = [None] * len(self.buckets)
+
+    def _launch(self, i: int):
+        bucket = self.buckets[i]
+        flat = torch.cat([p.grad.reshape(-1).float() for p in bucket])
+        self._flat[i] = flat
+        if flat.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(flat.device)
+            self._stream.wait_stream(torch.cuda.current_stream(flat.device))
+            with torch.cuda.stream(self._stream):
+                self._work[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            self._work[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _on_grad(self, p):
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        if self._pending[i] == 0:
+            self._launch(i)
+
+    def finish(self):
+        """Wait for every bucket, write the averaged gradients back.  Call between ``backward()`` and ``optimizer.step()``."""
+        if self.world <= 1:
+            return
+        for i, bucket in enumerate(self.buckets):
+            if self._work[i] is None:          # some gradient of the bucket never arrived (unused parameter): reduce what exists
+                for p in bucket:
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+                self._launch(i)
+            self._work[i].wait()
+            flat = self._flat[i]
+            if flat.is_cuda:
+                torch.cuda.current_stream(flat.device).wait_stream(self._stream)
+            flat.div_(self.world)
+            o = 0
+            for p in bucket:
+                n = p.numel()
+                p.grad.copy_(flat[o:o + n].view_as(p.grad))
+                o += n
+        self._reset()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None):
+    """Parameters and buffers (BatchNorm running statistics) follow rank ``src``, as DDP does at construction / each forward."""
+    if not dist.is_initialized() or dist.get_world_size(group) <= 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)

@@ -7,9 +7,11 @@ same constructor arguments, the same module tree (``cnn.{i}.0`` conv / deconv, `
 signatures and return shapes.  The torch layers only *hold* the parameters - the arithmetic runs in
 ``libm2h_b200.so`` (``csrc/unet_gemm.cuh``) through the C ABI of ``include/m2h.h``.
 
-Only the inference-statistics forward (``.eval()``: the RL rollout / update_sep / evaluation call sites,
-ppo_trainer.py:300-307, 359-364, ppo.py:197-204) is implemented; calling a module in ``.train()`` mode raises - there
-is no silent torch fallback.
+``.eval()`` modules run the inference-statistics forward (RL rollout / update_sep / evaluation call sites,
+ppo_trainer.py:300-307, 359-364, ppo.py:197-204) with BatchNorm folded into the GEMM epilogues.  ``.train()`` modules run
+the batch-statistics forward (running statistics updated in place like ``nn.BatchNorm2d``) and are differentiable through
+``torch.autograd`` (custom Functions whose backward calls the CUDA data-/weight-gradient kernels) - the pretraining
+call sites passive_trainer.py:226-236.  There is no torch fallback in either mode.
 """
 from __future__ import annotations
 
@@ -32,6 +34,15 @@ class _EncParams(ctypes.Structure):
 
 class _DecParams(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p * 5) for n in ("deconv_w", "bn_w", "bn_b", "bn_mean", "bn_var")] + \
+               [("head_w", ctypes.c_void_p), ("head_b", ctypes.c_void_p)]
+
+
+class _EncGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p * 5) for n in ("conv_w", "bn_w", "bn_b")]
+
+
+class _DecGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p * 5) for n in ("deconv_w", "bn_w", "bn_b")] + \
                [("head_w", ctypes.c_void_p), ("head_b", ctypes.c_void_p)]
 
 
@@ -99,6 +110,175 @@ class _Workspace:
         return out
 
 
+class _TrainWorkspace:
+    """Activations, raw conv outputs, gradients and packed weights of one encoder/decoder pair (train mode)."""
+
+    # slot -> (H = W, channels) of the haloed [B, H+2, W+2, C] maps used from Python
+    CAT = {1: (16, 128), 2: (8, 256), 3: (4, 512), 4: (2, 1024)}
+
+    def __init__(self, B: int, device):
+        lib = _lib.load()
+        self.B = B
+        self.nbytes = lib.m2h_unet_train_workspace_bytes(B)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        offs = (ctypes.c_size_t * 32)()
+        _lib.check(lib.m2h_unet_train_workspace_layout(B, offs), "m2h_unet_train_workspace_layout")
+        self.offsets = list(offs)
+        with torch.cuda.device(device):
+            rc = lib.m2h_unet_train_workspace_init(B, self.buf.data_ptr(), self.nbytes, torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "m2h_unet_train_workspace_init")
+
+    def _map(self, slot: int, hw: int, c: int):
+        n = self.B * (hw + 2) * (hw + 2) * c
+        t = self.buf[self.offsets[slot]: self.offsets[slot] + 2 * n].view(torch.bfloat16).view(self.B, hw + 2, hw + 2, c)
+        return t[:, 1:-1, 1:-1, :]
+
+    def _vec(self, slot: int):
+        return self.buf[self.offsets[slot]: self.offsets[slot] + 2 * self.B * 512].view(torch.bfloat16).view(self.B, 512)
+
+    def view(self, idx: int, shape):      # same contract as _Workspace.view (slots 1-5)
+        return self._vec(idx) if len(shape) == 2 else self._map(idx, shape[1], shape[3])
+
+    def skips(self, base: int = 0) -> List[torch.Tensor]:
+        """NCHW views of the skip features (base 0) or of their gradients (base 14: the dcat slots), deepest first."""
+        out = []
+        for lvl in (4, 3, 2, 1):
+            hw, c2 = self.CAT[lvl]
+            out.append(self._map(base + lvl, hw, c2)[..., c2 // 2:].permute(0, 3, 1, 2))
+        return out
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * 5)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class _EncTrainFn(torch.autograd.Function):
+    """Encoder forward with batch statistics; backward = BatchNorm backward + weight gradients + skip data gradients."""
+
+    @staticmethod
+    def forward(ctx, module, obs, cls, masks, *params):
+        lib = _lib.load()
+        device = obs.device
+        B = obs.size(0)
+        ws = module._train_workspace(B, device)
+        p, keep = module._param_struct()
+        nbt = _ptr_array([module.cnn[i][1].num_batches_tracked for i in range(5)])
+        bott = torch.empty((B, 512), dtype=torch.float32, device=device)
+        strides = (ctypes.c_int64 * 4)(*masks.stride()) if masks is not None else None
+        bn = module.cnn[0][1]
+        with torch.cuda.device(device):
+            rc = lib.m2h_unet_encoder_forward_train(
+                ctypes.byref(p), nbt, int(module._convert_bin2mono), float(bn.eps), float(bn.momentum), obs.data_ptr(),
+                cls.data_ptr() if cls is not None else None, masks.data_ptr() if masks is not None else None, strides, B,
+                ws.buf.data_ptr(), ws.nbytes, bott.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "m2h_unet_encoder_forward_train")
+        ctx.module, ctx.ws, ctx.cls, ctx.B, ctx.device = module, ws, cls, B, device
+        skips = ws.skips()
+        bott._m2h_ws = ws
+        return (bott, *skips)
+
+    @staticmethod
+    def backward(ctx, d_bott, *d_skips):
+        lib = _lib.load()
+        module, ws, B, device = ctx.module, ctx.ws, ctx.B, ctx.device
+        # gradients of the outputs must sit in the workspace slots the kernels read (they already do when they come from _DecTrainFn)
+        own = ws.skips(base=14)
+        for g, slot in zip(d_skips, own):
+            if g is None:
+                slot.zero_()
+            elif g.data_ptr() != slot.data_ptr() or g.stride() != slot.stride():
+                slot.copy_(g)
+        dbott = ws._vec(19)
+        if d_bott is None:
+            dbott.zero_()
+        else:
+            dbott.copy_(d_bott)
+        p, keep = module._param_struct()
+        grads, gstruct = module._grad_struct(device)
+        with torch.cuda.device(device):
+            rc = lib.m2h_unet_encoder_backward(ctypes.byref(p), int(module._convert_bin2mono),
+                                               ctx.cls.data_ptr() if ctx.cls is not None else None, B, ws.buf.data_ptr(), ws.nbytes,
+                                               ctypes.byref(gstruct), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "m2h_unet_encoder_backward")
+        return (None, None, None, None, *[g if q.requires_grad else None for g, q in zip(grads, module._train_params())])
+
+
+class _DecTrainFn(torch.autograd.Function):
+    """Decoder forward with batch statistics (-> fp32 [B, C, 512, 32]); backward leaves d(bottleneck) / d(skips) in the workspace."""
+
+    @staticmethod
+    def forward(ctx, module, ws, bott, s0, s1, s2, s3, *params):
+        lib = _lib.load()
+        device = bott.device
+        B = bott.size(0)
+        p, keep = module._param_struct()
+        nbt = _ptr_array([module.cnn[i][1].num_batches_tracked for i in range(5)])
+        C = module._n_out_audio // SLICE_FACTOR
+        out = torch.empty((B, C, 512, 32), dtype=torch.float32, device=device)
+        bn = module.cnn[0][1]
+        with torch.cuda.device(device):
+            rc = lib.m2h_unet_decoder_forward_train(ctypes.byref(p), nbt, int(module._convert_bin2mono), float(bn.eps), float(bn.momentum),
+                                                    B, ws.buf.data_ptr(), ws.nbytes, out.data_ptr(),
+                                                    torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "m2h_unet_decoder_forward_train")
+        ctx.module, ctx.ws, ctx.B, ctx.device = module, ws, B, device
+        return out
+
+    @staticmethod
+    def backward(ctx, dmask):
+        lib = _lib.load()
+        module, ws, B, device = ctx.module, ctx.ws, ctx.B, ctx.device
+        dmask = _f32(dmask)
+        p, keep = module._param_struct()
+        grads, gstruct = module._grad_struct(device)
+        with torch.cuda.device(device):
+            rc = lib.m2h_unet_decoder_backward(ctypes.byref(p), int(module._convert_bin2mono), dmask.data_ptr(), B, ws.buf.data_ptr(),
+                                               ws.nbytes, ctypes.byref(gstruct), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "m2h_unet_decoder_backward")
+        d_bott = ws._vec(19).float()
+        d_skips = ws.skips(base=14)
+        return (None, None, d_bott, *d_skips, *[g if q.requires_grad else None for g, q in zip(grads, module._train_params())])
+
+
+class _L1MaskLossFn(torch.autograd.Function):
+    """``F.l1_loss(mask * (exp(obs) - 1), gt)`` (use_mix) or ``F.l1_loss(mask, gt)`` in one kernel (passive_trainer.py:269-275)."""
+
+    @staticmethod
+    def forward(ctx, mask, obs, gt, use_mix):
+        lib = _lib.load()
+        device = mask.device
+        B, C = mask.size(0), mask.size(3)
+        nchw = mask.permute(0, 3, 1, 2)
+        if not nchw.is_contiguous() or nchw.dtype != torch.float32:
+            nchw = nchw.float().contiguous()
+        gt = _f32(gt)
+        obs_c = _f32(obs) if use_mix else None
+        numel = B * C * 512 * 32
+        loss_sum = torch.empty((), dtype=torch.float64, device=device)
+        dmask = torch.empty((B, C, 512, 32), dtype=torch.float32, device=device) if mask.requires_grad else None
+        with torch.cuda.device(device):
+            rc = lib.m2h_l1_mask_loss(nchw.data_ptr(), obs_c.data_ptr() if use_mix else None, gt.data_ptr(), B, C, int(use_mix),
+                                      1.0 / numel, loss_sum.data_ptr(), dmask.data_ptr() if dmask is not None else None,
+                                      torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "m2h_l1_mask_loss")
+        ctx.dmask = dmask
+        return (loss_sum / numel).float()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (ctx.dmask * grad_out).permute(0, 2, 3, 1), None, None, None
+
+
+def l1_mask_loss(pred_masks: torch.Tensor, gt: torch.Tensor, mixed_audio: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Mean-reduced L1 loss on CUDA: ``|pred_masks * (exp(mixed_audio) - 1) - gt|`` when ``mixed_audio`` is given, else ``|pred_masks - gt|``."""
+    if not pred_masks.is_cuda:
+        raise _lib.M2HError("l1_mask_loss needs CUDA tensors (there is no CPU path)")
+    return _L1MaskLossFn.apply(pred_masks, mixed_audio, gt, mixed_audio is not None)
+
+
 class _PackedModule(nn.Module):
     """Common parameter-packing cache: re-pack when any parameter/buffer changed (load_state_dict, optimiser step)."""
 
@@ -108,12 +288,29 @@ class _PackedModule(nn.Module):
             sig.append((t.data_ptr(), t._version, t.device.index, t.dtype))
         return tuple(sig)
 
-    def _require_cuda_eval(self, device):
+    def _require_cuda(self, device):
         if device.type != "cuda":
             raise _lib.M2HError("the B200 U-Net has no CPU path: move the module and its inputs to a CUDA device")
-        if self.training:
-            raise _lib.M2HError("train-mode (batch-statistics) forward/backward is not implemented by the CUDA path; "
-                                "call .eval() (RL rollout / update_sep / evaluation call sites)")
+
+    # ---- train mode -----------------------------------------------------------------------------------------------
+    def _train_workspace(self, B, device):
+        ws = getattr(self, "_tws", None)
+        if ws is None or ws.B != B or ws.buf.device != device:
+            ws = _TrainWorkspace(B, device)
+            self._tws = ws
+        return ws
+
+    def _train_params(self):
+        """Parameters in the order the autograd Functions return their gradients: conv weights, BN weights, BN biases (+ head)."""
+        ps = [self.cnn[i][0].weight for i in range(5)] + [self.cnn[i][1].weight for i in range(5)] + [self.cnn[i][1].bias for i in range(5)]
+        if len(self.cnn) > 5:
+            ps += [self.cnn[5][0].weight, self.cnn[5][0].bias]
+        return ps
+
+    def _check_train_dtypes(self):
+        for t in list(self.parameters()) + [b for b in self.buffers() if b.dtype.is_floating_point]:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise _lib.M2HError("train mode needs contiguous fp32 parameters / buffers (running statistics are updated in place)")
 
 
 class PassiveSepEncCNN(_PackedModule):
@@ -158,6 +355,36 @@ class PassiveSepEncCNN(_PackedModule):
         self._packed, self._packed_sig = packed, sig
         return packed
 
+    def _param_struct(self):
+        keep, p = [], _EncParams()
+        for i in range(5):
+            conv, bn = self.cnn[i][0], self.cnn[i][1]
+            for name, t in (("conv_w", conv.weight), ("bn_w", bn.weight), ("bn_b", bn.bias),
+                            ("bn_mean", bn.running_mean), ("bn_var", bn.running_var)):
+                keep.append(t)
+                getattr(p, name)[i] = t.data_ptr()
+        return p, keep
+
+    def _grad_struct(self, device):
+        grads = [torch.empty_like(q, memory_format=torch.contiguous_format) for q in self._train_params()]
+        g = _EncGrads()
+        for i in range(5):
+            g.conv_w[i], g.bn_w[i], g.bn_b[i] = grads[i].data_ptr(), grads[5 + i].data_ptr(), grads[10 + i].data_ptr()
+        return grads, g
+
+    def _forward_train(self, obs, observations, masks, B, device):
+        self._check_train_dtypes()
+        cls = None
+        if self._convert_bin2mono:
+            masks = masks.detach()                     # the converter consumes detached masks (passive_trainer.py:229-230)
+            if masks.dtype != torch.float32:
+                masks = masks.float()
+        else:
+            cls = (observations["target_class"].detach().reshape(B).float() + 1).contiguous()
+        outs = _EncTrainFn.apply(self, obs, cls, masks, *self._train_params())
+        outs[0]._m2h_ws = self._tws                    # lets the partner decoder find the activations (and leave its gradients) in place
+        return outs[0], list(outs[1:])
+
     def forward(self, observations, mixed_audio=None):
         lib = _lib.load()
         if self._convert_bin2mono:
@@ -168,11 +395,13 @@ class PassiveSepEncCNN(_PackedModule):
             obs = observations["mixed_bin_audio_mag"]
             masks = None
         device = obs.device
-        self._require_cuda_eval(device)
+        self._require_cuda(device)
         obs = _f32(obs)
         B = obs.size(0)
         if tuple(obs.shape[1:]) != (512, 32, 2):
             raise _lib.M2HError(f"expected a [B,512,32,2] spectrogram, got {tuple(obs.shape)}")
+        if self.training:
+            return self._forward_train(obs, observations, masks, B, device)
         packed = self._pack(device)
         ws = _Workspace(B, device)
         bott = torch.empty((B, 512), dtype=torch.float32, device=device)
@@ -244,12 +473,47 @@ class PassiveSepDecCNN(_PackedModule):
         self._packed, self._packed_sig = packed, sig
         return packed
 
+    def _param_struct(self):
+        keep, p = [], _DecParams()
+        for i in range(5):
+            conv, bn = self.cnn[i][0], self.cnn[i][1]
+            for name, t in (("deconv_w", conv.weight), ("bn_w", bn.weight), ("bn_b", bn.bias),
+                            ("bn_mean", bn.running_mean), ("bn_var", bn.running_var)):
+                keep.append(t)
+                getattr(p, name)[i] = t.data_ptr()
+        p.head_w, p.head_b = self.cnn[5][0].weight.data_ptr(), self.cnn[5][0].bias.data_ptr()
+        return p, keep
+
+    def _grad_struct(self, device):
+        grads = [torch.empty_like(q, memory_format=torch.contiguous_format) for q in self._train_params()]
+        g = _DecGrads()
+        for i in range(5):
+            g.deconv_w[i], g.bn_w[i], g.bn_b[i] = grads[i].data_ptr(), grads[5 + i].data_ptr(), grads[10 + i].data_ptr()
+        g.head_w, g.head_b = grads[15].data_ptr(), grads[16].data_ptr()
+        return grads, g
+
+    def _forward_train(self, bottleneck_feats, lst_skip_feats, B, device):
+        self._check_train_dtypes()
+        ws = getattr(bottleneck_feats, "_m2h_ws", None)
+        if not isinstance(ws, _TrainWorkspace) or ws.B != B or ws.buf.device != device:
+            # features did not come straight from the partner encoder in train mode: stage them into a fresh training workspace
+            ws = self._train_workspace(B, device)
+            ws.view(5, (B, 512)).copy_(bottleneck_feats.detach().reshape(B, 512))
+            for idx, feat, (hw, c) in zip((4, 3, 2, 1), lst_skip_feats, ((2, 512), (4, 256), (8, 128), (16, 64))):
+                ws.view(idx, (B, hw, hw, 2 * c))[..., c:].copy_(feat.detach().permute(0, 2, 3, 1))
+        out = _DecTrainFn.apply(self, ws, bottleneck_feats, *lst_skip_feats, *self._train_params())
+        return out.permute(0, 2, 3, 1)
+
     def forward(self, bottleneck_feats, lst_skip_feats):
         lib = _lib.load()
         device = bottleneck_feats.device
-        self._require_cuda_eval(device)
+        self._require_cuda(device)
         B = bottleneck_feats.size(0)
+        if self.training:
+            return self._forward_train(bottleneck_feats, lst_skip_feats, B, device)
         ws: Optional[_Workspace] = getattr(bottleneck_feats, "_m2h_ws", None)
+        if isinstance(ws, _TrainWorkspace):
+            ws = None
         if ws is None or ws.B != B or ws.buf.device != device:
             # features did not come straight from the partner encoder: stage them (layout/dtype copies only)
             ws = _Workspace(B, device)

@@ -77,6 +77,16 @@ def _bn(sd, prefix, c, g, randomize):
     sd[prefix + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
 
 
+def _r(x, emulate_bf16):
+    """Round to bf16 in the forward pass only (straight-through gradient).  With ``emulate_bf16`` the oracle rounds its GEMM
+    operands and stored activations where the CUDA path does (fp32 accumulation kept), so that activation gates and
+    BatchNorm statistics see the same values and a gradient comparison measures the backward arithmetic, not the
+    ReLU-gate flips that any reduced-precision forward causes."""
+    if not emulate_bf16:
+        return x
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+
 def _batchnorm(x, sd, prefix, training):
     return F.batch_norm(x, None if training else sd[prefix + ".running_mean"],
                         None if training else sd[prefix + ".running_var"],
@@ -101,38 +111,45 @@ def encoder_input(mixed_bin_audio_mag, target_class=None, convert_bin2mono=False
 
 
 def encoder_forward(enc_sd, mixed_bin_audio_mag, target_class=None, convert_bin2mono=False,
-                    mixed_audio=None, training=False):
+                    mixed_audio=None, training=False, emulate_bf16=False):
     """-> ``(bottleneck [B,512], [skip 512@2x2, 256@4x4, 128@8x8, 64@16x16])``."""
     out = encoder_input(mixed_bin_audio_mag, target_class, convert_bin2mono, mixed_audio)
+    if emulate_bf16:            # the class plane stays fp32 on the CUDA path (an epilogue term), the audio channels are bf16
+        out = torch.cat((_r(out[:, :32], True), out[:, 32:]), dim=1)
     feats = []
     for i in range(5):
-        out = F.conv2d(out, enc_sd[f"cnn.{i}.0.weight"], None, stride=2, padding=1)
+        w = enc_sd[f"cnn.{i}.0.weight"]
+        if emulate_bf16 and i == 0 and w.size(1) == 33:
+            w = torch.cat((_r(w[:, :32], True), w[:, 32:]), dim=1)
+        else:
+            w = _r(w, emulate_bf16)
+        out = _r(F.conv2d(out, w, None, stride=2, padding=1), emulate_bf16)
         out = _batchnorm(out, enc_sd, f"cnn.{i}.1", training)
-        out = F.leaky_relu(out, 0.2)
+        out = _r(F.leaky_relu(out, 0.2), emulate_bf16)
         feats.append(out)
     return out.reshape(out.size(0), -1), feats[:-1][::-1]
 
 
-def decoder_forward(dec_sd, bottleneck, skips, training=False):
+def decoder_forward(dec_sd, bottleneck, skips, training=False, emulate_bf16=False):
     """-> mask ``[B, 512, T, C]`` (C = 2 binaural / 1 bin2mono); no sigmoid."""
     out = bottleneck.reshape(bottleneck.size(0), -1, 1, 1)
     for i in range(5):
         if i > 0:
             out = torch.cat((out, skips[i - 1]), dim=1)
-        out = F.conv_transpose2d(out, dec_sd[f"cnn.{i}.0.weight"], None, stride=2, padding=1)
+        out = _r(F.conv_transpose2d(out, _r(dec_sd[f"cnn.{i}.0.weight"], emulate_bf16), None, stride=2, padding=1), emulate_bf16)
         out = _batchnorm(out, dec_sd, f"cnn.{i}.1", training)
-        out = F.relu(out)
-    out = F.conv2d(out, dec_sd["cnn.5.0.weight"], dec_sd["cnn.5.0.bias"])
+        out = _r(F.relu(out), emulate_bf16)
+    out = F.conv2d(out, _r(dec_sd["cnn.5.0.weight"], emulate_bf16), dec_sd["cnn.5.0.bias"])
     out = out.reshape(out.size(0), -1, SLICE_FACTOR, out.size(2), out.size(3))
     out = out.reshape(out.size(0), out.size(1), -1, out.size(4))
     return out.permute(0, 2, 3, 1)
 
 
 def separator_forward(enc_sd, dec_sd, mixed_bin_audio_mag, target_class=None, convert_bin2mono=False,
-                      mixed_audio=None, training=False):
+                      mixed_audio=None, training=False, emulate_bf16=False):
     """``Policy.get_binSepMasks`` / ``convert_bin2mono`` (pretrain/passive/policy.py:61-71)."""
-    b, s = encoder_forward(enc_sd, mixed_bin_audio_mag, target_class, convert_bin2mono, mixed_audio, training)
-    return decoder_forward(dec_sd, b, s, training)
+    b, s = encoder_forward(enc_sd, mixed_bin_audio_mag, target_class, convert_bin2mono, mixed_audio, training, emulate_bf16)
+    return decoder_forward(dec_sd, b, s, training, emulate_bf16)
 
 
 def supervised_losses(mixed_audio, pred_bin_masks, gt_bin_mag, pred_mono=None, gt_mono_mag=None):

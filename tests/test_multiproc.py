@@ -58,3 +58,48 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+GRAD_WORKER = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, %r)
+    import torch, torch.distributed as dist
+    from move2hear_active_av_separation_b200.distributed import GradientAllReducer, broadcast_module_state
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    torch.manual_seed(100 + rank)                       # ranks start from different weights ...
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.BatchNorm1d(16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    broadcast_module_state(net)                         # ... and follow rank 0 afterwards
+    red = GradientAllReducer(net.parameters(), bucket_bytes=256)      # tiny buckets: several per step
+    g = torch.Generator().manual_seed(7)
+    x_all, y_all = torch.randn(12, 8, generator=g), torch.randn(12, 4, generator=g)
+    x, y = x_all[rank * 6:(rank + 1) * 6], y_all[rank * 6:(rank + 1) * 6]
+    loss = torch.nn.functional.mse_loss(net(x), y)
+    loss.backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    red.finish()
+    # expected: mean over ranks of the local gradients
+    ok = True
+    for p, l in zip(net.parameters(), local):
+        gathered = [torch.zeros_like(l) for _ in range(world)]
+        dist.all_gather(gathered, l)
+        ok = ok and torch.allclose(p.grad, sum(gathered) / world, atol=1e-6)
+    w0 = [torch.zeros_like(net[0].weight) for _ in range(world)]
+    dist.all_gather(w0, net[0].weight.data)
+    same_init = bool(torch.equal(w0[0], w0[1]))
+    if rank == 0:
+        print(json.dumps({"ok": bool(ok), "same_init": same_init, "n_buckets": len(red.buckets)}))
+    dist.destroy_process_group()
+""") % ROOT
+
+
+def test_two_rank_gloo_gradient_allreduce(tmp_path):
+    script = tmp_path / "grad_worker.py"
+    script.write_text(GRAD_WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["ok"] and d["same_init"] and d["n_buckets"] > 1

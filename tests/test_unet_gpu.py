@@ -131,8 +131,9 @@ def test_no_fallbacks():
     from move2hear_active_av_separation_b200 import M2HError
     from move2hear_active_av_separation_b200.separator_cnn import PassiveSepEncCNN
     obs, tc = unet_case_inputs(1, seed=2)
-    enc = PassiveSepEncCNN().cuda()
-    with pytest.raises(M2HError):
-        enc.train()({"mixed_bin_audio_mag": obs.cuda(), "target_class": tc.cuda()})
-    with pytest.raises(M2HError):
+    with pytest.raises(M2HError):           # CPU module / CPU tensors: no silent torch path in either mode
         PassiveSepEncCNN().eval()({"mixed_bin_audio_mag": obs, "target_class": tc})
+    with pytest.raises(M2HError):
+        PassiveSepEncCNN().train()({"mixed_bin_audio_mag": obs, "target_class": tc})
+    with pytest.raises(M2HError):           # train mode updates fp32 running statistics in place: half-precision modules are refused
+        PassiveSepEncCNN().cuda().half().train()({"mixed_bin_audio_mag": obs.cuda(), "target_class": tc.cuda()})

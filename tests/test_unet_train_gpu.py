@@ -1,0 +1,283 @@
+"""GPU parity of the training path: train-mode forward, losses and every parameter gradient against torch autograd on the
+CPU oracle (fp32), plus the reference module's own train-mode golden outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet as U
+from oracle.gen_golden import unet_case_inputs
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD = 3e-2      # bf16 operands + bf16 activations through batch-statistics BatchNorm (2e-2 eval; train adds the stats)
+TOL_GRAD = 5e-2     # gradients rel-L2 <= 5e-2 (bf16)
+TOL_LOSS = 1e-2
+
+
+def build(bin2mono, seed, train=True):
+    from move2hear_active_av_separation_b200.separator_cnn import PassiveSepDecCNN, PassiveSepEncCNN
+    enc_sd, dec_sd = U.init_state(bin2mono, seed=seed)
+    enc, dec = PassiveSepEncCNN(bin2mono).cuda().train(train), PassiveSepDecCNN(bin2mono).cuda().train(train)
+    enc.load_state_dict(enc_sd)
+    dec.load_state_dict(dec_sd)
+    return enc, dec, enc_sd, dec_sd
+
+
+@pytest.mark.parametrize("bin2mono", [False, True])
+def test_train_forward_matches_reference_golden(bin2mono, golden_dir):
+    g = np.load(os.path.join(golden_dir, "unet_bin2mono.npz" if bin2mono else "unet_binsep.npz"))
+    enc, dec, enc_sd, _ = build(bin2mono, 3 + int(bin2mono))
+    obs, tc = unet_case_inputs(3, seed=5)
+    with torch.no_grad():          # the reference's validation splits: train-mode modules under no_grad
+        if bin2mono:
+            bott, skips = enc(torch.from_numpy(g["in_masks"]).cuda(), mixed_audio=obs.cuda())
+        else:
+            bott, skips = enc({"mixed_bin_audio_mag": obs.cuda(), "target_class": tc.cuda()})
+        mask = dec(bott, skips)
+    assert rel_l2(skips[3].float().cpu().numpy(), g["train_skip3"].astype(np.float32)) < TOL_FWD
+    assert tuple(mask.shape) == g["train_mask"].shape and list(mask.stride()) == list(g["train_mask_strides"])
+    # B = 3: the 1x1 bottleneck is normalised over three samples - bf16 rounding is amplified there, the mask stays well-conditioned
+    assert rel_l2(mask.cpu().numpy(), g["train_mask"]) < 2 * TOL_FWD
+    # running statistics follow nn.BatchNorm2d (momentum 0.1, unbiased variance), num_batches_tracked counts
+    assert rel_l2(enc.cnn[0][1].running_mean.cpu().numpy(), g["train_enc0_running_mean"]) < 1e-2
+    assert rel_l2(dec.cnn[4][1].running_var.cpu().numpy(), g["train_dec4_running_var"]) < 1e-2
+    assert int(enc.cnn[2][1].num_batches_tracked) == 1 and int(dec.cnn[4][1].num_batches_tracked) == 1
+
+
+def _policy(enc_sd, dec_sd, enc2_sd, dec2_sd):
+    from move2hear_active_av_separation_b200.policy import Move2HearPassiveWoMemoryPolicy
+    pol = Move2HearPassiveWoMemoryPolicy().cuda().train()
+    pol.binSep_enc.passive_sep_encoder.load_state_dict(enc_sd)
+    pol.binSep_dec.passive_sep_decoder.load_state_dict(dec_sd)
+    pol.bin2mono_enc.passive_sep_encoder.load_state_dict(enc2_sd)
+    pol.bin2mono_dec.passive_sep_decoder.load_state_dict(dec2_sd)
+    return pol
+
+
+def _grad_errors(pol, sds):
+    mods = (pol.binSep_enc.passive_sep_encoder, pol.binSep_dec.passive_sep_decoder,
+            pol.bin2mono_enc.passive_sep_encoder, pol.bin2mono_dec.passive_sep_decoder)
+    errs = {}
+    for mod, sd, tag in zip(mods, sds, ("enc", "dec", "enc2", "dec2")):
+        for name, p in mod.named_parameters():
+            want = sd[name].grad
+            assert p.grad is not None and want is not None, (tag, name)
+            assert p.grad.shape == want.shape and p.grad.dtype == torch.float32
+            errs[f"{tag}.{name}"] = rel_l2(p.grad.cpu().numpy(), want.numpy())
+    return errs
+
+
+def _leaf_sds(*sds_in):
+    out = []
+    for sd in sds_in:
+        d = {}
+        for k, v in sd.items():
+            d[k] = v.clone().requires_grad_(True) if (v.dtype.is_floating_point and "running" not in k) else v.clone()
+        out.append(d)
+    return out
+
+
+def _ws_map(ws, slot, hw, c):
+    """fp32 NCHW CPU copy of a haloed bf16 feature map of the training workspace."""
+    return ws._map(slot, hw, c).float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def test_backward_kernels_layer_by_layer():
+    """Every backward kernel against torch autograd, one layer at a time, on the CUDA path's OWN stored activations and
+    upstream gradients (read back from the training workspace): for each conv / deconv block the oracle recomputes
+    z = conv(a_in, bf16(W)), BatchNorm (batch statistics), the activation, and back-propagates the stored d(a_out); weight,
+    BatchNorm and input gradients must agree to TOL_LAYER.  (An end-to-end comparison is dominated by ReLU-gate flips:
+    any reduced-precision forward moves ~1 % of the near-zero pre-activations across zero, and each flipped gate changes
+    the fp32-forward gradient by its full magnitude - measured rel-L2 0.05 per layer.  See the next test.)"""
+    import torch.nn.functional as F
+    TOL_LAYER = TOL_GRAD        # gradients rel-L2 <= 5e-2 (bf16); measured 0.01-0.025 (w, dx), < 0.015 (gamma)
+    TOL_BETA = 8e-2             # d(beta) is a plain sum of zero-mean terms: the same element noise weighs more (measured 0.02-0.06)
+    B = 16
+    enc_sd, dec_sd = U.init_state(False, seed=11)
+    obs, tc = unet_case_inputs(B, seed=21)
+    g = torch.Generator().manual_seed(33)
+    w_bin = torch.randn(B, 512, 32, 2, generator=g)
+    from move2hear_active_av_separation_b200.separator_cnn import PassiveSepDecCNN, PassiveSepEncCNN
+    enc, dec = PassiveSepEncCNN().cuda().train(), PassiveSepDecCNN().cuda().train()
+    enc.load_state_dict(enc_sd)
+    dec.load_state_dict(dec_sd)
+    bott, skips = enc({"mixed_bin_audio_mag": obs.cuda(), "target_class": tc.cuda()})
+    mask = dec(bott, skips)
+    (mask * w_bin.cuda()).sum().backward()
+    ws = bott._m2h_ws
+    bf = lambda t: t.to(torch.bfloat16).float()
+    CAT = {1: (16, 128), 2: (8, 256), 3: (4, 512), 4: (2, 1024)}
+    cat = {l: _ws_map(ws, l, *CAT[l]) for l in CAT}                  # activations: [decoder output | encoder skip]
+    dcat = {l: _ws_map(ws, 14 + l, *CAT[l]) for l in CAT}            # their gradients from the decoder side
+    denc = {l: _ws_map(ws, 20 + l, CAT[l][0], CAT[l][1] // 2) for l in CAT}      # encoder-side gradient of the skip at level l
+    vec = lambda slot: ws._vec(slot).float().cpu()
+    errs = {}
+
+    def block(tag, x, w, gamma, beta, transposed, slope, d_out):
+        x = x.clone().requires_grad_(True)
+        w = w.clone().requires_grad_(True)
+        gamma, beta = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        z = (F.conv_transpose2d if transposed else F.conv2d)(x, w, None, stride=2, padding=1)
+        y = F.batch_norm(z, None, None, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+        a = F.leaky_relu(y, slope) if slope else F.relu(y)
+        a.backward(d_out)
+        return x.grad, w.grad, gamma.grad, beta.grad
+
+    # ---- decoder blocks 4 .. 0 (block i reads level 5 - i, writes level 4 - i; level 5 = bottleneck, level 0 = a4)
+    for i in range(4, -1, -1):
+        lvl_in, lvl_out = 5 - i, 4 - i
+        x = vec(5).reshape(B, 512, 1, 1) if i == 0 else cat[lvl_in]
+        c_out = dec_sd[f"cnn.{i}.0.weight"].shape[1]
+        d_out = _ws_map(ws, 20, 32, 32) if i == 4 else dcat[lvl_out][:, :c_out]
+        dx, dw, dg, db = block(f"dec{i}", x, bf(dec_sd[f"cnn.{i}.0.weight"]), dec_sd[f"cnn.{i}.1.weight"], dec_sd[f"cnn.{i}.1.bias"], True, 0.0, d_out)
+        blk = dec.cnn[i]
+        errs[f"dec{i}.w"] = rel_l2(blk[0].weight.grad.cpu().numpy(), dw.numpy())
+        errs[f"dec{i}.gamma"] = rel_l2(blk[1].weight.grad.cpu().numpy(), dg.numpy())
+        errs[f"dec{i}.beta"] = rel_l2(blk[1].bias.grad.cpu().numpy(), db.numpy())
+        got_dx = vec(19).reshape(B, 512, 1, 1) if i == 0 else dcat[lvl_in]
+        errs[f"dec{i}.dx"] = rel_l2(got_dx.numpy(), dx.numpy())
+    # ---- head
+    a4 = _ws_map(ws, 7, 32, 32).requires_grad_(True)
+    hw = bf(dec_sd["cnn.5.0.weight"]).requires_grad_(True)
+    hb = dec_sd["cnn.5.0.bias"].clone().requires_grad_(True)
+    out = F.conv2d(a4, hw, hb)
+    out.backward(w_bin.permute(0, 3, 1, 2).reshape(B, 2, 16, 32, 32).reshape(B, 32, 32, 32))
+    errs["head.w"] = rel_l2(dec.cnn[5][0].weight.grad.cpu().numpy(), hw.grad.numpy())
+    errs["head.b"] = rel_l2(dec.cnn[5][0].bias.grad.cpu().numpy(), hb.grad.numpy())
+    errs["head.dx"] = rel_l2(_ws_map(ws, 20, 32, 32).numpy(), a4.grad.numpy())
+    # ---- encoder blocks 4 .. 0 (block i reads the skip half of level i, writes the skip half of level i + 1; level 5 = bottleneck)
+    x0 = U.encoder_input(obs, tc)
+    x0 = torch.cat((bf(x0[:, :32]), x0[:, 32:]), dim=1)
+    for i in range(4, -1, -1):
+        c_in = enc_sd[f"cnn.{i}.0.weight"].shape[1]
+        x = x0 if i == 0 else cat[i][:, cat[i].shape[1] // 2:]
+        w = enc_sd[f"cnn.{i}.0.weight"]
+        w = torch.cat((bf(w[:, :32]), w[:, 32:]), dim=1) if i == 0 else bf(w)
+        if i == 4:
+            d_out = vec(19).reshape(B, 512, 1, 1)
+        else:
+            lvl = i + 1
+            d_out = dcat[lvl][:, dcat[lvl].shape[1] // 2:] + denc[lvl]
+        dx, dw, dg, db = block(f"enc{i}", x, w, enc_sd[f"cnn.{i}.1.weight"], enc_sd[f"cnn.{i}.1.bias"], False, 0.2, d_out)
+        blk = enc.cnn[i]
+        errs[f"enc{i}.w"] = rel_l2(blk[0].weight.grad.cpu().numpy(), dw.numpy())
+        if i == 0:                  # the constant target-class plane (input channel 32) has its own gradient kernel
+            errs["enc0.w_class_plane"] = rel_l2(blk[0].weight.grad[:, 32].cpu().numpy(), dw[:, 32].numpy())
+            errs["enc0.w_audio"] = rel_l2(blk[0].weight.grad[:, :32].cpu().numpy(), dw[:, :32].numpy())
+        errs[f"enc{i}.gamma"] = rel_l2(blk[1].weight.grad.cpu().numpy(), dg.numpy())
+        errs[f"enc{i}.beta"] = rel_l2(blk[1].bias.grad.cpu().numpy(), db.numpy())
+        if i > 0:
+            errs[f"enc{i}.dx"] = rel_l2(denc[i].numpy(), dx.numpy())
+    print({k: round(v, 4) for k, v in errs.items()})
+    bad = {k: round(v, 4) for k, v in errs.items() if not v < (TOL_BETA if k.endswith("beta") else TOL_LAYER)}
+    assert not bad, bad
+
+
+def test_backward_end_to_end_against_fp32_autograd():
+    """All parameter gradients of both separators under a linear functional of the outputs against fp32 autograd with the
+    CUDA path's operand roundings emulated in the oracle's forward.  Tolerance: rel-L2 0.2 and cosine 0.98 - the residual
+    is the gate-flip noise described above, which grows with depth (measured 0.05 at the last decoder block, 0.13 at the
+    deepest encoder block) and is unbiased (norm ratios within 1 %)."""
+    B = 16
+    enc_sd, dec_sd = U.init_state(False, seed=11)
+    enc2_sd, dec2_sd = U.init_state(True, seed=12)
+    obs, tc = unet_case_inputs(B, seed=21)
+    g = torch.Generator().manual_seed(33)
+    w_bin = torch.randn(B, 512, 32, 2, generator=g)
+    w_mono = torch.randn(B, 512, 32, 1, generator=g)
+    in_masks = torch.randn(B, 512, 32, 2, generator=g) * 0.5 + 0.3
+
+    pol = _policy(enc_sd, dec_sd, enc2_sd, dec2_sd)
+    mask = pol.get_binSepMasks({"mixed_bin_audio_mag": obs.cuda(), "target_class": tc.cuda()})
+    mono = pol.convert_bin2mono(in_masks.cuda(), mixed_audio=obs.cuda())
+    ((mask * w_bin.cuda()).sum() + (mono * w_mono.cuda()).sum()).backward()
+
+    sds = _leaf_sds(enc_sd, dec_sd, enc2_sd, dec2_sd)
+    wm = U.separator_forward(sds[0], sds[1], obs, tc, training=True, emulate_bf16=True)
+    wmono = U.separator_forward(sds[2], sds[3], in_masks, convert_bin2mono=True, mixed_audio=obs, training=True, emulate_bf16=True)
+    ((wm * w_bin).sum() + (wmono * w_mono).sum()).backward()
+    assert rel_l2(mask.detach().cpu().numpy(), wm.detach().numpy()) < TOL_FWD
+    assert rel_l2(mono.detach().cpu().numpy(), wmono.detach().numpy()) < TOL_FWD
+    errs = _grad_errors(pol, sds)
+    bad = {k: round(v, 4) for k, v in errs.items() if not v < 0.2}
+    assert not bad, bad
+    mods = (pol.binSep_enc.passive_sep_encoder, pol.binSep_dec.passive_sep_decoder,
+            pol.bin2mono_enc.passive_sep_encoder, pol.bin2mono_dec.passive_sep_decoder)
+    for mod, sd in zip(mods, sds):
+        a = torch.cat([p.grad.reshape(-1).cpu() for _, p in mod.named_parameters()])
+        b = torch.cat([sd[n].grad.reshape(-1) for n, _ in mod.named_parameters()])
+        assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.98
+        assert abs(float(a.norm() / b.norm()) - 1) < 0.02
+
+
+def test_pretraining_step_losses_and_gradient_direction():
+    """The reference's own objective (two L1 losses, passive_trainer.py:269-284): losses to 1e-2; gradients compared by
+    direction (cosine): sign(pred - gt) flips wherever the bf16 forward error crosses zero, which perturbs an L1 gradient
+    element-wise without biasing it."""
+    from move2hear_active_av_separation_b200.separator_cnn import l1_mask_loss
+    B = 16
+    enc_sd, dec_sd = U.init_state(False, seed=11)
+    enc2_sd, dec2_sd = U.init_state(True, seed=12)
+    obs, tc = unet_case_inputs(B, seed=21)
+    g = torch.Generator().manual_seed(33)
+    gt_bin = torch.rand(B, 512, 32, 2, generator=g) * 2.0
+    gt_mono = torch.rand(B, 512, 32, 1, generator=g) * 2.0
+    pol = _policy(enc_sd, dec_sd, enc2_sd, dec2_sd)
+    obs_c = obs.cuda()
+    mask = pol.get_binSepMasks({"mixed_bin_audio_mag": obs_c, "target_class": tc.cuda()})
+    mono = pol.convert_bin2mono(mask.detach(), mixed_audio=obs_c)
+    bin_loss = l1_mask_loss(mask, gt_bin.cuda(), mixed_audio=obs_c)
+    mono_loss = l1_mask_loss(mono, gt_mono.cuda())
+    (bin_loss + mono_loss).backward()
+
+    sds = _leaf_sds(enc_sd, dec_sd, enc2_sd, dec2_sd)
+    wm = U.separator_forward(sds[0], sds[1], obs, tc, training=True)
+    wmono = U.separator_forward(sds[2], sds[3], wm.detach(), convert_bin2mono=True, mixed_audio=obs, training=True)
+    wbl, wml = U.supervised_losses(obs, wm, gt_bin, wmono, gt_mono)
+    (wbl + wml).backward()
+    assert abs(float(bin_loss) - float(wbl)) / float(wbl) < TOL_LOSS
+    assert abs(float(mono_loss) - float(wml)) / float(wml) < TOL_LOSS
+    mods = (pol.binSep_enc.passive_sep_encoder, pol.binSep_dec.passive_sep_decoder,
+            pol.bin2mono_enc.passive_sep_encoder, pol.bin2mono_dec.passive_sep_decoder)
+    for mod, sd in zip(mods, sds):
+        a = torch.cat([p.grad.reshape(-1).cpu() for _, p in mod.named_parameters()])
+        b = torch.cat([sd[n].grad.reshape(-1) for n, _ in mod.named_parameters()])
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        assert cos > 0.95, cos
+
+
+def test_loss_kernel_matches_torch():
+    from move2hear_active_av_separation_b200.separator_cnn import l1_mask_loss
+    g = torch.Generator().manual_seed(5)
+    B = 5
+    mask_nchw = torch.randn(B, 2, 512, 32, generator=g).cuda().requires_grad_(True)
+    obs = torch.log1p(torch.rand(B, 512, 32, 2, generator=g) * 3).cuda()
+    gt = (torch.rand(B, 512, 32, 2, generator=g) * 2).cuda()
+    loss = l1_mask_loss(mask_nchw.permute(0, 2, 3, 1), gt, mixed_audio=obs)
+    loss.backward()
+    m2 = mask_nchw.detach().clone().requires_grad_(True)
+    want = torch.nn.functional.l1_loss(m2.permute(0, 2, 3, 1) * (torch.exp(obs) - 1), gt)
+    want.backward()
+    assert abs(float(loss) - float(want)) < 1e-5 * float(want)
+    assert torch.allclose(mask_nchw.grad, m2.grad, atol=1e-9, rtol=1e-5)
+
+
+def test_optimizer_step_reduces_loss():
+    """Three Adam steps of ``pretrain.train_step`` (lr 5e-4, eps 1e-5 as passive_trainer.py:194-195) on one batch."""
+    from move2hear_active_av_separation_b200.policy import Move2HearPassiveWoMemoryPolicy
+    from move2hear_active_av_separation_b200.pretrain import train_step
+    torch.manual_seed(0)
+    pol = Move2HearPassiveWoMemoryPolicy().cuda().train()
+    opt = torch.optim.Adam(pol.parameters(), lr=5e-4, eps=1e-5)
+    B = 8
+    obs, tc = unet_case_inputs(B, seed=2)
+    g = torch.Generator().manual_seed(3)
+    gt_bin, gt_mono = torch.rand(B, 512, 32, 2, generator=g), torch.rand(B, 512, 32, 1, generator=g)
+    losses = []
+    for _ in range(4):
+        b, m = train_step(pol, opt, obs.cuda(), gt_bin.cuda(), gt_mono.cuda(), tc.cuda())
+        losses.append(float(b) + float(m))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
