@@ -314,10 +314,22 @@ def run_ours(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- BASELINE configs[2]: separator pretraining step (dataset-path render + both U-Nets fwd/bwd + L1 losses + Adam),
+    # B = 256 per GPU, gradients all-reduced (mean) across ranks over NCCL, overlapped with backward
+    train = None
+    ms_train = 0.0
+    if not args.no_train:
+        train, ms_train = run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_len, d_tc, barrier, stream)
+
+    times = torch.tensor([ms_total, ms_e2e, ms_train], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(times[0]), float(times[1])
+    ms_total, ms_e2e, ms_train = float(times[0]), float(times[1]), float(times[2])
+    if train is not None:
+        train["ms_per_step"] = ms_train / train["steps"]
+        train["value"] = world * train["batch_per_gpu"] * train["steps"] / (ms_train * 1e-3)
+        train["tflops"] = train["value"] * FLOPS_TRAIN / 1e12
+        train["frac_of_bf16_peak"] = train["tflops"] / world / peaks()["bf16_tflops_sustained"]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -360,8 +372,51 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / e2e_steps},
         "gpu_launches": 14 * args.steps,
         "clocks": clocks,
+        "train_step": train,
     }
     print(json.dumps(line), flush=True)
+
+
+B_TRAIN = 256
+FLOPS_TRAIN = 3 * (220.7e6 + 201.9e6)        # fwd + dgrad + wgrad of both separators, nominal 2*MACs per mixture
+
+
+def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_len, d_tc, barrier, stream):
+    """Times K pretraining steps (PassiveTrainer.train body, passive_trainer.py:218-245) on this rank's shard."""
+    from move2hear_active_av_separation_b200.distributed import GradientAllReducer, broadcast_module_state
+    from move2hear_active_av_separation_b200.policy import Move2HearPassiveWoMemoryPolicy
+    from move2hear_active_av_separation_b200.pretrain import train_step
+    torch.manual_seed(1234)
+    pol = Move2HearPassiveWoMemoryPolicy().to(dev).train()
+    broadcast_module_state(pol)
+    opt = torch.optim.Adam(pol.parameters(), lr=5e-4, eps=1e-5, fused=True)       # passive_trainer.py:194-195
+    red = GradientAllReducer(pol.parameters()) if world > 1 else None
+    B = B_TRAIN
+    mono, rir, ln, tc = d_mono[:B], d_rir[:B], d_len[:B], d_tc[:B]
+
+    def step():
+        out = rend.render(mono, rir, ln, n_gt=1)                                   # dataset path: fp32 log-mag mixture + target GT magnitude
+        mixed, gt_bin = out["mix_mag"], out["gt"][:, 0]
+        gt_mono, _ = rend.stft_f32((mono[:, :1].float() * (1.0 / 32768)).contiguous())      # monaural GT magnitude [B,512,T,1]
+        return train_step(pol, opt, mixed, gt_bin, gt_mono, tc, grad_sync=red.finish if red else None)
+
+    losses = []
+    for _ in range(2):
+        b, m = step()
+    losses.append((float(b), float(m)))
+    steps = max(3, args.steps // 4)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        b, m = step()
+    e1.record(stream)
+    barrier()
+    losses.append((float(b), float(m)))
+    info = {"workload": "configs[2] pretraining step: render (dataset path) + binSep & bin2mono U-Nets fwd/bwd (train-mode BN) + L1 losses + fused Adam",
+            "batch_per_gpu": B, "steps": steps, "unit": "mixtures/s", "grad_allreduce": "NCCL, 32 MB fp32 buckets overlapped with backward" if world > 1 else "none (1 GPU)",
+            "bin_mono_loss_first_last": losses}
+    return info, e0.elapsed_time(e1)
 
 
 def main():
@@ -371,6 +426,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the pretraining-step measurement (train_step key)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -9,6 +9,7 @@
 #include "m2h_internal.h"
 #include "unet_gemm.cuh"
 #include "unet_slab.cuh"
+#include "unet_gemm_tma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // static network description (separator_cnn.py:44-50, 128-135)
@@ -374,6 +375,64 @@ static int make_tmap(CUtensorMap* tm, const void* base, size_t rows, int cols, i
   if (r != CUDA_SUCCESS) { m2h_set_error("cuTensorMapEncodeTiled failed (%d): rows=%zu cols=%d ld=%d box_rows=%d", (int)r, rows, cols, ld, box_rows); return M2H_ERR_CUDA; }
   return M2H_OK;
 }
+static int make_tmap_nd(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, bool sw64) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { m2h_set_error("cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r); return M2H_ERR_CUDA; }
+  return M2H_OK;
+}
+// TMA-fed layer launch (unet_gemm_tma.cuh) for Cin >= 64 layers with bf16 NHWC output; falls back to the gather kernel otherwise
+template <int BN>
+static int launch_tma_bn(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const UGLayer& L, const UTGeom& G, int n_mtiles, cudaStream_t st) {
+  static bool attr_set[M2H_MAX_DEVICES];
+  int dev = 0;
+  M2H_CUDA_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, UTCfg<BN>::kSmemBytes));
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set[dev] = true;
+  }
+  dim3 grid(n_mtiles, L.Cout / BN, L.n_phase);
+  unet_gemm_tma_kernel<BN><<<grid, UT_THREADS, UTCfg<BN>::kSmemBytes, st>>>(tm_a, tm_w, L, G);
+  M2H_CUDA_CHECK(cudaGetLastError());
+  return M2H_OK;
+}
+static int launch_layer_auto(const UGLayer& L, int bn, int B, cudaStream_t st) {
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("M2H_UNET_TMA"); use_tma = e ? atoi(e) : 1; }
+  if (!use_tma || L.Cin < 64 || L.out_mode != UG_OUT_NHWC_BF16 || L.cls != nullptr || (bn != 64 && bn != 128) || L.Hq != L.Wq || L.Hq > 16 || L.Kvalid != L.Kpad)
+    return launch_layer(L, bn, st);
+  if (L.Cout % bn != 0 || L.M <= 0) { m2h_set_error("unet layer: unsupported shape Cout=%d bn=%d", L.Cout, bn); return M2H_ERR_ARG; }
+  UTGeom G;
+  const int Hq = L.Hq;
+  G.rows_y = Hq >= 8 ? 8 : Hq; G.nb = 128 / (Hq * G.rows_y); G.tiles_per_grp = Hq / G.rows_y; G.conv = L.in_stride == 2 ? 1 : 0; G.B = B;
+  const int n_mtiles = ((B + G.nb - 1) / G.nb) * G.tiles_per_grp;
+  alignas(64) CUtensorMap tm_a, tm_w;
+  int rc;
+  if (G.conv) {
+    const int hp = L.Hin + 2;
+    cuuint64_t dims[5] = {(cuuint64_t)2 * L.in_ld, (cuuint64_t)hp / 2, 2, (cuuint64_t)hp / 2, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)2 * L.in_ld * 2, (cuuint64_t)hp * L.in_ld * 2, (cuuint64_t)2 * hp * L.in_ld * 2, (cuuint64_t)hp * hp * L.in_ld * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)Hq, 1, (cuuint32_t)G.rows_y, (cuuint32_t)G.nb};
+    rc = make_tmap_nd(&tm_a, L.in, 5, dims, strides, box, false);
+  } else {
+    const int hp = L.Hin + 2 * L.in_pad;
+    cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)hp, (cuuint64_t)hp, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)L.in_ld * 2, (cuuint64_t)hp * L.in_ld * 2, (cuuint64_t)hp * hp * L.in_ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)Hq, (cuuint32_t)G.rows_y, (cuuint32_t)G.nb};
+    rc = make_tmap_nd(&tm_a, L.in, 4, dims, strides, box, false);
+  }
+  if (rc != M2H_OK) return rc;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L.Kpad, (cuuint64_t)L.n_phase * L.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)L.Kpad * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    rc = make_tmap_nd(&tm_w, L.w, 2, dims, strides, box, false);
+    if (rc != M2H_OK) return rc;
+  }
+  return bn == 128 ? launch_tma_bn<128>(tm_a, tm_w, L, G, n_mtiles, st) : launch_tma_bn<64>(tm_a, tm_w, L, G, n_mtiles, st);
+}
 // geometry + tensor maps + launch of one slab layer; items / epilogue fields of L are filled by the caller
 static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, int B, const __nv_bfloat16* w, cudaStream_t st) {
   L.Hp = L.Wp = Hp; L.PI = Hp * Hp; L.B = B;
@@ -585,7 +644,7 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
     g.w = (const __nv_bfloat16*)(pk + PL.w[i]); g.Cout = kEncCout[i]; g.Kvalid = g.Kpad = kEncTaps[i] * kEncCin[i];
     g.scale = (const float*)(pk + PL.scale[i]); g.bias = (const float*)(pk + PL.bias[i]); g.n_mod = kEncCout[i]; g.slope = 0.2f;
     g.out = out_ptr[i]; g.Hout = g.Wout = g.Hq; g.out_ld = out_ld[i]; g.out_pad = i == 4 ? 0 : 1; g.n_valid = g.Cout;
-    rc = launch_layer(g, 128, st);
+    rc = launch_layer_auto(g, 128, B, st);
     if (rc != M2H_OK) return rc;
   }
   if (bottleneck_f32) {
@@ -617,7 +676,7 @@ extern "C" int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2
     g.scale = (const float*)(pk + PL.scale[0]); g.bias = (const float*)(pk + PL.bias[0]); g.n_mod = 512; g.slope = 0.f;
     g.out = W.cat[4]; g.Hout = g.Wout = 1; g.out_ld = 16 * 1024; g.n_split = 512; g.n_valid = 2048;
     for (int pix = 0; pix < 4; ++pix) g.pix_off[pix] = (((pix >> 1) + 1) * 4 + (pix & 1) + 1) * 1024;
-    rc = launch_layer(g, 128, st);
+    rc = launch_layer_auto(g, 128, B, st);
     if (rc != M2H_OK) return rc;
   }
   const __nv_bfloat16* in_ptr[5] = {nullptr, W.cat[4], W.cat[3], W.cat[2], W.cat[1]};
@@ -634,7 +693,7 @@ extern "C" int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2
     g.w = (const __nv_bfloat16*)(pk + PL.w[i]); g.Cout = kDecCoutBase[i]; g.Kvalid = g.Kpad = 4 * kDecCin[i];
     g.scale = (const float*)(pk + PL.scale[i]); g.bias = (const float*)(pk + PL.bias[i]); g.n_mod = kDecCoutBase[i]; g.slope = 0.f;
     g.out = out_ptr[i]; g.Hout = g.Wout = 2 * hin[i]; g.out_stride = 2; g.out_ld = out_ld[i]; g.out_pad = 1; g.n_valid = g.Cout;
-    rc = launch_layer(g, 128, st);
+    rc = launch_layer_auto(g, 128, B, st);
     if (rc != M2H_OK) return rc;
   }
   for (int i = 3; i < 5; ++i) {   // layers 3, 4: slab kernel; layer 4 carries the 1x1 head and writes fp32 [B, C, 512, 32]

@@ -81,7 +81,7 @@ static int bn_forward(const TW& W, int layer, const FMap& z, const FMap& a, int 
                       float* run_mean, float* run_var, long long* nbt, float eps, float momentum, float slope, cudaStream_t st) {
   double* stats = W.stats(layer);
   M2H_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)4 * 512 * 8, st));
-  bn_stats_kernel<<<grid_for(z.P, 256 / (C / 8)), 256, 0, st>>>(z, C, stats);
+  bn_stats_kernel<<<grid_for(z.P, 4 * (256 / (C / 8))), 256, 2 * 256 * 8 * sizeof(float), st>>>(z, C, stats);
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, n, gamma, beta, eps, momentum, run_mean, run_var, nbt, W.aux(layer), Creal, C);
   bn_apply_kernel<<<grid_for(z.P * (C / 8), 256), 256, 0, st>>>(z, a, C, W.aux(layer), slope);
   M2H_CUDA_CHECK(cudaGetLastError());
@@ -93,7 +93,7 @@ static int bn_backward(const TW& W, int layer, const FMap& da1, const FMap& da2,
   double* red = W.stats(layer) + 2 * 512;
   M2H_CUDA_CHECK(cudaMemsetAsync(red, 0, (size_t)2 * 512 * 8, st));
   // reductions use [C] strides inside the 512-wide slots: kernels index red[c] and red[C + c]
-  bn_bwd_reduce_kernel<<<grid_for(z.P, 256 / (C / 8)), 256, 0, st>>>(da1, da2, a, z, C, W.aux(layer), slope, red);
+  bn_bwd_reduce_kernel<<<grid_for(z.P, 4 * (256 / (C / 8))), 256, 2 * 256 * 8 * sizeof(float), st>>>(da1, da2, a, z, C, W.aux(layer), slope, red);
   bn_bwd_apply_kernel<<<grid_for(z.P * (C / 8), 256), 256, 0, st>>>(da1, da2, a, z, C, Creal, W.aux(layer), slope, red, n, dgamma, dbeta);
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
@@ -103,13 +103,6 @@ static int bn_backward(const TW& W, int layer, const FMap& da1, const FMap& da2,
 // weight-gradient launch
 // ------------------------------------------------------------------------------------------------
 static bool g_wgrad_attr_set[M2H_MAX_DEVICES];
-static int make_tmap_nd(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, bool sw64) {
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { m2h_set_error("cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r); return M2H_ERR_CUDA; }
-  return M2H_OK;
-}
 // dense: [B][Hq+2][Hq+2][d_ld] haloed (or plain [B][d_ld] when Hq == 1 && !d_haloed); sampled: [B][2Hq+2][2Hq+2][s_ld] haloed
 static int launch_wgrad(const __nv_bfloat16* dense, int d_ld, int d_coff, int Cd, bool d_haloed, const __nv_bfloat16* sampled, int s_ld, int s_coff,
                         int Cs, int Cs_full, int Hq, int B, float* dw, cudaStream_t st) {
@@ -238,7 +231,7 @@ extern "C" int m2h_unet_encoder_forward_train(const m2h_unet_enc_params* p, int6
       if (i < 4) { g.out = W.bf(zcat_slot[i + 1]) + cat_ld[i + 1] / 2; g.out_ld = cat_ld[i + 1]; g.out_pad = 1; }
       else { g.out = W.bf(TW_ZBOTT); g.out_ld = 512; g.out_pad = 0; }
       g.Hout = g.Wout = g.Hq; g.n_valid = g.Cout;
-      rc = launch_layer(g, 128, st);
+      rc = launch_layer_auto(g, 128, B, st);
       if (rc != M2H_OK) return rc;
     }
     const int C = kEncCout[i];
@@ -298,7 +291,7 @@ extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int6
       g.w = (const __nv_bfloat16*)(pk + PL.w[0]); g.Cout = 2048; g.Kvalid = g.Kpad = 512; g.n_mod = 512; g.slope = 1.f;
       g.out = W.bf(TW_ZCAT4); g.Hout = g.Wout = 1; g.out_ld = 16 * 1024; g.n_split = 512; g.n_valid = 2048;
       for (int pix = 0; pix < 4; ++pix) g.pix_off[pix] = (((pix >> 1) + 1) * 4 + (pix & 1) + 1) * 1024;
-      rc = launch_layer(g, 128, st);
+      rc = launch_layer_auto(g, 128, B, st);
     } else if (i < 3) {
       UGLayer g;
       layer_defaults(g);
@@ -307,7 +300,7 @@ extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int6
       deconv_phases(g, hp[lvl_in] - 2, B);
       g.w = (const __nv_bfloat16*)(pk + PL.w[i]); g.Cout = kDecCoutBase[i]; g.Kvalid = g.Kpad = 4 * kDecCin[i]; g.n_mod = g.Cout; g.slope = 1.f;
       g.out = W.bf(zcat_slot[lvl_out]); g.out_ld = cat_ld[lvl_out]; g.n_valid = g.Cout;
-      rc = launch_layer(g, 128, st);
+      rc = launch_layer_auto(g, 128, B, st);
     } else {
       USLayer sl; SlabPackDesc pd;
       memset(&sl, 0, sizeof(sl));
@@ -385,7 +378,7 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
     if (i == 0) { g.out = W.bf(TW_DBOTT); g.out_ld = 512; g.out_pad = 0; }
     else { g.out = W.bf(dcat_slot[lvl_in]); g.out_ld = cat_ld[lvl_in]; g.out_pad = 1; }
     g.Hout = g.Wout = g.Hq; g.n_valid = g.Cout;
-    rc = launch_layer(g, 128, st);
+    rc = launch_layer_auto(g, 128, B, st);
     if (rc != M2H_OK) return rc;
   }
   return M2H_OK;
@@ -428,7 +421,7 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
       rc = launch_wgrad(z.p, z.ld, z.coff, 64, true, W.bf(TW_X0P), 32, 0, 32, convert_bin2mono ? 32 : 33, 16, B, grads->conv_w[0], st);
       if (rc != M2H_OK) return rc;
       if (!convert_bin2mono) {
-        wgrad_cls_kernel<<<64, 256, 0, st>>>(z.p, z.ld, z.coff, target_class_plus1, B, grads->conv_w[0], 33);
+        wgrad_cls_kernel<<<dim3(64, 16), 256, 0, st>>>(z.p, z.ld, z.coff, target_class_plus1, B, grads->conv_w[0], 33);
         M2H_CUDA_CHECK(cudaGetLastError());
       }
     } else {
@@ -449,7 +442,7 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
         g.Cout = kEncCin[i]; g.Kvalid = g.Kpad = 4 * C; g.n_mod = g.Cout;
         g.out = W.bf(denc_slot[i]); g.out_ld = kEncCin[i]; g.n_valid = g.Cout;
       }
-      rc = launch_layer(g, kEncCin[i] >= 128 ? 128 : 64, st);
+      rc = launch_layer_auto(g, kEncCin[i] >= 128 ? 128 : 64, B, st);
       if (rc != M2H_OK) return rc;
     }
   }

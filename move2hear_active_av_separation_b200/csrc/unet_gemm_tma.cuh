@@ -1,0 +1,143 @@
+// TMA-fed implicit-GEMM conv / transposed-conv layer (Cin >= 64) of the passive-separator U-Net on tcgen05.
+//
+// Same arithmetic and epilogue as unet_gemm.cuh (nn.Conv2d / nn.ConvTranspose2d k4 s2 p1 + BatchNorm + activation,
+// audio_separation/rl/models/separator_cnn.py:5-24), but the A operand is no longer gathered with cp.async by four warps:
+// with haloed NHWC feature maps every (tap, 64-channel chunk) of a 128-row tile is ONE dense TMA box
+//   transposed conv (stride-1 taps): box [nb][rows][W][64 ch] of the 4-D map at pixel offset (1 + dy, 1 + dx)
+//   stride-2 conv: box of the 5-D parity view [B][Hp/2][2][Wp/2][2*ld] (pixel (2y + kh, 2x + kw) = cell (y + kh/2, x + kw/2),
+//   parity (kh & 1, kw & 1))
+// which lands as the 128B-swizzled K-major tile tcgen05.mma reads.  One thread feeds a deep ring of (A box, weight box)
+// stages; the old kernel's 1024 cp.async per k-block and its two-deep look-ahead were the bottleneck of the deep layers
+// (1.2 us per 64-wide k-block at any batch size).
+#pragma once
+#include "unet_slab.cuh"
+
+#define UT_THREADS 192
+struct UTGeom {
+  int rows_y, nb;          // M tile = [nb images][rows_y rows][Wq columns] = 128 positions
+  int tiles_per_grp;       // Hq / rows_y
+  int conv;                // 1: stride-2 conv (5-D parity view), 0: stride-1 taps (4-D map)
+  int B;
+};
+
+template <int BN> struct UTCfg {
+  static constexpr int kStages = BN >= 128 ? 3 : 4;
+  static constexpr int kABytes = 16384, kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(UT_THREADS, 2)
+unet_gemm_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ UGLayer L,
+                     const __grid_constant__ UTGeom G) {
+  using C = UTCfg<BN>;
+  extern __shared__ unsigned char ut_smem_raw[];
+  const uint32_t raw = ug::smem_u32(ut_smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;
+  unsigned char* tiles_ptr = ut_smem_raw + (tiles - raw);
+  const uint32_t bars = tiles + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::kStages + s); };
+  const uint32_t accum_bar = bars + 8u * (2 * C::kStages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tiles_ptr + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 1));
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int n0 = blockIdx.y * BN, phase = blockIdx.z;
+  const int grp = blockIdx.x / G.tiles_per_grp, b0 = grp * G.nb, y0 = (blockIdx.x % G.tiles_per_grp) * G.rows_y;
+  const int kpt = L.Cin >> 6;                     // 64-channel chunks per tap
+  const int nkb = L.n_taps * kpt;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::kStages; ++s) { ug::mbar_init(full_bar(s), 1); ug::mbar_init(empty_bar(s), 1); }
+    ug::mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ug::smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  ug::tc_fence_before();
+  __syncthreads();
+  ug::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % C::kStages;
+        if (kb >= C::kStages) ug::mbar_wait(empty_bar(s), (uint32_t)((kb / C::kStages - 1) & 1));
+        const int tap = kb / kpt, c0 = (kb - tap * kpt) * 64;
+        const int dy = L.dy[phase][tap], dx = L.dx[phase][tap];
+        const uint32_t st = tiles + s * C::kStageBytes;
+        us::mbar_expect_tx(full_bar(s), (uint32_t)C::kStageBytes);
+        if (G.conv) {     // dy, dx hold kh - 1, kw - 1: haloed pixel (2y + kh, 2x + kw)
+          const int kh = dy + 1, kw = dx + 1;
+          us::tma_load_5d(st, &tm_a, (kw & 1) * L.in_ld + c0, (kw >> 1), (kh & 1), y0 + (kh >> 1), b0, full_bar(s));
+        } else {
+          us::tma_load_4d(st, &tm_a, c0, L.in_pad + dx, L.in_pad + y0 + dy, b0, full_bar(s));
+        }
+        us::tma_load_2d(st + C::kABytes, &tm_w, kb * 64, phase * L.Cout + n0, full_bar(s));
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------ MMA issuer ------------------------------
+    const uint32_t idesc = ug::instr_desc_bf16(BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % C::kStages;
+      ug::mbar_wait(full_bar(s), (uint32_t)((kb / C::kStages) & 1));
+      ug::tc_fence_after();
+      const uint32_t st = tiles + s * C::kStageBytes;
+      const uint64_t adesc = ug::smem_desc_sw128(st), bdesc = ug::smem_desc_sw128(st + C::kABytes);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) us::umma_bf16_elect(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+      us::umma_commit_elect(empty_bar(s));
+    }
+    us::umma_commit_elect(accum_bar);
+  } else {
+    // ------------------------------ epilogue: TMEM -> registers -> global (bf16 NHWC) ------------------------------
+    const int r = warp * 32 + lane;
+    const int per_img = G.rows_y * L.Wq;
+    const int ib = r / per_img, rr = r - ib * per_img;
+    const int b = b0 + ib, qy = y0 + rr / L.Wq, qx = rr % L.Wq;
+    const bool row_ok = b < G.B;
+    ug::mbar_wait(accum_bar, 0);
+    ug::tc_fence_after();
+    const int oy = qy * L.out_stride + (phase >> 1), ox = qx * L.out_stride + (phase & 1);
+    const int op = L.out_pad;
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t v[32];
+      ug::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+      if (!row_ok) continue;
+      float y[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int nm = (n0 + cb + i) % L.n_mod;
+        const float a = fmaf(__uint_as_float(v[i]), L.scale ? L.scale[nm] : 1.f, L.bias ? L.bias[nm] : 0.f);
+        y[i] = a > 0.f ? a : a * L.slope;
+      }
+      const int nn = n0 + cb;
+      const size_t col = (size_t)L.pix_off[nn / L.n_split] + (nn % L.n_split);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.out) + (((size_t)b * (L.Hout + 2 * op) + oy + op) * (L.Wout + 2 * op) + ox + op) * L.out_ld + col;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(y[i], y[i + 1]), t1 = __floats2bfloat162_rn(y[i + 2], y[i + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(y[i + 4], y[i + 5]), t3 = __floats2bfloat162_rn(y[i + 6], y[i + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(o + i) = pk;
+      }
+    }
+    ug::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    ug::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}

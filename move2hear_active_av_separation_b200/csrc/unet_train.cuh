@@ -38,10 +38,25 @@ __device__ __forceinline__ void st8(const FMap& m, long long pos, int c8, const 
 
 // ---- BatchNorm forward (batch statistics) ----------------------------------------------------------------------------------
 // per-channel sum / sum of squares of z over all positions (border positions hold zeros and add nothing): stats[0][C], stats[1][C]
+// block-level tree reduction of per-thread partial sums laid out [pl][C] in shared memory, then ONE fp64 atomic per channel and
+// block (thread-level fp64 atomics on a few hundred addresses serialise in L2: first capture 700 us per call)
+__device__ __forceinline__ void block_reduce_2xC(float* sm, int C, int ppi, int c8, int pl, const float (&s)[8], const float (&q)[8],
+                                                 double* out0, double* out1) {
+  float* sm1 = sm + ppi * C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sm[pl * C + c8 * 8 + i] = s[i]; sm1[pl * C + c8 * 8 + i] = q[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    const float* src = c < C ? sm + c : sm1 + (c - C);
+    float t = 0.f;
+    for (int p = 0; p < ppi; ++p) t += src[p * C];
+    atomicAdd(c < C ? out0 + c : out1 + (c - C), (double)t);
+  }
+}
 __global__ void bn_stats_kernel(const FMap z, int C, double* __restrict__ stats) {
+  extern __shared__ float bn_sm[];
   const int chunks = C / 8, ppi = blockDim.x / chunks;            // positions per block iteration
   const int c8 = threadIdx.x % chunks, pl = threadIdx.x / chunks;
-  if (pl >= ppi) return;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long pos = (long long)blockIdx.x * ppi + pl; pos < z.P; pos += (long long)gridDim.x * ppi) {
     float v[8];
@@ -49,8 +64,7 @@ __global__ void bn_stats_kernel(const FMap z, int C, double* __restrict__ stats)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { atomicAdd(stats + c8 * 8 + i, (double)s[i]); atomicAdd(stats + C + c8 * 8 + i, (double)q[i]); }
+  block_reduce_2xC(bn_sm, C, ppi, c8, pl, s, q, stats, stats + C);
 }
 // mean / biased variance -> scale = gamma * invstd, shift = beta - mean * scale; running stats (unbiased variance) updated in place.
 // aux = [scale | shift | mean | invstd] (each Cpad); channels >= Creal (zero-padded weight rows) get scale = shift = 0.
@@ -99,9 +113,9 @@ __global__ void bn_apply_kernel(const FMap z, const FMap a, int C, const float* 
 // dy = (da1 + da2) * act'(a);  red[0][C] = sum dy * xhat, red[1][C] = sum dy      (xhat = (z - mean) * invstd)
 __global__ void bn_bwd_reduce_kernel(const FMap da1, const FMap da2, const FMap a, const FMap z, int C, const float* __restrict__ aux,
                                      float slope, double* __restrict__ red) {
+  extern __shared__ float bn_sm[];
   const int chunks = C / 8, ppi = blockDim.x / chunks;
   const int c8 = threadIdx.x % chunks, pl = threadIdx.x / chunks;
-  if (pl >= ppi) return;
   float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long pos = (long long)blockIdx.x * ppi + pl; pos < z.P; pos += (long long)gridDim.x * ppi) {
     if (!fmap_interior(z, pos)) continue;
@@ -120,8 +134,7 @@ __global__ void bn_bwd_reduce_kernel(const FMap da1, const FMap da2, const FMap 
       sb[k] += dy;
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { atomicAdd(red + c8 * 8 + k, (double)sg[k]); atomicAdd(red + C + c8 * 8 + k, (double)sb[k]); }
+  block_reduce_2xC(bn_sm, C, ppi, c8, pl, sg, sb, red, red + C);
 }
 // dz = scale * (dy - dbeta/n - xhat * dgamma/n), written over z (interior positions); block 0 also emits the fp32 parameter grads
 __global__ void bn_bwd_apply_kernel(const FMap da1, const FMap da2, const FMap a, const FMap z, int C, int Creal, const float* __restrict__ aux,
@@ -183,11 +196,9 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a4, const floa
 __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ a4, const float* __restrict__ w, const float* __restrict__ dmask,
                                 __nv_bfloat16* __restrict__ da4, float* __restrict__ dw, float* __restrict__ db, int B, int Creal) {
   __shared__ float ws[32 * 33];
-  __shared__ float acc[32 * 33 + 32];
-  for (int i = threadIdx.x; i < 32 * 33 + 32; i += blockDim.x) acc[i] = 0.f;
   for (int i = threadIdx.x; i < Creal * Creal; i += blockDim.x) ws[(i / Creal) * 33 + i % Creal] = __bfloat162float(__float2bfloat16_rn(w[i]));
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // launched with 128 threads per block
   const bool ok = i < B * 1024;
   const int x = i & 31, y = (i >> 5) & 31, b = i >> 10;
   float v[32], g[32];
@@ -221,23 +232,27 @@ __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ a4, const floa
       dst[k] = u;
     }
   }
-  // dW[n][c], db[n]: warp-shuffle reduce over the 32 pixels of a warp, then shared / global atomics
-  const int lane = threadIdx.x & 31;
-  for (int n = 0; n < Creal; ++n) {
-    float gb = ok ? g[n] : 0.f;
+  // dW[n][c] = sum_pix g[n] v[c], db[n] = sum_pix g[n]: stage the block's 128 pixels in shared memory, each thread owns 8 (n, c) pairs
+  __shared__ float gs[128 * 33], vs[128 * 33];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
-    if (lane == 0) atomicAdd(&acc[32 * 33 + n], gb);
-    for (int c = 0; c < Creal; ++c) {
-      float t = ok ? g[n] * v[c] : 0.f;
+  for (int k = 0; k < 32; ++k) { gs[threadIdx.x * 33 + k] = g[k]; vs[threadIdx.x * 33 + k] = ok ? v[k] : 0.f; }
+  __syncthreads();
+  {
+    const int n = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 8;
+    float t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tb = 0.f;
+    for (int px = 0; px < 128; ++px) {
+      const float gn = gs[px * 33 + n];
+      tb += gn;
 #pragma unroll
-      for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) atomicAdd(&acc[n * 33 + c], t);
+      for (int k = 0; k < 8; ++k) t[k] = fmaf(gn, vs[px * 33 + c0 + k], t[k]);
+    }
+    if (n < Creal) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (c0 + k < Creal) atomicAdd(dw + n * Creal + c0 + k, t[k]);
+      if (c0 == 0) atomicAdd(db + n, tb);
     }
   }
-  __syncthreads();
-  for (int i2 = threadIdx.x; i2 < Creal * Creal; i2 += blockDim.x) atomicAdd(dw + i2, acc[(i2 / Creal) * 33 + i2 % Creal]);
-  for (int n = threadIdx.x; n < Creal; n += blockDim.x) atomicAdd(db + n, acc[32 * 33 + n]);
 }
 
 // ---- L1 mask loss (passive_trainer.py:269-275) -----------------------------------------------------------------------------------
@@ -267,6 +282,7 @@ __global__ void l1_mask_loss_kernel(const float* __restrict__ mask, const float*
 // dz: haloed [B][18][18][ld] (+coff).  One block per (co), threads over (b, oy, ox); 16 taps reduced in shared memory.
 __global__ void wgrad_cls_kernel(const __nv_bfloat16* __restrict__ dz, int ld, int coff, const float* __restrict__ cls, int B,
                                  float* __restrict__ dw, int CinFull) {
+  // grid = (64 output channels, batch slices); per-tap sums reduced over the block, then one atomic per tap (dw pre-zeroed)
   __shared__ float acc[16];
   if (threadIdx.x < 16) acc[threadIdx.x] = 0.f;
   __syncthreads();
@@ -274,7 +290,7 @@ __global__ void wgrad_cls_kernel(const __nv_bfloat16* __restrict__ dz, int ld, i
   float t[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) t[k] = 0.f;
-  for (int i = threadIdx.x; i < B * 256; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < B * 256; i += gridDim.y * blockDim.x) {
     const int ox = i & 15, oy = (i >> 4) & 15, b = i >> 8;
     const float v = __bfloat162float(dz[(((size_t)b * 18 + oy + 1) * 18 + ox + 1) * ld + coff + co]) * cls[b];
 #pragma unroll
@@ -296,7 +312,7 @@ __global__ void wgrad_cls_kernel(const __nv_bfloat16* __restrict__ dz, int ld, i
     if ((threadIdx.x & 31) == 0) atomicAdd(&acc[k], s);
   }
   __syncthreads();
-  if (threadIdx.x < 16) dw[((size_t)co * CinFull + (CinFull - 1)) * 16 + threadIdx.x] = acc[threadIdx.x];
+  if (threadIdx.x < 16) atomicAdd(&dw[((size_t)co * CinFull + (CinFull - 1)) * 16 + threadIdx.x], acc[threadIdx.x]);
 }
 
 // ---- weight-gradient GEMM on tcgen05 ------------------------------------------------------------------------------------------------
