@@ -401,22 +401,23 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
         return train_step(pol, opt, mixed, gt_bin, gt_mono, tc, grad_sync=red.finish if red else None)
 
     losses = []
-    for _ in range(2):
+    for _ in range(3):
         b, m = step()
-    losses.append((float(b), float(m)))
-    steps = max(3, args.steps // 4)
+    losses.append((float(b.detach()), float(m.detach())))
+    steps = max(5, args.steps // 2)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    marks[0].record(stream)
+    for i in range(steps):
         b, m = step()
-    e1.record(stream)
+        marks[i + 1].record(stream)
     barrier()
-    losses.append((float(b), float(m)))
+    losses.append((float(b.detach()), float(m.detach())))
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
     info = {"workload": "configs[2] pretraining step: render (dataset path) + binSep & bin2mono U-Nets fwd/bwd (train-mode BN) + L1 losses + fused Adam",
             "batch_per_gpu": B, "steps": steps, "unit": "mixtures/s", "grad_allreduce": "NCCL, 32 MB fp32 buckets overlapped with backward" if world > 1 else "none (1 GPU)",
-            "bin_mono_loss_first_last": losses}
-    return info, e0.elapsed_time(e1)
+            "bin_mono_loss_first_last": losses, "ms_per_step_median_this_rank": per_step[len(per_step) // 2], "ms_per_step_max_this_rank": per_step[-1]}
+    return info, marks[0].elapsed_time(marks[-1])
 
 
 def main():

@@ -545,3 +545,29 @@ def smoke_check(obs: torch.Tensor) -> None:
         want = U.separator_forward(enc_sd, dec_sd, obs.cpu(), tc.cpu())
     err = (mask.cpu() - want).norm() / want.norm()
     assert float(err) < 2e-2, float(err)
+
+
+def smoke_check_train(obs: torch.Tensor) -> None:
+    """One tiny pretraining forward/backward (train-mode BatchNorm, L1 loss) checked against torch autograd on the oracle."""
+    from oracle import unet as U
+    B = obs.size(0)
+    enc_sd, dec_sd = U.init_state(False, seed=3)
+    enc, dec = PassiveSepEncCNN().cuda().train(), PassiveSepDecCNN().cuda().train()
+    enc.load_state_dict(enc_sd)
+    dec.load_state_dict(dec_sd)
+    tc = torch.arange(B, device=obs.device).reshape(-1, 1) % 11
+    g = torch.Generator().manual_seed(1)
+    gt = torch.rand(B, 512, 32, 2, generator=g) * 2
+    mask = dec(*enc({"mixed_bin_audio_mag": obs, "target_class": tc}))
+    loss = l1_mask_loss(mask, gt.cuda(), mixed_audio=obs)
+    loss.backward()
+    sd_e = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in enc_sd.items()}
+    sd_d = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in dec_sd.items()}
+    want_mask = U.separator_forward(sd_e, sd_d, obs.cpu(), tc.cpu(), training=True, emulate_bf16=True)
+    want, _ = U.supervised_losses(obs.cpu(), want_mask, gt)
+    want.backward()
+    assert abs(float(loss) - float(want)) < 1e-2 * float(want), (float(loss), float(want))
+    gw, ww = dec.cnn[4][0].weight.grad.cpu(), sd_d["cnn.4.0.weight"].grad
+    assert float((gw - ww).norm() / ww.norm()) < 0.2
+    cos = float(torch.dot(gw.reshape(-1), ww.reshape(-1)) / (gw.norm() * ww.norm()))
+    assert cos > 0.97, cos
