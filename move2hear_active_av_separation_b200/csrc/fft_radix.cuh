@@ -39,7 +39,8 @@ M2H_DEV float2 mul_tw32(float2 d, int k) {
              : make_float2(d.x * c + d.y * s, d.y * c - d.x * s);
 }
 
-template <int R, bool INV>
+// ZERO_UPPER: v[R/2 .. R) is zero padding on entry (never read): the first stage degenerates to twiddle multiplies.
+template <int R, bool INV, bool ZERO_UPPER = false>
 M2H_DEV void fft_reg(float2 (&v)[R]) {
   M2H_UNROLL
   for (int half = R / 2; half >= 1; half >>= 1) {
@@ -47,6 +48,10 @@ M2H_DEV void fft_reg(float2 (&v)[R]) {
     for (int blk = 0; blk < R; blk += 2 * half) {
       M2H_UNROLL
       for (int j = 0; j < half; ++j) {
+        if (ZERO_UPPER && half == R / 2) {
+          v[j + half] = mul_tw32<INV>(v[j], j * (16 / half));
+          continue;
+        }
         const float2 a = v[blk + j], b = v[blk + j + half];
         v[blk + j] = c_add(a, b);
         v[blk + j + half] = mul_tw32<INV>(c_sub(a, b), j * (16 / half));

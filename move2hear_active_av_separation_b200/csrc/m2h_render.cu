@@ -49,11 +49,13 @@ int m2h_num_sms(int dev) { return g_tables[dev].n_sms; }
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
+// VEC = packed row accesses (even N / Lmax, aligned base pointers: conv_can_vectorise); the scalar variant serves the rest
+template <bool VEC>
 __global__ void __launch_bounds__(M2H_CONV_THREADS, 1)
 m2h_rir_conv_kernel(const ConvParams P, const M2hConvTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_raw);
-  conv_cta_body(P, s, tab, blockIdx.x, gridDim.x);
+  conv_cta_body<VEC>(P, s, tab, blockIdx.x, gridDim.x);
 }
 
 // 64 registers / thread (no spills): two 512-thread CTAs per SM, 2 x 86 KB of shared memory
@@ -81,11 +83,13 @@ extern "C" int m2h_init(int device) {
   M2H_CUDA_CHECK(cudaMalloc(&d.stft, sizeof(M2hStftTables)));
   M2H_CUDA_CHECK(cudaMemcpy(d.conv, &hc, sizeof(hc), cudaMemcpyHostToDevice));
   M2H_CUDA_CHECK(cudaMemcpy(d.stft, &hs, sizeof(hs), cudaMemcpyHostToDevice));
-  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
   // the driver's default carve-out (102 KB, ncu r1b) left room for ONE STFT CTA per SM: ask for the maximum
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaSetDevice(prev));
   d.ready = true;
   return M2H_OK;
@@ -121,7 +125,8 @@ extern "C" int m2h_rir_convolve(const int16_t* mono, const float* rir, const int
   ConvParams P;
   P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.waves = waves; P.scratch = (float4*)workspace;
   P.n_items = n_items; P.N = N; P.Lmax = Lmax;
-  m2h_rir_conv_kernel<<<grid, M2H_CONV_THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(P, g_tables[dev].conv);
+  if (conv_can_vectorise(P)) m2h_rir_conv_kernel<true><<<grid, M2H_CONV_THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(P, g_tables[dev].conv);
+  else m2h_rir_conv_kernel<false><<<grid, M2H_CONV_THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(P, g_tables[dev].conv);
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }

@@ -38,6 +38,7 @@ struct ConvParams {
 
 struct ConvSmem {
   float2 buf[M2H_CONV_BUF];
+  uint32_t stage[M2H_CONV_M];   // quantised output of one inverse transform, natural order: word j = samples (2j, 2j+1)
 };
 
 // Every inter-pass twiddle set is a geometric sequence whose base depends only on the thread id: each pass fetches
@@ -95,27 +96,48 @@ M2H_DEV void conv_inv_pass_b(ConvSmem& s, int tid) {
 }
 
 // Pass A of the forward transform with the global loads fused in.  Thread `tid` owns the residue
-// r = tid of the packed index j = n1*512 + r and reads packed samples (x[2j], x[2j+1]).
-//   SRC = 0: int16 mono, SRC = 1: float RIR taps.  `len` = number of valid real samples.
-template <int SRC>
-M2H_DEV void conv_fwd_pass_a(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const void* src, int len) {
+// r = tid of the packed index j = n1*512 + r and reads packed samples (x[2j], x[2j+1]); `len` = number of valid
+// real samples.  VEC: the row is 4-byte (int16) / 8-byte (float) aligned and, for int16, `len` is even, so that a
+// packed sample is one load.  ZU: len <= 16384, i.e. n1 >= 16 is zero padding and the first butterfly stage is pruned.
+template <bool VEC, bool ZU>
+M2H_DEV void conv_fwd_pass_a_mono(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const int16_t* x, int len) {
   const int r = tid;
+  const int lim = len - 2 * r;               // packed sample n1 is valid iff n1*1024 < lim (second half iff n1*1024 + 1 < lim)
   float2 v[32];
-  M2H_UNROLL for (int n1 = 0; n1 < 32; ++n1) {
-    const int i0 = 2 * (n1 * 512 + r);
+  M2H_UNROLL for (int n1 = 0; n1 < (ZU ? 16 : 32); ++n1) {
     float a = 0.f, b = 0.f;
-    if (SRC == 0) {
-      const int16_t* x = (const int16_t*)src;
-      if (i0 < len) a = (float)x[i0];
-      if (i0 + 1 < len) b = (float)x[i0 + 1];
+    if (VEC) {
+      uint32_t w = 0;
+      if (n1 * 1024 < lim) w = m2h_ldg_u32((const uint32_t*)x + n1 * 512 + r);
+      a = (float)(int16_t)(w & 0xffffu);
+      b = (float)(int16_t)(w >> 16);
     } else {
-      const float* x = (const float*)src;
-      if (i0 < len) a = m2h_ldg(x + i0);
-      if (i0 + 1 < len) b = m2h_ldg(x + i0 + 1);
+      if (n1 * 1024 < lim) a = (float)x[n1 * 1024 + 2 * r];
+      if (n1 * 1024 + 1 < lim) b = (float)x[n1 * 1024 + 2 * r + 1];
     }
     v[n1] = make_float2(a, b);
   }
-  fft_reg<32, false>(v);
+  fft_reg<32, false, ZU>(v);
+  float2* p = s.buf + (r >> 4) * M2H_CONV_S2 + (r & 15);
+  twiddle_powers_out<32, 5, false>(v, M2H_CONV_TW(t, 0, tid), M2H_CONV_TW(t, 1, tid), [&](int k1, float2 x) { p[k1 * M2H_CONV_S1] = x; });    // W_16384^(r*k1)
+}
+template <bool VEC, bool ZU>
+M2H_DEV void conv_fwd_pass_a_rir(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const float* x, int len) {
+  const int r = tid;
+  const int lim = len - 2 * r;
+  float2 v[32];
+  M2H_UNROLL for (int n1 = 0; n1 < (ZU ? 16 : 32); ++n1) {
+    float2 a = make_float2(0.f, 0.f);
+    if (VEC) {
+      if (n1 * 1024 < lim) a = m2h_ldg2((const float2*)x + n1 * 512 + r);
+      if (n1 * 1024 + 1 >= lim) a.y = 0.f;
+    } else {
+      if (n1 * 1024 < lim) a.x = m2h_ldg(x + n1 * 1024 + 2 * r);
+      if (n1 * 1024 + 1 < lim) a.y = m2h_ldg(x + n1 * 1024 + 2 * r + 1);
+    }
+    v[n1] = a;
+  }
+  fft_reg<32, false, ZU>(v);
   float2* p = s.buf + (r >> 4) * M2H_CONV_S2 + (r & 15);
   twiddle_powers_out<32, 5, false>(v, M2H_CONV_TW(t, 0, tid), M2H_CONV_TW(t, 1, tid), [&](int k1, float2 x) { p[k1 * M2H_CONV_S1] = x; });    // W_16384^(r*k1)
 }
@@ -129,19 +151,37 @@ M2H_DEV void conv_untangle(float2 za, float2 zb, float2 w, float2& xa, float2& x
   xb = c_conj(c_sub(p, q));
 }
 
+// The pointwise phases walk the 8192 pairs (f, M-f), f = k1 + 32*k2 + 1024*k3 < 8192, as idx = tid + 512*i:
+// (k2, k3) = ((tid>>3)&31, tid&7) belong to the thread and k1 = (tid>>8) + 2*i, so the buffer position of f advances by
+// 2*S1 per step and that of M-f (digits 32-k1, 31-k2, 15-k3 whenever k1 != 0) retreats by 2*S1: no per-element index
+// arithmetic.  Only the k1 = 0 column (i = 0, tid < 256) borrows differently.
+struct ConvPairWalk {
+  int pa0, pb0, pb_first;
+};
+M2H_DEV ConvPairWalk conv_pair_walk(int tid) {
+  const int t8 = tid >> 8, k2 = (tid >> 3) & 31, k3 = tid & 7;
+  ConvPairWalk w;
+  w.pa0 = t8 * M2H_CONV_S1 + k2 * M2H_CONV_S2 + k3;
+  w.pb0 = (32 - t8) * M2H_CONV_S1 + (31 - k2) * M2H_CONV_S2 + (15 - k3);
+  // i = 0: k1 = t8.  k1 = 0: M - f has digits (0, (32-k2)&31, 16 - k3 - (k2 != 0))   [tid = 0 is handled apart]
+  w.pb_first = t8 ? w.pb0 : ((32 - k2) & 31) * M2H_CONV_S2 + (16 - k3 - (k2 != 0 ? 1 : 0));
+  return w;
+}
+
 // Phase: spectrum of the mono signal -> per-CTA scratch (float4 = {2X[f], 2X[M-f]}).
 M2H_DEV void conv_store_mono_spectrum(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, float4* g) {
   const float2 wU = M2H_CONV_TW(t, 6, tid);
+  const ConvPairWalk pw = conv_pair_walk(tid);
   M2H_UNROLL for (int i = 0; i < 8192 / M2H_CONV_THREADS; ++i) {
     const int idx = tid + i * M2H_CONV_THREADS;
-    if (idx == 0) {
+    if (i == 0 && tid == 0) {
       const float2 z0 = s.buf[0], zh = s.buf[conv_pos(8192)];
       g[0] = make_float4(2.f * (z0.x + z0.y), 2.f * (z0.x - z0.y), 2.f * zh.x, -2.f * zh.y);   // X[0], X[M] (real), X[M/2]
     } else {
-      const int f = conv_pair_f(idx);
       float2 xa, xb;
       const float2 w = c_mul(wU, make_float2(conv_w16384_cos(i), conv_w16384_sin(i)));   // W_32768^(f0 + 2i)
-      conv_untangle(s.buf[conv_pos(f)], s.buf[conv_pos(16384 - f)], w, xa, xb);
+      const int pa = pw.pa0 + i * 2 * M2H_CONV_S1, pb = i == 0 ? pw.pb_first : pw.pb0 - i * 2 * M2H_CONV_S1;
+      conv_untangle(s.buf[pa], s.buf[pb], w, xa, xb);
       g[idx] = make_float4(xa.x, xa.y, xb.x, xb.y);
     }
   }
@@ -150,10 +190,15 @@ M2H_DEV void conv_store_mono_spectrum(ConvSmem& s, int tid, const M2hConvTables*
 // Phase: untangle H, multiply by X, re-tangle for the inverse transform (in place).
 M2H_DEV void conv_multiply_spectrum(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const float4* g) {
   const float2 wU = M2H_CONV_TW(t, 6, tid);
+  const ConvPairWalk pw = conv_pair_walk(tid);
+  float4 xs[8192 / M2H_CONV_THREADS / 2];
   M2H_UNROLL for (int i = 0; i < 8192 / M2H_CONV_THREADS; ++i) {
     const int idx = tid + i * M2H_CONV_THREADS;
-    const float4 x = g[idx];
-    if (idx == 0) {
+    // the X loads (L2-resident scratch) run half a phase ahead of their use
+    if (i == 0) { M2H_UNROLL for (int u = 0; u < 8; ++u) xs[u] = g[idx + u * M2H_CONV_THREADS]; }
+    const float4 x = xs[i & 7];
+    if (i + 8 < 8192 / M2H_CONV_THREADS) xs[i & 7] = g[idx + 8 * M2H_CONV_THREADS];
+    if (i == 0 && tid == 0) {
       const int ph = conv_pos(8192);
       const float2 z0 = s.buf[0], zh = s.buf[ph];
       const float y0 = x.x * (2.f * (z0.x + z0.y));
@@ -162,32 +207,30 @@ M2H_DEV void conv_multiply_spectrum(ConvSmem& s, int tid, const M2hConvTables* M
       const float2 y = c_mul(make_float2(x.z, x.w), make_float2(2.f * zh.x, -2.f * zh.y));
       s.buf[ph] = make_float2(2.f * y.x, -2.f * y.y);
     } else {
-      const int f = conv_pair_f(idx);
-      const int pa = conv_pos(f), pb = conv_pos(16384 - f);
+      const int pa = pw.pa0 + i * 2 * M2H_CONV_S1, pb = i == 0 ? pw.pb_first : pw.pb0 - i * 2 * M2H_CONV_S1;
       const float2 w = c_mul(wU, make_float2(conv_w16384_cos(i), conv_w16384_sin(i)));
       float2 ha, hb;
       conv_untangle(s.buf[pa], s.buf[pb], w, ha, hb);
       const float2 ya = c_mul(make_float2(x.x, x.y), ha);
       const float2 yb = c_mul(make_float2(x.z, x.w), hb);
       const float2 e = make_float2(ya.x + yb.x, ya.y - yb.y);            // Ya + conj(Yb)
-      const float2 t = make_float2(ya.x - yb.x, ya.y + yb.y);            // Ya - conj(Yb)
-      const float2 o = c_mulc(t, w);                                       // conj(w) * t
+      const float2 d = make_float2(ya.x - yb.x, ya.y + yb.y);            // Ya - conj(Yb)
+      const float2 o = c_mulc(d, w);                                       // conj(w) * d
       s.buf[pa] = make_float2(e.x - o.y, e.y + o.x);                       // E + i O
       s.buf[pb] = make_float2(e.x + o.y, o.x - e.y);                       // conj(E) + i conj(O)
     }
   }
 }
 
-// numpy: np.round (half to even) then astype(int16) wraps modulo 2^16
-M2H_DEV int16_t conv_quantise(float v) {
-  const float r = m2h_rintf(v);
-  const float lim = 2147483520.f;
-  const int32_t i = (int32_t)(r > lim ? lim : (r < -lim ? -lim : r));
-  return (int16_t)(uint16_t)(uint32_t)i;
+// numpy: np.round (half to even) then astype(int16) wraps modulo 2^16: round-to-nearest-even conversion to int32
+// (saturating far outside any reachable amplitude), low 16 bits kept
+M2H_DEV uint32_t conv_quantise_pair(float a, float b) {
+  return ((uint32_t)m2h_f2i_rn(a) & 0xffffu) | ((uint32_t)m2h_f2i_rn(b) << 16);
 }
 
-// Pass A' of the inverse transform fused with scale / round / window / store.
-M2H_DEV void conv_inv_pass_a_store(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, int16_t* out, int N, int c_off) {
+// Pass A' of the inverse transform fused with scale / round: the packed results j = n1*512 + r that overlap the output
+// window (sample indices [c_off, c_off + N)) go to the staging buffer as int16 pairs.
+M2H_DEV void conv_inv_pass_a_stage(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, int N, int c_off) {
   const int r = tid;
   const float2* p = s.buf + (r >> 4) * M2H_CONV_S2 + (r & 15);
   float2 v[32];
@@ -195,24 +238,55 @@ M2H_DEV void conv_inv_pass_a_store(ConvSmem& s, int tid, const M2hConvTables* M2
   twiddle_powers_inplace<32, true>(v, M2H_CONV_TW(t, 0, tid), M2H_CONV_TW(t, 1, tid));                                                        // conj W_16384^(r*k1)
   fft_reg<32, true>(v);
   const float scale = 1.0f / (8.0f * 16384.0f);      // 1/M inverse scale, 2*2*2 from the untangle/re-tangle steps
+  const int n1_lo = c_off >> 10, n1_hi = (c_off + N - 1) >> 10;
   M2H_UNROLL for (int n1 = 0; n1 < 32; ++n1) {
-    const float2 z = v[bitrev<5>(n1)];
-    const int m = 2 * (n1 * 512 + r) - c_off;        // output sample index of the real part
-    if (m >= 0 && m < N) out[m] = conv_quantise(z.x * scale);
-    if (m + 1 >= 0 && m + 1 < N) out[m + 1] = conv_quantise(z.y * scale);
+    if (n1 >= n1_lo && n1 <= n1_hi) {
+      const float2 z = v[bitrev<5>(n1)];
+      s.stage[n1 * 512 + r] = conv_quantise_pair(z.x * scale, z.y * scale);
+    }
+  }
+}
+// Window copy-out: out[m] = staged sample (m + c_off), m < N.  Runs after the barrier that ends pass A' and needs no
+// barrier of its own (the staging buffer is next written several phases later).
+template <bool VEC>
+M2H_DEV void conv_copy_out(const ConvSmem& s, int tid, int16_t* out, int N, int c_off) {
+  if (VEC) {                    // N even, row 4-byte aligned: one 32-bit store per sample pair, funnel-shifted when c_off is odd
+    uint32_t* o = (uint32_t*)out;
+    const int sh = (c_off & 1) * 16;
+    for (int w = tid; w < (N >> 1); w += M2H_CONV_THREADS) {
+      const int k = (2 * w + c_off) >> 1;
+      o[w] = m2h_funnel_r(s.stage[k], s.stage[(k + 1) & (M2H_CONV_M - 1)], sh);
+    }
+  } else {
+    for (int m = tid; m < N; m += M2H_CONV_THREADS) {
+      const int q = m + c_off;
+      const uint32_t w = s.stage[q >> 1];
+      out[m] = (int16_t)(uint16_t)((q & 1) ? (w >> 16) : (w & 0xffffu));
+    }
   }
 }
 
+// Rows can be read / written with packed accesses when every row start is suitably aligned.
+M2H_HD bool conv_can_vectorise(const ConvParams& P) {
+  return (P.N % 2 == 0) && (P.Lmax % 2 == 0) && ((uintptr_t)P.mono % 4 == 0) && ((uintptr_t)P.rir % 8 == 0) && ((uintptr_t)P.waves % 4 == 0);
+}
+
 // The whole per-CTA loop.  `cta`/`n_ctas` = blockIdx.x / gridDim.x.
+template <bool VEC>
 M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables* M2H_RESTRICT gtab, int cta, int n_ctas) {
   float4* g = P.scratch + (size_t)cta * M2H_CONV_SCRATCH_F4;
+  const int N = P.N;
+  int16_t* pend_out = nullptr;    // window of the previous inverse transform, still in the staging buffer
+  int pend_off = 0;
   for (int item = cta; item < P.n_items; item += n_ctas) {
-    const int N = P.N;
     const int L = P.rir_len[item];
     // taps that can reach the "same" window [c, c+N) of the full convolution: j in [c-N+1, c+N-1]
     const int c = (L - 1) / 2;
-    const int jmin = c - N + 1 > 0 ? c - N + 1 : 0;
+    int jmin = c - N + 1 > 0 ? c - N + 1 : 0;
     const int jmax = c + N - 1 < L - 1 ? c + N - 1 : L - 1;
+    // VEC: start one tap earlier when that makes the first tap 8-byte aligned (rows are: Lmax is even).  The extra tap
+    // j = c - N cannot reach the window, and the window stays alias-free: c_off + N - 1 <= 2N - 1 < F.
+    if (VEC && (jmin & 1)) jmin -= 1;
     const int Leff = jmax - jmin + 1;
     const int c_off = c - jmin;
     if (L <= 0) {     // unreadable / empty RIR -> the reference substitutes zeros (simulator_train.py:407-415)
@@ -222,7 +296,11 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
       }
       continue;
     }
-    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_a<0>(s, tid, gtab, P.mono + (size_t)item * N, N);
+    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) {
+      if (pend_out) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off);
+      conv_fwd_pass_a_mono<VEC, true>(s, tid, gtab, P.mono + (size_t)item * N, N);      // N <= 16384 always
+    }
+    pend_out = nullptr;
     M2H_SYNC();
     M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid, gtab);
     M2H_SYNC();
@@ -232,7 +310,11 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
     M2H_SYNC();
     for (int ear = 0; ear < 2; ++ear) {
       const float* h = P.rir + ((size_t)item * 2 + ear) * P.Lmax + jmin;
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_a<1>(s, tid, gtab, h, Leff);
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) {
+        if (pend_out) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off);
+        if (Leff <= 16384) conv_fwd_pass_a_rir<VEC, true>(s, tid, gtab, h, Leff);
+        else conv_fwd_pass_a_rir<VEC, false>(s, tid, gtab, h, Leff);
+      }
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid, gtab);
       M2H_SYNC();
@@ -244,9 +326,11 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_inv_pass_b(s, tid);
       M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS)
-        conv_inv_pass_a_store(s, tid, gtab, P.waves + ((size_t)item * 2 + ear) * N, N, c_off);
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_inv_pass_a_stage(s, tid, gtab, N, c_off);
       M2H_SYNC();
+      pend_out = P.waves + ((size_t)item * 2 + ear) * N;
+      pend_off = c_off;
     }
   }
+  if (pend_out) { M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off); }
 }

@@ -59,9 +59,12 @@ extern "C" int emu_rir_convolve(const int16_t* mono, const float* rir, const int
   ConvParams P;
   P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.waves = waves; P.scratch = scratch.data();
   P.n_items = B * K; P.N = N; P.Lmax = Lmax;
-  for (int cta = 0; cta < n_ctas; ++cta) conv_cta_body(P, *s, &g_ct, cta, n_ctas);
+  const bool vec = conv_can_vectorise(P);      // same dispatch rule as m2h_rir_convolve
+  for (int cta = 0; cta < n_ctas; ++cta) {
+    if (vec) conv_cta_body<true>(P, *s, &g_ct, cta, n_ctas); else conv_cta_body<false>(P, *s, &g_ct, cta, n_ctas);
+  }
   delete s;
-  return 0;
+  return vec ? 1 : 0;
 }
 
 extern "C" int emu_stft_waves(const int16_t* waves, int B, int K, int N, int n_gt, int gt_with_phase, int f16, int raw,

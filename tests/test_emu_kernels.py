@@ -107,7 +107,8 @@ def test_emulated_conv_wraps_like_numpy(emu):
 def test_emulated_conv_short_signal(emu):
     # N < 16000 and odd RIR lengths exercise the window-offset arithmetic
     rng = np.random.default_rng(5)
-    for N, L in ((1024, 333), (5000, 12001), (16384, 32767)):
+    # (5000, 12002) / (16000, 48002): even row length with an odd first tap -> the packed-load variant's one-tap shift
+    for N, L in ((1024, 333), (5000, 12001), (16384, 32767), (5000, 12002), (16000, 48002), (16384, 32768)):
         mono = np.round(3000 * rng.standard_normal((1, N))).astype(np.int16)
         h = (rng.standard_normal((1, 2, L)) * 0.02).astype(np.float32)
         waves = run_conv(emu, mono, h, np.array([L]), n_ctas=1)
