@@ -71,7 +71,7 @@ int m2h_rir_convolve(const int16_t* mono, const float* rir, const int32_t* rir_l
  *   habitat_audio/simulator_train.py:425-441, 469-486, habitat_audio/simulator_eval.py:437-500,
  *   audio_separation/pretrain/datasets/dataset.py:190-198, 216-228.
  *   waves      int16 [B, K, 2, N]
- *   mix_mag    OUT [B, 512, T, 2]  log1p(|STFT(mix)|)  (fp32, or fp16 with M2H_RENDER_F16_OBS), T = 1 + N/512
+ *   mix_mag    OUT [B, 512, T, 2]  log1p(|STFT(mix)|)  (fp32, or fp16 with M2H_RENDER_F16_OBS), T = 1 + (N-1)/512
  *   mix_phase  OUT [B, 512, T, 2]  angle(STFT(mix)) or NULL
  *   gt         OUT or NULL.  gt_with_phase = 0: [B, n_gt, 512, T, 2] magnitudes (dataset.py:198);
  *              gt_with_phase = 1: [B, n_gt, 512, T, 4] = (mag_l, phase_l, mag_r, phase_r)

@@ -151,7 +151,7 @@ extern "C" int m2h_stft_waves(const int16_t* waves, int B, int K, int N, int n_g
   if (rc != M2H_OK) return rc;
   StftParams P;
   memset(&P, 0, sizeof(P));
-  P.waves = waves; P.B = B; P.K = K; P.N = N; P.T = 1 + N / M2H_HOP;
+  P.waves = waves; P.B = B; P.K = K; P.N = N; P.T = 1 + (N - 1) / M2H_HOP;
   P.n_gt = n_gt; P.n_signals = 1 + n_gt;
   P.flags = ((flags & M2H_RENDER_RAW_MAG) ? 0 : M2H_OUT_MIX_LOG1P) | ((flags & M2H_RENDER_F16_OBS) ? M2H_OUT_F16 : 0);
   P.mix_mag = mix_mag; P.mix_phase = mix_phase; P.gt_mag = gt; P.gt_interleaved_phase = gt_with_phase ? 1 : 0;
@@ -167,7 +167,7 @@ extern "C" int m2h_stft_f32(const float* wave, int B, int C, int N, float* mag, 
   if (rc != M2H_OK) return rc;
   StftParams P;
   memset(&P, 0, sizeof(P));
-  P.fwave = wave; P.fwave_channels = C; P.B = B; P.K = 0; P.N = N; P.T = 1 + N / M2H_HOP;
+  P.fwave = wave; P.fwave_channels = C; P.B = B; P.K = 0; P.N = N; P.T = 1 + (N - 1) / M2H_HOP;
   P.n_signals = 1; P.f_mag = mag; P.f_phase = phase;
   return launch_stft(P, dev, stream);
 }

@@ -95,15 +95,15 @@ M2H_DEV void conv_inv_pass_b(ConvSmem& s, int tid) {
   M2H_UNROLL for (int n2 = 0; n2 < 32; ++n2) p[n2 * M2H_CONV_S2] = v[bitrev<5>(n2)];
 }
 
-// Pass A of the forward transform with the global loads fused in.  Thread `tid` owns the residue
-// r = tid of the packed index j = n1*512 + r and reads packed samples (x[2j], x[2j+1]); `len` = number of valid
-// real samples.  VEC: the row is 4-byte (int16) / 8-byte (float) aligned and, for int16, `len` is even, so that a
-// packed sample is one load.  ZU: len <= 16384, i.e. n1 >= 16 is zero padding and the first butterfly stage is pruned.
+// Pass A of the forward transform, split into its global loads and the radix pass so that the caller can put
+// independent work (the previous window's copy-out) under the load latency.  Thread `tid` owns the residue r = tid of
+// the packed index j = n1*512 + r and reads packed samples (x[2j], x[2j+1]); `len` = number of valid real samples.
+// VEC: the row is 4-byte (int16) / 8-byte (float) aligned and, for int16, `len` is even, so a packed sample is one load.
+// ZU: len <= 16384, i.e. n1 >= 16 is zero padding (not loaded) and the first butterfly stage is pruned.
 template <bool VEC, bool ZU>
-M2H_DEV void conv_fwd_pass_a_mono(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const int16_t* x, int len) {
+M2H_DEV void conv_load_mono(float2 (&v)[32], int tid, const int16_t* x, int len) {
   const int r = tid;
   const int lim = len - 2 * r;               // packed sample n1 is valid iff n1*1024 < lim (second half iff n1*1024 + 1 < lim)
-  float2 v[32];
   M2H_UNROLL for (int n1 = 0; n1 < (ZU ? 16 : 32); ++n1) {
     float a = 0.f, b = 0.f;
     if (VEC) {
@@ -117,15 +117,11 @@ M2H_DEV void conv_fwd_pass_a_mono(ConvSmem& s, int tid, const M2hConvTables* M2H
     }
     v[n1] = make_float2(a, b);
   }
-  fft_reg<32, false, ZU>(v);
-  float2* p = s.buf + (r >> 4) * M2H_CONV_S2 + (r & 15);
-  twiddle_powers_out<32, 5, false>(v, M2H_CONV_TW(t, 0, tid), M2H_CONV_TW(t, 1, tid), [&](int k1, float2 x) { p[k1 * M2H_CONV_S1] = x; });    // W_16384^(r*k1)
 }
 template <bool VEC, bool ZU>
-M2H_DEV void conv_fwd_pass_a_rir(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const float* x, int len) {
+M2H_DEV void conv_load_rir(float2 (&v)[32], int tid, const float* x, int len) {
   const int r = tid;
   const int lim = len - 2 * r;
-  float2 v[32];
   M2H_UNROLL for (int n1 = 0; n1 < (ZU ? 16 : 32); ++n1) {
     float2 a = make_float2(0.f, 0.f);
     if (VEC) {
@@ -137,9 +133,17 @@ M2H_DEV void conv_fwd_pass_a_rir(ConvSmem& s, int tid, const M2hConvTables* M2H_
     }
     v[n1] = a;
   }
+}
+template <bool ZU>
+M2H_DEV void conv_fwd_pass_a(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, float2 (&v)[32]) {
+  const int r = tid;
   fft_reg<32, false, ZU>(v);
   float2* p = s.buf + (r >> 4) * M2H_CONV_S2 + (r & 15);
   twiddle_powers_out<32, 5, false>(v, M2H_CONV_TW(t, 0, tid), M2H_CONV_TW(t, 1, tid), [&](int k1, float2 x) { p[k1 * M2H_CONV_S1] = x; });    // W_16384^(r*k1)
+}
+// L2 prefetch of a row that a later phase will load (one 128-byte line per thread and step)
+M2H_DEV void conv_prefetch_row(int tid, const void* row, int bytes) {
+  for (int o = tid * 128; o < bytes; o += M2H_CONV_THREADS * 128) m2h_prefetch_l2((const char*)row + o);
 }
 
 // Untangle the packed-real spectrum at (f, M-f):  returns 2*X[f] in xa and 2*X[M-f] in xb.
@@ -187,38 +191,51 @@ M2H_DEV void conv_store_mono_spectrum(ConvSmem& s, int tid, const M2hConvTables*
   }
 }
 
-// Phase: untangle H, multiply by X, re-tangle for the inverse transform (in place).
+// Phase: untangle H, multiply by X, re-tangle for the inverse transform (in place).  Four pairs per batch: their
+// shared-memory loads are issued together (in-place stores would otherwise fence every following load).
 M2H_DEV void conv_multiply_spectrum(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const float4* g) {
   const float2 wU = M2H_CONV_TW(t, 6, tid);
   const ConvPairWalk pw = conv_pair_walk(tid);
-  float4 xs[8192 / M2H_CONV_THREADS / 2];
-  M2H_UNROLL for (int i = 0; i < 8192 / M2H_CONV_THREADS; ++i) {
-    const int idx = tid + i * M2H_CONV_THREADS;
-    // the X loads (L2-resident scratch) run half a phase ahead of their use
-    if (i == 0) { M2H_UNROLL for (int u = 0; u < 8; ++u) xs[u] = g[idx + u * M2H_CONV_THREADS]; }
-    const float4 x = xs[i & 7];
-    if (i + 8 < 8192 / M2H_CONV_THREADS) xs[i & 7] = g[idx + 8 * M2H_CONV_THREADS];
-    if (i == 0 && tid == 0) {
-      const int ph = conv_pos(8192);
-      const float2 z0 = s.buf[0], zh = s.buf[ph];
-      const float y0 = x.x * (2.f * (z0.x + z0.y));
-      const float ym = x.y * (2.f * (z0.x - z0.y));
-      s.buf[0] = make_float2(y0 + ym, y0 - ym);
-      const float2 y = c_mul(make_float2(x.z, x.w), make_float2(2.f * zh.x, -2.f * zh.y));
-      s.buf[ph] = make_float2(2.f * y.x, -2.f * y.y);
-    } else {
-      const int pa = pw.pa0 + i * 2 * M2H_CONV_S1, pb = i == 0 ? pw.pb_first : pw.pb0 - i * 2 * M2H_CONV_S1;
-      const float2 w = c_mul(wU, make_float2(conv_w16384_cos(i), conv_w16384_sin(i)));
-      float2 ha, hb;
-      conv_untangle(s.buf[pa], s.buf[pb], w, ha, hb);
-      const float2 ya = c_mul(make_float2(x.x, x.y), ha);
-      const float2 yb = c_mul(make_float2(x.z, x.w), hb);
-      const float2 e = make_float2(ya.x + yb.x, ya.y - yb.y);            // Ya + conj(Yb)
-      const float2 d = make_float2(ya.x - yb.x, ya.y + yb.y);            // Ya - conj(Yb)
-      const float2 o = c_mulc(d, w);                                       // conj(w) * d
-      s.buf[pa] = make_float2(e.x - o.y, e.y + o.x);                       // E + i O
-      s.buf[pb] = make_float2(e.x + o.y, o.x - e.y);                       // conj(E) + i conj(O)
+  constexpr int NI = 8192 / M2H_CONV_THREADS, NB = 4;
+  float4 xs[2][NB];
+  M2H_UNROLL for (int u = 0; u < NB; ++u) xs[0][u] = g[tid + u * M2H_CONV_THREADS];
+  M2H_UNROLL for (int i0 = 0; i0 < NI; i0 += NB) {
+    const int cur = (i0 / NB) & 1;
+    if (i0 + NB < NI) { M2H_UNROLL for (int u = 0; u < NB; ++u) xs[cur ^ 1][u] = g[tid + (i0 + NB + u) * M2H_CONV_THREADS]; }   // X of the next batch (L2)
+    float2 za[NB], zb[NB];
+    int pa[NB], pb[NB];
+    M2H_UNROLL for (int u = 0; u < NB; ++u) {
+      const int i = i0 + u;
+      pa[u] = pw.pa0 + i * 2 * M2H_CONV_S1;
+      pb[u] = i == 0 ? pw.pb_first : pw.pb0 - i * 2 * M2H_CONV_S1;
+      if (i == 0 && tid == 0) pb[u] = conv_pos(8192);
+      za[u] = s.buf[pa[u]];
+      zb[u] = s.buf[pb[u]];
     }
+    M2H_UNROLL for (int u = 0; u < NB; ++u) {
+      const int i = i0 + u;
+      const float4 x = xs[cur][u];
+      if (i == 0 && tid == 0) {      // X[0], X[M] (real) ride in one complex slot; X[M/2]
+        const float2 z0 = za[u], zh = zb[u];
+        const float y0 = x.x * (2.f * (z0.x + z0.y));
+        const float ym = x.y * (2.f * (z0.x - z0.y));
+        za[u] = make_float2(y0 + ym, y0 - ym);
+        const float2 y = c_mul(make_float2(x.z, x.w), make_float2(2.f * zh.x, -2.f * zh.y));
+        zb[u] = make_float2(2.f * y.x, -2.f * y.y);
+      } else {
+        const float2 w = c_mul(wU, make_float2(conv_w16384_cos(i), conv_w16384_sin(i)));
+        float2 ha, hb;
+        conv_untangle(za[u], zb[u], w, ha, hb);
+        const float2 ya = c_mul(make_float2(x.x, x.y), ha);
+        const float2 yb = c_mul(make_float2(x.z, x.w), hb);
+        const float2 e = make_float2(ya.x + yb.x, ya.y - yb.y);            // Ya + conj(Yb)
+        const float2 d = make_float2(ya.x - yb.x, ya.y + yb.y);            // Ya - conj(Yb)
+        const float2 o = c_mulc(d, w);                                       // conj(w) * d
+        za[u] = make_float2(e.x - o.y, e.y + o.x);                           // E + i O
+        zb[u] = make_float2(e.x + o.y, o.x - e.y);                           // conj(E) + i conj(O)
+      }
+    }
+    M2H_UNROLL for (int u = 0; u < NB; ++u) { s.buf[pa[u]] = za[u]; s.buf[pb[u]] = zb[u]; }
   }
 }
 
@@ -297,8 +314,11 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
       continue;
     }
     M2H_FOR_THREADS(tid, M2H_CONV_THREADS) {
-      if (pend_out) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off);
-      conv_fwd_pass_a_mono<VEC, true>(s, tid, gtab, P.mono + (size_t)item * N, N);      // N <= 16384 always
+      float2 v[32];
+      conv_load_mono<VEC, true>(v, tid, P.mono + (size_t)item * N, N);                  // N <= 16384 always
+      conv_prefetch_row(tid, P.rir + (size_t)item * 2 * P.Lmax + jmin, Leff * 4);       // ear 0, loaded four phases from now
+      if (pend_out) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off);                  // under the load latency
+      conv_fwd_pass_a<true>(s, tid, gtab, v);
     }
     pend_out = nullptr;
     M2H_SYNC();
@@ -311,10 +331,21 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
     for (int ear = 0; ear < 2; ++ear) {
       const float* h = P.rir + ((size_t)item * 2 + ear) * P.Lmax + jmin;
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) {
-        if (pend_out) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off);
-        if (Leff <= 16384) conv_fwd_pass_a_rir<VEC, true>(s, tid, gtab, h, Leff);
-        else conv_fwd_pass_a_rir<VEC, false>(s, tid, gtab, h, Leff);
+        float2 v[32];
+        if (Leff <= 16384) {
+          conv_load_rir<VEC, true>(v, tid, h, Leff);
+          if (pend_out) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off);
+          conv_fwd_pass_a<true>(s, tid, gtab, v);
+        } else {
+          conv_load_rir<VEC, false>(v, tid, h, Leff);
+          if (pend_out) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off);
+          conv_fwd_pass_a<false>(s, tid, gtab, v);
+        }
+        // rows the next transforms will load: the other ear, or the next item's clip
+        if (ear == 0) conv_prefetch_row(tid, h + P.Lmax, Leff * 4);
+        else if (item + n_ctas < P.n_items) conv_prefetch_row(tid, P.mono + (size_t)(item + n_ctas) * N, N * 2);
       }
+      pend_out = nullptr;
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid, gtab);
       M2H_SYNC();

@@ -35,7 +35,7 @@ struct StftParams {
   // input B: generic fp32 waveforms [B, C, N] (C = 1 or 2), used when waves == null
   const float* fwave;
   int fwave_channels;
-  int B, K, N, T;          // T = 1 + N / 512 frames
+  int B, K, N, T;          // T = 1 + (N - 1) / 512 frames (librosa centre framing with the odd n_fft)
   int n_signals;           // waves mode: 1 (mixture only) .. 1 + n_gt ; fwave mode: 1
   int n_gt;                // number of leading sources that get their own GT spectrogram (0, 1 or K)
   int flags;
@@ -48,14 +48,24 @@ struct StftParams {
   void* f_phase;           // fwave mode: [B, 512, T, C] fp32 or null
 };
 
+// samples [512*t0 - 512, 512*t0 + 2048) cover the four frames t0 .. t0+3 (reflection at either end maps back inside)
+#define M2H_STFT_STAGE 2560
 struct StftSmem {
   float2 buf[M2H_STFT_GROUPS][M2H_STFT_BUF];
   float2 bf[2048];          // chirp spectrum, [k3][k1*16+k2] so that consecutive threads read consecutive entries
+  float2 stage[M2H_STFT_STAGE];   // (left, right) samples of the signal being transformed, exactly the reference's fp32 values
 };
 #define M2H_STFT_TW(t, which, tid) m2h_ldg2(&(t)->thr[which][(tid) & 127])
 
 M2H_DEV int stft_reflect(int i, int N) { return i < 0 ? -i : (i >= N ? 2 * (N - 1) - i : i); }
 
+// fp32 value of an integer sample sum: the fp32 sum of x*2^-15 terms is exact for K <= 256; the divide is the reference's
+// float32 divide by K (simulator_train.py:471) - a multiplication by the exact reciprocal when K is a power of two
+M2H_DEV float stft_scale(int v, int K, bool mix) {
+  const float x = (float)v * (1.0f / 32768.0f);
+  if (!mix) return x;
+  return (K & (K - 1)) == 0 ? x * (1.0f / (float)K) : x / (float)K;
+}
 // one sample of signal `sig` for item b, both ears
 M2H_DEV float2 stft_sample(const StftParams& P, int b, int sig, int i) {
   if (P.waves) {
@@ -66,16 +76,46 @@ M2H_DEV float2 stft_sample(const StftParams& P, int b, int sig, int i) {
         sl += w[(size_t)(2 * k) * P.N + i];
         sr += w[(size_t)(2 * k + 1) * P.N + i];
       }
-      // fp32 sum of x*2^-15 terms is exact for K <= 256; the divide is the reference's float32 divide by K
-      const float kf = (float)P.K;
-      return make_float2(((float)sl * (1.0f / 32768.0f)) / kf, ((float)sr * (1.0f / 32768.0f)) / kf);
+      return make_float2(stft_scale(sl, P.K, true), stft_scale(sr, P.K, true));
     }
     const int k = sig - 1;
-    return make_float2((float)w[(size_t)(2 * k) * P.N + i] * (1.0f / 32768.0f),
-                       (float)w[(size_t)(2 * k + 1) * P.N + i] * (1.0f / 32768.0f));
+    return make_float2(stft_scale(w[(size_t)(2 * k) * P.N + i], 1, false), stft_scale(w[(size_t)(2 * k + 1) * P.N + i], 1, false));
   }
   const float* f = P.fwave + (size_t)b * P.fwave_channels * P.N;
   return make_float2(f[i], P.fwave_channels > 1 ? f[P.N + i] : 0.f);
+}
+
+struct StftI16x8 { uint32_t w[4]; };
+M2H_DEV void stft_acc8(int (&acc)[8], const int16_t* p) {
+  const StftI16x8 q = *reinterpret_cast<const StftI16x8*>(p);       // 16-byte aligned by construction
+  M2H_UNROLL for (int u = 0; u < 4; ++u) {
+    acc[2 * u] += (int)(int16_t)(q.w[u] & 0xffffu);
+    acc[2 * u + 1] += (int)(int16_t)(q.w[u] >> 16);
+  }
+}
+// P0: stage the samples the four frames t0 .. t0+3 touch.  Rows that allow it are read as 8 x int16 vectors.
+M2H_DEV void stft_stage(const StftParams& P, StftSmem& s, int tid, int b, int sig, int t0) {
+  const int i0 = M2H_HOP * t0 - M2H_HOP;
+  if (P.waves && (P.N & 7) == 0 && ((uintptr_t)P.waves & 15) == 0) {
+    const int i = i0 + 8 * tid;
+    if (tid < M2H_STFT_STAGE / 8 && i >= 0 && i < P.N) {
+      const int16_t* w = P.waves + (size_t)b * P.K * 2 * P.N + i;
+      int al[8], ar[8];
+      M2H_UNROLL for (int u = 0; u < 8; ++u) { al[u] = 0; ar[u] = 0; }
+      const int k_lo = sig == 0 ? 0 : sig - 1, k_hi = sig == 0 ? P.K : sig;
+      for (int k = k_lo; k < k_hi; ++k) {
+        stft_acc8(al, w + (size_t)(2 * k) * P.N);
+        stft_acc8(ar, w + (size_t)(2 * k + 1) * P.N);
+      }
+      M2H_UNROLL for (int u = 0; u < 8; ++u)
+        s.stage[8 * tid + u] = make_float2(stft_scale(al[u], P.K, sig == 0), stft_scale(ar[u], P.K, sig == 0));
+    }
+  } else {
+    for (int j = tid; j < M2H_STFT_STAGE; j += M2H_STFT_THREADS) {
+      const int i = i0 + j;
+      if (i >= 0 && i < P.N) s.stage[j] = stft_sample(P, b, sig, i);
+    }
+  }
 }
 
 #ifndef M2H_HOST_EMU
@@ -149,7 +189,7 @@ M2H_DEV void stft_p1(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_
     const int n = n1 * 128 + r;
     float2 a = make_float2(0.f, 0.f);
     if (n < M2H_NFFT) {
-      const float2 x = stft_sample(P, b, sig, stft_reflect(M2H_HOP * t - (M2H_NFFT / 2) + n, P.N));
+      const float2 x = s.stage[stft_reflect(M2H_HOP * t - (M2H_NFFT / 2) + n, P.N) - (M2H_HOP * t0 - M2H_HOP)];
       a = c_mul(x, gt->wc[n]);
     }
     v[n1] = a;
@@ -232,6 +272,8 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
   for (int item = cta; item < n_items; item += n_ctas) {
     const int b = item / P.n_signals, sig = item % P.n_signals;
     for (int t0 = 0; t0 < P.T; t0 += M2H_STFT_GROUPS) {
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_stage(P, s, tid, b, sig, t0);
+      M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p1(P, s, gt, tid, b, sig, t0);
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p2(P, s, gt, tid, t0);

@@ -77,7 +77,7 @@ class AudioRenderer:
         """STFT of the mixture (and of the first ``n_gt`` sources).  Returns ``(mix_mag, mix_phase|None, gt|None)``."""
         waves = _need_cuda(waves, "waves", torch.int16)
         B, K, _, N = waves.shape
-        T = 1 + N // HOP_LENGTH
+        T = 1 + (N - 1) // HOP_LENGTH
         dt = torch.float16 if sim_dtypes else torch.float32
         mix = torch.empty((B, N_BINS, T, 2), dtype=dt, device=self.device)
         phase = torch.empty((B, N_BINS, T, 2), dtype=dt, device=self.device) if want_phase else None
@@ -103,7 +103,7 @@ class AudioRenderer:
         """fp32 ``[B,C,N]`` -> (``|STFT|`` ``[B,512,T,C]``, phase or None)."""
         wave = _need_cuda(wave, "wave", torch.float32)
         B, C, N = wave.shape
-        T = 1 + N // HOP_LENGTH
+        T = 1 + (N - 1) // HOP_LENGTH
         mag = torch.empty((B, N_BINS, T, C), dtype=torch.float32, device=self.device)
         ph = torch.empty_like(mag) if want_phase else None
         with torch.cuda.device(self.device):

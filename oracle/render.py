@@ -33,8 +33,8 @@ N_BINS = 1 + N_FFT // 2   # 512
 
 
 def n_frames(n_samples: int) -> int:
-    """Frame count of librosa.stft(center=True): 1 + len(y) // hop."""
-    return 1 + n_samples // HOP_LENGTH
+    """Frame count of librosa.stft(center=True) with the odd n_fft = 1023: 1 + (len(y) + 2*511 - 1023) // hop."""
+    return 1 + (n_samples + 2 * (N_FFT // 2) - N_FFT) // HOP_LENGTH
 
 
 def hann_periodic(n_fft: int = N_FFT) -> np.ndarray:

@@ -34,7 +34,7 @@ def test_emulated_kernels_match_golden(case, emu, golden_dir):
     g = np.load(os.path.join(golden_dir, f"render_{name}.npz"))
     monos, rirs, rp, ln = render_case_inputs(K, lens, seed)
     N = monos.shape[1]
-    T = 1 + N // 512
+    T = 1 + (N - 1) // 512
     waves = run_conv(emu, monos, rp, ln)
     want = g["source_waves_i16"]
     d = waves[0].astype(np.int32) - want.astype(np.int32)
@@ -130,3 +130,23 @@ def test_unet_slab_schedule_host_emulation(tmp_path):
                            "-o", exe, os.path.join(root, "tests", "emu", "emu_unet_slab.cu")])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("N", [16384, 5004, 512, 1536])
+def test_emulated_stft_other_lengths(emu, N):
+    # N a multiple of 512 (frame count 1 + (N-1)//512), N not a multiple of 8 (scalar staging path), shortest signals
+    rng = np.random.default_rng(N)
+    K = 3
+    waves = np.round(2000 * rng.standard_normal((1, K, 2, N))).astype(np.int16)
+    T = R.n_frames(N)
+    mix = np.zeros((1, 512, T, 2), np.float32)
+    gt = np.zeros((1, K, 512, T, 2), np.float32)
+    emu.emu_stft_waves(ptr(waves), 1, K, N, K, 0, 0, 1, ptr(mix), None, ptr(gt), 2)
+    mixed = (waves[0].astype(np.float32) * np.float32(1 / 32768)).sum(0) / np.float32(K)
+    for ear in range(2):
+        want = np.abs(R.stft_librosa(mixed[ear]))
+        assert want.shape == (512, T)
+        assert rel_l2(mix[0, :, :, ear], want) < 1e-4 and max_rel(mix[0, :, :, ear], want) < 1e-4
+        for k in range(K):
+            wk = np.abs(R.stft_librosa(waves[0, k, ear].astype(np.float32) * np.float32(1 / 32768)))
+            assert rel_l2(gt[0, k, :, :, ear], wk) < 1e-4
