@@ -205,6 +205,10 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     }
   } else if (warp == 8) {
     // ------------------------------ MMA issuer (convergent warp, one elected lane issues) ------------------------------
+    // Everything the issue path needs is a function of kernel parameters and warp-uniform counters: the item table is read
+    // from the constant bank with uniform indices and the K16 steps of a part are unrolled with immediate descriptor
+    // increments, so that an MMA costs two uniform adds + UTCHMMA (the first version walked a shared-memory list through
+    // per-thread registers: ~45 instructions and several R2UR round trips per MMA, ~300 cycles - the tensor pipe idled).
     if (resident) { ug::mbar_wait(b_full(0), 0); ug::tc_fence_after(); }
     int ss = 0, bs = 0, iter = 0;                 // ring positions of the NEXT slab chunk / weight tile to consume
     uint32_t s_par = 0, b_par = 0;
@@ -213,33 +217,44 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       const int buf = iter & 1;
       if (iter >= 2) { ug::mbar_wait(t_empty(buf), (uint32_t)(((iter >> 1) - 1) & 1)); ug::tc_fence_after(); }
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * L.tile_cols);
-      uint32_t a_lo = 0, b_lo = (b0 >> 4);
-      int cs = 0, cb = 0;                           // stages in use by the current chunk / tile
-      uint4 e1 = mma_smem[0], e2 = mma_smem[1 < L.n_mmas ? 1 : 0];
-#pragma unroll 2
-      for (int j = 0; j < L.n_mmas; ++j) {
-        const uint4 e = e1;                          // entries are fetched two MMAs ahead of their use
-        e1 = e2;
-        e2 = mma_smem[j + 2 < L.n_mmas ? j + 2 : 0];
-        const uint32_t flags = e.w >> 16;
-        if (flags & (US_F_WAIT_SLAB | US_F_WAIT_B)) {
-          if (flags & US_F_WAIT_SLAB) {
-            ug::mbar_wait(s_full(ss), s_par);
-            cs = ss;
-            a_lo = (slab0 + ss * L.slab_bytes) >> 4;
-            if (++ss == NS) { ss = 0; s_par ^= 1u; }
-          }
-          if (flags & US_F_WAIT_B) {
+      int item = 0;
+      for (int c = 0; c < L.n_chunks; ++c) {
+        ug::mbar_wait(s_full(ss), s_par);
+        const int cs = ss;
+        const uint32_t a_base16 = (slab0 + (uint32_t)ss * (uint32_t)L.slab_bytes) >> 4;
+        if (++ss == NS) { ss = 0; s_par ^= 1u; }
+        ug::tc_fence_after();
+        for (; item < L.n_items && L.items[item].chunk == c; ++item) {
+          const USItem& it = L.items[item];
+          int cb = 0;
+          uint32_t b_base16;
+          if (!resident) {
             ug::mbar_wait(b_full(bs), b_par);
             cb = bs;
-            b_lo = (b0 + bs * US_B_STAGE_BYTES) >> 4;
+            b_base16 = (b0 + (uint32_t)bs * US_B_STAGE_BYTES) >> 4;
             if (++bs == NB) { bs = 0; b_par ^= 1u; }
+            ug::tc_fence_after();
+          } else {
+            b_base16 = (b0 >> 4) + (uint32_t)it.w_row * 8u;
           }
-          ug::tc_fence_after();
+          const uint32_t a16 = a_base16 + (uint32_t)it.a_shift * 8u + (uint32_t)it.a_k16 * 2u;
+          for (int p = 0; p < it.n_parts; ++p) {
+            const uint32_t idesc = us::instr_desc_bf16_n(it.part[p].n);
+            const uint32_t d = tmem_d + (uint32_t)it.part[p].tmem_col;
+            const uint32_t b16 = b_base16 + (uint32_t)it.part[p].b_row * 8u;
+            const uint32_t acc0 = it.part[p].init ? 0u : 1u;
+            if (it.n_k16 == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                us::umma_bf16_elect(d, desc_hi | (uint64_t)((a16 + 2u * k) & 0x3FFFu), desc_hi | (uint64_t)((b16 + 2u * k) & 0x3FFFu), idesc, k ? 1u : acc0);
+            } else {
+              for (int k = 0; k < it.n_k16; ++k)
+                us::umma_bf16_elect(d, desc_hi | (uint64_t)((a16 + 2u * k) & 0x3FFFu), desc_hi | (uint64_t)((b16 + 2u * k) & 0x3FFFu), idesc, k ? 1u : acc0);
+            }
+          }
+          if (!resident) us::umma_commit_elect(b_empty(cb));
         }
-        us::umma_bf16_elect(tmem_d + (e.w & 0xFFFFu), desc_hi | (uint64_t)((a_lo + e.x) & 0x3FFFu), desc_hi | (uint64_t)((b_lo + e.y) & 0x3FFFu), e.z, flags & US_F_ACC);
-        if (flags & US_F_COMMIT_B) us::umma_commit_elect(b_empty(cb));
-        if (flags & US_F_COMMIT_SLAB) us::umma_commit_elect(s_empty(cs));
+        us::umma_commit_elect(s_empty(cs));
       }
       us::umma_commit_elect(t_full(buf));
     }
