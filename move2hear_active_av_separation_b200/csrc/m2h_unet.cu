@@ -453,8 +453,10 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
   const size_t positions = (size_t)B * L.PI;
   L.n_tiles = (int)((positions + 127) / 128);
   // weights stay resident in shared memory when they fit next to >= 2 tiles' worth of slab chunks, else they stream through a ring
-  const int budget = kSlabMaxSmem - 1024 - 512 - US_AUX_BYTES;
-  if (w_rows * 128 + 2 * L.n_chunks * L.slab_bytes <= budget) {
+  L.head_bytes = L.out_mode == UG_OUT_HEAD_NCHW_F32 ? US_HEAD_BYTES : 0;
+  const int budget = kSlabMaxSmem - 1024 - 512 - US_AUX_BYTES - L.head_bytes;
+  const int min_stages = L.n_chunks > 2 ? L.n_chunks : 2;         // at least one tile's worth of chunks in flight
+  if (w_rows * 128 + min_stages * L.slab_bytes <= budget) {
     L.n_b_stages = 0;
     L.n_slab_stages = (budget - w_rows * 128) / L.slab_bytes;
   } else {
@@ -462,29 +464,6 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
     L.n_slab_stages = (budget - L.n_b_stages * US_B_STAGE_BYTES) / L.slab_bytes;
   }
   if (L.n_slab_stages > US_MAX_STAGES) L.n_slab_stages = US_MAX_STAGES;
-  // flatten items -> parts -> K16 steps into the MMA list the issuing thread walks
-  L.n_mmas = 0;
-  for (int i = 0; i < L.n_items; ++i) {
-    const USItem& it = L.items[i];
-    const bool first_of_chunk = i == 0 || L.items[i - 1].chunk != it.chunk;
-    const bool last_of_chunk = i + 1 == L.n_items || L.items[i + 1].chunk != it.chunk;
-    for (int p = 0; p < it.n_parts; ++p) {
-      for (int k = 0; k < it.n_k16; ++k) {
-        if (L.n_mmas >= US_MAX_MMAS) { m2h_set_error("slab layer: too many MMAs"); return M2H_ERR_ARG; }
-        USMma& m = L.mmas[L.n_mmas++];
-        const bool first = p == 0 && k == 0, last = p + 1 == it.n_parts && k + 1 == it.n_k16;
-        static int dbg_align = -1;      // timing experiment only: round tap shifts down to whole 8-row swizzle atoms (wrong results)
-        if (dbg_align < 0) { const char* e = getenv("M2H_SLAB_DEBUG_ALIGN"); dbg_align = e ? atoi(e) : 0; }
-        m.a_off16 = (uint32_t)((dbg_align ? (it.a_shift & ~7) : it.a_shift) * 128 + (it.a_k16 + k) * 32) >> 4;
-        m.b_off16 = (uint32_t)(((L.n_b_stages ? 0 : it.w_row) + it.part[p].b_row) * 128 + k * 32) >> 4;
-        m.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(it.part[p].n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        m.tmem_col = (uint16_t)it.part[p].tmem_col;
-        m.flags = (uint16_t)(((!it.part[p].init || k) ? US_F_ACC : 0) | (first && first_of_chunk ? US_F_WAIT_SLAB : 0) |
-                             (first && L.n_b_stages ? US_F_WAIT_B : 0) | (last && L.n_b_stages ? US_F_COMMIT_B : 0) |
-                             (last && last_of_chunk ? US_F_COMMIT_SLAB : 0));
-      }
-    }
-  }
   if (L.n_items > US_MAX_ITEMS || L.slab_rows > 256 || L.n_slab_stages < 2 || L.tmem_cols > 512 || w_rows > 32767) { m2h_set_error("slab layer: unsupported geometry"); return M2H_ERR_ARG; }
   alignas(64) CUtensorMap tm_in, tm_w;
   int rc = make_tmap(&tm_in, in, positions, in_ld, in_ld, L.slab_rows);
@@ -495,7 +474,7 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
   M2H_CUDA_CHECK(cudaGetDevice(&dev));
   M2H_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const unsigned grid = (unsigned)(L.n_tiles < sms ? L.n_tiles : sms);
-  unet_slab_kernel<<<grid, US_THREADS, us::smem_bytes(L.slab_bytes, L.n_slab_stages, L.n_b_stages, w_rows), st>>>(tm_in, tm_w, L);
+  unet_slab_kernel<<<grid, US_THREADS, us::smem_bytes(L.slab_bytes, L.n_slab_stages, L.n_b_stages, w_rows, L.head_bytes), st>>>(tm_in, tm_w, L);
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }
@@ -707,7 +686,7 @@ extern "C" int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2
       sl.out = out_ptr[3]; sl.out_mode = UG_OUT_NHWC_BF16; sl.out_stride = 2; sl.Hop = sl.Wop = 18; sl.out_ld = out_ld[3]; sl.out_coff = 0;
     } else {
       sl.out = mask_out; sl.out_mode = UG_OUT_HEAD_NCHW_F32; sl.n_valid = convert_bin2mono ? 16 : 32;
-      sl.head_w = (const float*)(pk + PL.head_wf); sl.head_b = (const float*)(pk + PL.head_b);
+      sl.head_w = (const __nv_bfloat16*)(pk + PL.head_w); sl.head_b = (const float*)(pk + PL.head_b);
     }
     rc = launch_slab(sl, in_ptr[i], kDecCin[i], hp, B, (const __nv_bfloat16*)(pk + PL.w[i]), st);
     if (rc != M2H_OK) return rc;

@@ -29,7 +29,8 @@
 #define US_MAX_ITEMS 40
 #define US_B_STAGE_BYTES 16384        // up to 128 weight rows x 64 k (bf16)
 #define US_MAX_STAGES 8
-#define US_AUX_BYTES 12288            // head weights (4224 B) | scale, bias | class-plane sums | MMA list
+#define US_AUX_BYTES 4096             // scale, bias (2 x 128 fp32) | class-plane sums (9 x 64 fp32) | head bias (32 fp32)
+#define US_HEAD_BYTES (4096 + 2 * 16384)   // fused 1x1 head: weight tile [32 n][64 k] + one activation tile [128 pos][64 k] per epilogue group
 
 struct USPart { int16_t b_row, n, tmem_col, init; };   // init: first MMA writing these accumulator columns
 struct USItem {                       // one weight tile and the MMAs that consume it
@@ -42,19 +43,8 @@ struct USItem {                       // one weight tile and the MMAs that consu
   USPart part[2];
 };
 
-// One tcgen05.mma, flattened on the host so that the issuing thread only adds bases (a single thread issues every MMA:
-// anything it has to look up or derive per instruction shows up as idle tensor cycles).
-#define US_MAX_MMAS 208
-enum { US_F_ACC = 1, US_F_WAIT_SLAB = 2, US_F_WAIT_B = 4, US_F_COMMIT_B = 8, US_F_COMMIT_SLAB = 16 };
-struct USMma {
-  uint32_t a_off16;                   // (a_shift*128 + k16*32) >> 4, relative to the slab stage
-  uint32_t b_off16;                   // byte offset >> 4 inside the resident weight block / the ring stage
-  uint32_t idesc;                     // instruction descriptor (N of this part)
-  uint16_t tmem_col, flags;
-};
-
 struct USLayer {
-  int n_items, n_chunks, n_tiles, n_mmas;
+  int n_items, n_chunks, n_tiles;
   int slab_rows;                      // 128 + 2*(Wp+1)
   int slab_bytes;                     // slab_rows*128 rounded up to 1024
   int n_slab_stages, n_b_stages;      // ring depths; n_b_stages == 0: weights resident (w_rows*128 B)
@@ -69,10 +59,10 @@ struct USLayer {
   const float* cls; const float* cls_w;           // class-plane term (encoder layer 0)
   void* out; int out_mode;                          // UG_OUT_NHWC_BF16 | UG_OUT_HEAD_NCHW_F32
   int out_stride, Hop, Wop, out_ld, out_coff;       // output pixel (y-1)*out_stride + py + 1 in a haloed [Hop][Wop] grid
-  int n_valid; const float* head_w; const float* head_b;
+  int n_valid; const __nv_bfloat16* head_w; const float* head_b;   // head weights: bf16 [32 n][64 k], zero padded (pack_head_kernel)
+  int head_bytes;                     // US_HEAD_BYTES when the 1x1 head is fused (out_mode == UG_OUT_HEAD_NCHW_F32), else 0
   int desc_base_offset;               // debug: 1 = put (start address >> 7) & 7 into the A descriptor's base-offset field
   USItem items[US_MAX_ITEMS];
-  USMma mmas[US_MAX_MMAS];
 };
 
 namespace us {
@@ -115,9 +105,13 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
       "}" ::"r"(bar) : "memory");
 }
-__host__ __device__ constexpr int smem_bytes(int slab_bytes, int n_slab_stages, int n_b_stages, int w_rows) {
-  return n_slab_stages * slab_bytes + (n_b_stages ? n_b_stages * US_B_STAGE_BYTES : w_rows * 128) + 1024 /*align*/ + 512 /*barriers*/ + US_AUX_BYTES;
+__host__ __device__ constexpr int smem_bytes(int slab_bytes, int n_slab_stages, int n_b_stages, int w_rows, int head_bytes) {
+  return n_slab_stages * slab_bytes + (n_b_stages ? n_b_stages * US_B_STAGE_BYTES : w_rows * 128) + head_bytes + 1024 /*align*/ + 512 /*barriers*/ + US_AUX_BYTES;
 }
+// byte offset of 16-byte chunk c of row r inside a K-major 128B-swizzled tile (8-row atoms of 1024 B)
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace us
 
 __global__ void __launch_bounds__(US_THREADS, 1)
@@ -130,8 +124,10 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   const uint32_t w_bytes = resident ? (uint32_t)L.w_rows * 128u : (uint32_t)L.n_b_stages * US_B_STAGE_BYTES;
   const uint32_t b0 = base;                                   // weights (resident block or ring)
   const uint32_t slab0 = base + w_bytes;
-  const uint32_t bars = slab0 + (uint32_t)L.n_slab_stages * L.slab_bytes;
-  unsigned char* bars_ptr = base_ptr + w_bytes + (size_t)L.n_slab_stages * L.slab_bytes;
+  const uint32_t head0 = slab0 + (uint32_t)L.n_slab_stages * L.slab_bytes;      // head weight tile, then the two activation tiles
+  unsigned char* head_ptr = base_ptr + w_bytes + (size_t)L.n_slab_stages * L.slab_bytes;
+  const uint32_t bars = head0 + (uint32_t)L.head_bytes;
+  unsigned char* bars_ptr = head_ptr + L.head_bytes;
   auto s_full = [&](int s) { return bars + 8u * s; };
   auto s_empty = [&](int s) { return bars + 8u * (US_MAX_STAGES + s); };
   auto b_full = [&](int s) { return bars + 8u * (2 * US_MAX_STAGES + s); };      // slot 0 doubles as "resident weights landed"
@@ -139,10 +135,10 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   auto t_full = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + s); };
   auto t_empty = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 2 + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (4 * US_MAX_STAGES + 4));
-  float* head_smem = reinterpret_cast<float*>(bars_ptr + 512);           // [32][32] weights + [32] bias
-  float* sb_smem = head_smem + 1056;                                      // scale[Cout], bias[Cout]
+  auto h_done = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 5 + s); };   // head MMAs of epilogue group s have completed
+  float* sb_smem = reinterpret_cast<float*>(bars_ptr + 512);             // scale[Cout], bias[Cout]
   float* cls_smem = sb_smem + 2 * 128;                                    // [9][Cout]
-  uint4* mma_smem = reinterpret_cast<uint4*>(bars_ptr + 512 + 8192);     // copy of L.mmas (constant-bank loads cost ~100+ cycles each)
+  float* hb_smem = cls_smem + 9 * 64;                                     // head bias [32]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role code stays on the uniform datapath
@@ -151,15 +147,20 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     for (int s = 0; s < US_MAX_STAGES; ++s) {
       ug::mbar_init(s_full(s), 1); ug::mbar_init(s_empty(s), 1); ug::mbar_init(b_full(s), 1); ug::mbar_init(b_empty(s), 1);
     }
-    for (int s = 0; s < 2; ++s) { ug::mbar_init(t_full(s), 1); ug::mbar_init(t_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) { ug::mbar_init(t_full(s), 1); ug::mbar_init(t_empty(s), 4); ug::mbar_init(h_done(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (L.out_mode == UG_OUT_HEAD_NCHW_F32)
-    for (int i = tid; i < 32 * 32 + 32; i += US_THREADS) head_smem[i] = i < 1024 ? L.head_w[i] : L.head_b[i - 1024];
+  if (L.out_mode == UG_OUT_HEAD_NCHW_F32) {
+    // head weights [32 n][64 k] bf16 -> K-major 128B-swizzled operand tile (written by threads: made visible to the tensor
+    // core's async proxy before the barrier below)
+    for (int i = tid; i < 32 * 8; i += US_THREADS)
+      *reinterpret_cast<uint4*>(head_ptr + us::sw128_off(i >> 3, i & 7)) = reinterpret_cast<const uint4*>(L.head_w)[i];
+    if (tid < 32) hb_smem[tid] = L.head_b[tid];
+    us::fence_async_smem();
+  }
   for (int i = tid; i < L.Cout; i += US_THREADS) { sb_smem[i] = L.scale ? L.scale[i] : 1.f; sb_smem[128 + i] = L.bias ? L.bias[i] : 0.f; }
   if (L.cls != nullptr)
     for (int i = tid; i < 9 * L.Cout; i += US_THREADS) cls_smem[i] = L.cls_w[i];
-  for (int i = tid; i < L.n_mmas; i += US_THREADS) mma_smem[i] = *reinterpret_cast<const uint4*>(&L.mmas[i]);
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ug::smem_u32(tmem_slot)), "r"((uint32_t)L.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -310,52 +311,79 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         __syncwarp();
         if (lane == 0) ug::mbar_arrive(t_empty(grp));
       } else {
-        // last up-conv (Cout = 32) + BN + ReLU, then the 1x1 head z = head_b + head_w y (separator_cnn.py:135) on the
-        // activated pixel (operands rounded to bf16 like the unfused layer pair); fp32 NCHW store [B][n_valid][Hm][Wm],
-        // the two x-phases of a pixel pair go out as one float2
+        // last up-conv (Cout = 32) + BN + ReLU, then the 1x1 head z = head_b + head_w y (separator_cnn.py:135) as a second
+        // tcgen05.mma: the activated pixels (bf16, like the unfused layer pair) of two sub-pixel phases form one K-major
+        // [128 positions][2 x 32 channels] operand tile in shared memory; four MMAs (2 phases x 2 K16 steps, N = 32) write
+        // z over the accumulator columns the group has just read.  Two rounds (phases 0-1, 2-3) share the tile.
+        // (On CUDA cores the head cost 4096 FMAs per position: the epilogue, not the tensor pipe, bounded this layer.)
         const int Hm = (L.Hp - 2) * 2, Wm = (L.Wp - 2) * 2;
-        float yv[4][32];
+        const uint32_t ytile = head0 + 4096u + (uint32_t)grp * 16384u;
+        unsigned char* yrow = head_ptr + 4096 + grp * 16384;
+        const uint32_t tcol = tmem_base + (uint32_t)(grp * L.tile_cols);
+        const uint64_t desc_hi = ug::smem_desc_sw128(0);
+        const uint32_t idesc = us::instr_desc_bf16_n(32);
+        uint32_t hpar = 0;                                      // every tile of a group consumes exactly two phases of its barrier
+        uint32_t pk[2][16];
 #pragma unroll
-        for (int ph = 0; ph < 4; ++ph) {
-          uint32_t v[32];
-          ug::tmem_ld32(trow + (uint32_t)(ph * 32), v);
+        for (int rd = 0; rd < 2; ++rd) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = fmaf(__uint_as_float(v[i]), sb_smem[i], sb_smem[128 + i]);
-            a = a > 0.f ? a : a * L.slope;
-            yv[ph][i] = __bfloat162float(__float2bfloat16_rn(a));
+          for (int pl = 0; pl < 2; ++pl) {
+            uint32_t v[32];
+            ug::tmem_ld32(trow + (uint32_t)((rd * 2 + pl) * 32), v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float a0 = fmaf(__uint_as_float(v[i]), sb_smem[i], sb_smem[128 + i]);
+              float a1 = fmaf(__uint_as_float(v[i + 1]), sb_smem[i + 1], sb_smem[128 + i + 1]);
+              a0 = a0 > 0.f ? a0 : a0 * L.slope;
+              a1 = a1 > 0.f ? a1 : a1 * L.slope;
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(a0, a1);
+              pk[pl][i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+          }
+          if (rd == 1) {      // the tile still feeds the first round's MMAs
+            ug::mbar_wait(h_done(grp), hpar);
+            hpar ^= 1u;
+          }
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(yrow + us::sw128_off(row, pl * 4 + c)) = make_uint4(pk[pl][4 * c], pk[pl][4 * c + 1], pk[pl][4 * c + 2], pk[pl][4 * c + 3]);
+          us::fence_async_smem();
+          ug::tc_fence_before();
+          us::group_sync(1 + grp);
+          if (wq == 0) {
+            ug::tc_fence_after();
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                us::umma_bf16_elect(tcol + (uint32_t)((rd * 2 + pl) * 32), desc_hi | (uint64_t)(((ytile + pl * 64 + k * 32) >> 4) & 0x3FFFu),
+                                    desc_hi | (uint64_t)(((head0 + k * 32) >> 4) & 0x3FFFu), idesc, (uint32_t)k);
+            us::umma_commit_elect(h_done(grp));
+          }
+        }
+        ug::mbar_wait(h_done(grp), hpar);
+        ug::tc_fence_after();
+        float* o = reinterpret_cast<float*>(L.out) + ((size_t)b * L.n_valid * Hm + (size_t)((y - 1) * 2)) * Wm + (x - 1) * 2;
+#pragma unroll
+        for (int rd = 0; rd < 2; ++rd) {
+          uint32_t z0[32], z1[32];
+          ug::tmem_ld32(trow + (uint32_t)(rd * 64), z0);
+          ug::tmem_ld32(trow + (uint32_t)(rd * 64 + 32), z1);
+          if (ok) {
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+              if (n < L.n_valid) {
+                const float hb = hb_smem[n];
+                *reinterpret_cast<float2*>(o + (size_t)n * Hm * Wm + rd * Wm) = make_float2(__uint_as_float(z0[n]) + hb, __uint_as_float(z1[n]) + hb);
+              }
+            }
           }
         }
         ug::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ug::mbar_arrive(t_empty(grp));       // accumulators are in registers: the MMA warp may reuse the buffer
-        if (ok) {
-          float* o = reinterpret_cast<float*>(L.out) + ((size_t)b * L.n_valid * Hm + (size_t)((y - 1) * 2)) * Wm + (x - 1) * 2;
-#pragma unroll 1
-          for (int n4 = 0; n4 < L.n_valid; n4 += 4) {
-            float z[4][4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int ph = 0; ph < 4; ++ph) z[ph][u] = head_smem[1024 + n4 + u];
-#pragma unroll
-            for (int c4 = 0; c4 < 32; c4 += 4) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float4 w4 = *reinterpret_cast<const float4*>(head_smem + (n4 + u) * 32 + c4);
-#pragma unroll
-                for (int ph = 0; ph < 4; ++ph)
-                  z[ph][u] = fmaf(w4.x, yv[ph][c4], fmaf(w4.y, yv[ph][c4 + 1], fmaf(w4.z, yv[ph][c4 + 2], fmaf(w4.w, yv[ph][c4 + 3], z[ph][u]))));
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float* on = o + (size_t)(n4 + u) * Hm * Wm;
-              *reinterpret_cast<float2*>(on) = make_float2(z[0][u], z[1][u]);
-              *reinterpret_cast<float2*>(on + Wm) = make_float2(z[2][u], z[3][u]);
-            }
-          }
-        }
+        if (lane == 0) ug::mbar_arrive(t_empty(grp));
       }
     }
   }
