@@ -464,6 +464,23 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
     L.n_slab_stages = (budget - L.n_b_stages * US_B_STAGE_BYTES) / L.slab_bytes;
   }
   if (L.n_slab_stages > US_MAX_STAGES) L.n_slab_stages = US_MAX_STAGES;
+  // issue records (unet_slab.cuh::USIssue): what the MMA-issuing warp reads, one item ahead of its use
+  for (int i = 0; i < L.n_items; ++i) {
+    const USItem& it = L.items[i];
+    USIssue& r = L.rec[i];
+    memset(&r, 0, sizeof(r));
+    if (it.n_k16 != 2 && it.n_k16 != 4) { m2h_set_error("slab layer: unsupported K16 count %d", (int)it.n_k16); return M2H_ERR_ARG; }
+    const bool first_of_chunk = i == 0 || L.items[i - 1].chunk != it.chunk;
+    const bool last_of_chunk = i + 1 == L.n_items || L.items[i + 1].chunk != it.chunk;
+    r.a_off16 = (uint32_t)(it.a_shift * 128 + it.a_k16 * 32) >> 4;
+    r.b_off16 = L.n_b_stages ? 0u : (uint32_t)(it.w_row * 128) >> 4;
+    r.ctl = (uint32_t)it.n_k16 | ((uint32_t)it.n_parts << 8) | (first_of_chunk ? 1u << 16 : 0u) | (last_of_chunk ? 1u << 17 : 0u);
+    for (int p = 0; p < it.n_parts; ++p) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(it.part[p].n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t pw = (uint32_t)it.part[p].tmem_col | ((uint32_t)(it.part[p].b_row * 8) << 16) | (it.part[p].init ? 0u : 1u << 31);
+      if (p == 0) { r.idesc0 = idesc; r.p0 = pw; } else { r.idesc1 = idesc; r.p1 = pw; }
+    }
+  }
   if (L.n_items > US_MAX_ITEMS || L.slab_rows > 256 || L.n_slab_stages < 2 || L.tmem_cols > 512 || w_rows > 32767) { m2h_set_error("slab layer: unsupported geometry"); return M2H_ERR_ARG; }
   alignas(64) CUtensorMap tm_in, tm_w;
   int rc = make_tmap(&tm_in, in, positions, in_ld, in_ld, L.slab_rows);

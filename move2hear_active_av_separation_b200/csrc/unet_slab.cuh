@@ -43,6 +43,16 @@ struct USItem {                       // one weight tile and the MMAs that consu
   USPart part[2];
 };
 
+// Issue record of an item: everything the MMA-issuing warp needs, pre-combined on the host into eight 32-bit words so that
+// one record is two 16-byte constant-bank loads into uniform registers (fetched one item ahead of its use).
+struct alignas(32) USIssue {
+  uint32_t a_off16;                   // (a_shift*128 + a_k16*32) >> 4, relative to the slab stage
+  uint32_t b_off16;                   // resident weights: (w_row*128) >> 4; streamed: 0 (relative to the ring stage)
+  uint32_t ctl;                       // n_k16 | n_parts << 8 | first_of_chunk << 16 | last_of_chunk << 17
+  uint32_t pad;
+  uint32_t idesc0, p0;                // part 0: instruction descriptor; tmem_col | (b_row*8) << 16 | accumulate-from-start << 31
+  uint32_t idesc1, p1;                // part 1
+};
 struct USLayer {
   int n_items, n_chunks, n_tiles;
   int slab_rows;                      // 128 + 2*(Wp+1)
@@ -63,6 +73,7 @@ struct USLayer {
   int head_bytes;                     // US_HEAD_BYTES when the 1x1 head is fused (out_mode == UG_OUT_HEAD_NCHW_F32), else 0
   int desc_base_offset;               // debug: 1 = put (start address >> 7) & 7 into the A descriptor's base-offset field
   USItem items[US_MAX_ITEMS];
+  USIssue rec[US_MAX_ITEMS];
 };
 
 namespace us {
@@ -218,44 +229,54 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       const int buf = iter & 1;
       if (iter >= 2) { ug::mbar_wait(t_empty(buf), (uint32_t)(((iter >> 1) - 1) & 1)); ug::tc_fence_after(); }
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * L.tile_cols);
-      int item = 0;
-      for (int c = 0; c < L.n_chunks; ++c) {
-        ug::mbar_wait(s_full(ss), s_par);
-        const int cs = ss;
-        const uint32_t a_base16 = (slab0 + (uint32_t)ss * (uint32_t)L.slab_bytes) >> 4;
-        if (++ss == NS) { ss = 0; s_par ^= 1u; }
-        ug::tc_fence_after();
-        for (; item < L.n_items && L.items[item].chunk == c; ++item) {
-          const USItem& it = L.items[item];
-          int cb = 0;
-          uint32_t b_base16;
-          if (!resident) {
-            ug::mbar_wait(b_full(bs), b_par);
-            cb = bs;
-            b_base16 = (b0 + (uint32_t)bs * US_B_STAGE_BYTES) >> 4;
-            if (++bs == NB) { bs = 0; b_par ^= 1u; }
-            ug::tc_fence_after();
-          } else {
-            b_base16 = (b0 >> 4) + (uint32_t)it.w_row * 8u;
-          }
-          const uint32_t a16 = a_base16 + (uint32_t)it.a_shift * 8u + (uint32_t)it.a_k16 * 2u;
-          for (int p = 0; p < it.n_parts; ++p) {
-            const uint32_t idesc = us::instr_desc_bf16_n(it.part[p].n);
-            const uint32_t d = tmem_d + (uint32_t)it.part[p].tmem_col;
-            const uint32_t b16 = b_base16 + (uint32_t)it.part[p].b_row * 8u;
-            const uint32_t acc0 = it.part[p].init ? 0u : 1u;
-            if (it.n_k16 == 4) {
+      int cs = 0;
+      uint32_t a_base16 = 0;
+      uint4 ra = *reinterpret_cast<const uint4*>(&L.rec[0]), rb = *(reinterpret_cast<const uint4*>(&L.rec[0]) + 1);
+      for (int item = 0; item < L.n_items; ++item) {
+        const uint4 ca = ra, cbw = rb;
+        if (item + 1 < L.n_items) {       // next record: its constant-bank latency hides behind this item's MMAs
+          ra = *reinterpret_cast<const uint4*>(&L.rec[item + 1]);
+          rb = *(reinterpret_cast<const uint4*>(&L.rec[item + 1]) + 1);
+        }
+        const uint32_t ctl = ca.z;
+        if (ctl & (1u << 16)) {           // first item of a chunk: its slab must have landed
+          ug::mbar_wait(s_full(ss), s_par);
+          cs = ss;
+          a_base16 = (slab0 + (uint32_t)ss * (uint32_t)L.slab_bytes) >> 4;
+          if (++ss == NS) { ss = 0; s_par ^= 1u; }
+          ug::tc_fence_after();
+        }
+        int cb = 0;
+        uint32_t b_base16 = (b0 >> 4) + ca.y;
+        if (!resident) {
+          ug::mbar_wait(b_full(bs), b_par);
+          cb = bs;
+          b_base16 = (b0 + (uint32_t)bs * US_B_STAGE_BYTES) >> 4;
+          if (++bs == NB) { bs = 0; b_par ^= 1u; }
+          ug::tc_fence_after();
+        }
+        const uint32_t a16 = a_base16 + ca.x;
+        const uint32_t nk = ctl & 0xffu, np = (ctl >> 8) & 0xffu;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          if (p < (int)np) {
+            const uint32_t idesc = p ? cbw.z : cbw.x, pw = p ? cbw.w : cbw.y;
+            const uint32_t d = tmem_d + (pw & 0xffffu);
+            const uint32_t b16 = b_base16 + ((pw >> 16) & 0x7fffu);
+            const uint32_t acc0 = pw >> 31;
+            if (nk == 4) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 us::umma_bf16_elect(d, desc_hi | (uint64_t)((a16 + 2u * k) & 0x3FFFu), desc_hi | (uint64_t)((b16 + 2u * k) & 0x3FFFu), idesc, k ? 1u : acc0);
             } else {
-              for (int k = 0; k < it.n_k16; ++k)
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
                 us::umma_bf16_elect(d, desc_hi | (uint64_t)((a16 + 2u * k) & 0x3FFFu), desc_hi | (uint64_t)((b16 + 2u * k) & 0x3FFFu), idesc, k ? 1u : acc0);
             }
           }
-          if (!resident) us::umma_commit_elect(b_empty(cb));
         }
-        us::umma_commit_elect(s_empty(cs));
+        if (!resident) us::umma_commit_elect(b_empty(cb));
+        if (ctl & (1u << 17)) us::umma_commit_elect(s_empty(cs));
       }
       us::umma_commit_elect(t_full(buf));
     }
