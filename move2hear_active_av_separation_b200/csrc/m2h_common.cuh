@@ -21,6 +21,7 @@
   #define M2H_HD static inline
   #define M2H_FOR_THREADS(tid, nthreads) for (int tid = 0; tid < (nthreads); ++tid)
   #define M2H_SYNC() do {} while (0)
+  #define M2H_SYNC_GROUP128() do {} while (0)
   #define M2H_UNROLL
   #define M2H_RESTRICT
   M2H_DEV float m2h_rintf(float v) { return nearbyintf(v); }
@@ -40,6 +41,9 @@
   #define M2H_HD __host__ __device__ __forceinline__
   #define M2H_FOR_THREADS(tid, nthreads) for (int tid = threadIdx.x, m2h_once_ = 1; m2h_once_; m2h_once_ = 0)
   #define M2H_SYNC() __syncthreads()
+  // named barrier of the 128-thread group a thread belongs to (ids 1..): groups of a CTA that work on independent data
+  // drift apart instead of meeting at every phase boundary
+  #define M2H_SYNC_GROUP128() asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory")
   #define M2H_UNROLL _Pragma("unroll")
   #define M2H_RESTRICT __restrict__
   M2H_DEV float m2h_rintf(float v) { return rintf(v); }

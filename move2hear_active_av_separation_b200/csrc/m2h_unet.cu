@@ -603,8 +603,8 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
   const EncLayout PL = enc_layout();
   const char* pk = (const char*)packed_enc;
 
-  rc = m2h_unet_workspace_clear_halos(B, workspace, workspace_bytes, stream);
-  if (rc != M2H_OK) return rc;
+  // the workspace's zero borders are the caller's contract (m2h_unet_workspace_clear_halos once per allocation): every
+  // kernel below writes interiors only
   PackInParams pp;
   pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.x0; pp.B = B; pp.x0_plain = nullptr;
   for (int i = 0; i < 4; ++i) pp.ms[i] = convert_bin2mono ? (long long)mask_strides[i] : 0;

@@ -274,18 +274,19 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
     for (int t0 = 0; t0 < P.T; t0 += M2H_STFT_GROUPS) {
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_stage(P, s, tid, b, sig, t0);
       M2H_SYNC();
+      // each 128-thread group owns one frame pair and its buffer: only the group meets between the passes
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p1(P, s, gt, tid, b, sig, t0);
-      M2H_SYNC();
+      M2H_SYNC();      // CTA-wide: the staged samples may be rewritten (next t0) as soon as every group is past its P1
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p2(P, s, gt, tid, t0);
-      M2H_SYNC();
+      M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p3(P, s, gt, tid, t0);
-      M2H_SYNC();
+      M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p4(P, s, tid, t0);
-      M2H_SYNC();
+      M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p5(P, s, gt, tid, t0);
-      M2H_SYNC();
+      M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p6(P, s, tid, b, sig, t0);
-      M2H_SYNC();
+      // no barrier: the next staging pass touches neither buffer, and the CTA barrier after it orders P6 before the next P1
     }
   }
 }

@@ -73,6 +73,42 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
+class _Lease:
+    """Held by the tensors a forward pass returns; its death tells the pool that their workspace may be reused."""
+    __slots__ = ("__weakref__",)
+
+
+class _WorkspacePool:
+    """Per-module cache of activation workspaces.
+
+    A workspace (0.29 MB per sample) is reused by the next forward pass once every tensor returned from the previous pass
+    that used it has been released; otherwise a new one is allocated, so results keep the reference's value semantics.
+    Reuse matters because a workspace's zero borders are written once, not per call (43 us per 1024 samples).
+    """
+
+    def __init__(self, max_items: int = 8):
+        self.items = []
+        self.max_items = max_items
+
+    def acquire(self, B: int, device):
+        """A workspace is only handed out again on the CUDA stream that used it last (stream order = safe reuse: the
+        previous pass's kernels may still be running when its Python results are released)."""
+        import weakref
+        lease = _Lease()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        for ent in self.items:
+            ws, ref = ent
+            if ws.B == B and ws.buf.device == device and ws.stream == stream and ref() is None:
+                ent[1] = weakref.ref(lease)
+                return ws, lease
+        if len(self.items) >= self.max_items:
+            self.items = [e for e in self.items if e[1]() is not None][-(self.max_items - 1):]
+        ws = _Workspace(B, device)
+        ws.stream = stream
+        self.items.append([ws, weakref.ref(lease)])
+        return ws, lease
+
+
 class _Workspace:
     """bf16 NHWC activations of one encoder/decoder pass (skip connections included)."""
 
@@ -84,6 +120,8 @@ class _Workspace:
         offs = (ctypes.c_size_t * 7)()
         _lib.check(lib.m2h_unet_workspace_layout(B, offs), "m2h_unet_workspace_layout")
         self.offsets = list(offs)
+        # the kernels only ever write interiors: the zero borders (= the convolutions' padding) are established once
+        self.clear_halos()
 
     def view(self, idx: int, shape):
         """Logical (un-haloed) view of slot ``idx``: ``(B, H, W, C)`` feature map or the ``(B, 512)`` bottleneck."""
@@ -403,7 +441,9 @@ class PassiveSepEncCNN(_PackedModule):
         if self.training:
             return self._forward_train(obs, observations, masks, B, device)
         packed = self._pack(device)
-        ws = _Workspace(B, device)
+        if getattr(self, "_ws_pool", None) is None:
+            self._ws_pool = _WorkspacePool()
+        ws, lease = self._ws_pool.acquire(B, device)
         bott = torch.empty((B, 512), dtype=torch.float32, device=device)
         cls_ptr = mask_ptr = strides = None
         keep = []
@@ -425,6 +465,9 @@ class PassiveSepEncCNN(_PackedModule):
         _lib.check(rc, "m2h_unet_encoder_forward")
         skips = ws.skips()
         bott._m2h_ws = ws                              # lets the partner decoder reuse the activations in place
+        bott._m2h_lease = lease
+        for t in skips:
+            t._m2h_lease = lease
         return bott, skips
 
 
@@ -517,7 +560,6 @@ class PassiveSepDecCNN(_PackedModule):
         if ws is None or ws.B != B or ws.buf.device != device:
             # features did not come straight from the partner encoder: stage them (layout/dtype copies only)
             ws = _Workspace(B, device)
-            ws.clear_halos()
             ws.view(5, (B, 512)).copy_(bottleneck_feats.reshape(B, 512))
             for idx, feat, (hw, c) in zip((4, 3, 2, 1), lst_skip_feats, ((2, 512), (4, 256), (8, 128), (16, 64))):
                 ws.view(idx, (B, hw, hw, 2 * c))[..., c:].copy_(feat.permute(0, 2, 3, 1))

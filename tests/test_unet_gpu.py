@@ -137,3 +137,30 @@ def test_no_fallbacks():
         PassiveSepEncCNN().train()({"mixed_bin_audio_mag": obs, "target_class": tc})
     with pytest.raises(M2HError):           # train mode updates fp32 running statistics in place: half-precision modules are refused
         PassiveSepEncCNN().cuda().half().train()({"mixed_bin_audio_mag": obs.cuda(), "target_class": tc.cuda()})
+
+
+def test_workspace_pool_keeps_value_semantics():
+    """Workspaces are reused (their zero borders are written once), but never while a previous result is alive."""
+    enc, dec, _, _ = build(False, 11)
+    obs_a, tc_a = unet_case_inputs(5, seed=21)
+    obs_b, tc_b = unet_case_inputs(5, seed=22)
+    with torch.no_grad():
+        bott_a, skips_a = enc({"mixed_bin_audio_mag": obs_a.cuda(), "target_class": tc_a.cuda()})
+        keep = [s.clone() for s in skips_a]
+        ptr_a = bott_a._m2h_ws.buf.data_ptr()
+        bott_b, skips_b = enc({"mixed_bin_audio_mag": obs_b.cuda(), "target_class": tc_b.cuda()})    # a's outputs are alive
+        assert bott_b._m2h_ws.buf.data_ptr() != ptr_a
+        for s, k in zip(skips_a, keep):
+            assert torch.equal(s, k)
+        mask_a = dec(bott_a, skips_a).clone()
+        mask_b = dec(bott_b, skips_b).clone()
+        del bott_a, skips_a, bott_b, skips_b, s
+        # both workspaces are free again: the next passes reuse them and reproduce the results bit for bit
+        for _ in range(3):
+            bott, skips = enc({"mixed_bin_audio_mag": obs_a.cuda(), "target_class": tc_a.cuda()})
+            assert len(enc._ws_pool.items) == 2
+            assert torch.equal(dec(bott, skips), mask_a)
+            del bott, skips
+            bott, skips = enc({"mixed_bin_audio_mag": obs_b.cuda(), "target_class": tc_b.cuda()})
+            assert torch.equal(dec(bott, skips), mask_b)
+            del bott, skips
