@@ -43,7 +43,16 @@
   #define M2H_SYNC() __syncthreads()
   // named barrier of the 128-thread group a thread belongs to (ids 1..): groups of a CTA that work on independent data
   // drift apart instead of meeting at every phase boundary
-  #define M2H_SYNC_GROUP128() asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory")
+  // (immediate ids: with a register operand ptxas reserves all 16 barriers of the CTA)
+  __device__ __forceinline__ void m2h_sync_group128() {
+    switch (threadIdx.x >> 7) {
+      case 0: asm volatile("bar.sync 1, 128;" ::: "memory"); break;
+      case 1: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
+      case 2: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
+      default: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
+    }
+  }
+  #define M2H_SYNC_GROUP128() m2h_sync_group128()
   #define M2H_UNROLL _Pragma("unroll")
   #define M2H_RESTRICT __restrict__
   M2H_DEV float m2h_rintf(float v) { return rintf(v); }

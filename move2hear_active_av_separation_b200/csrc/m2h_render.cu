@@ -59,11 +59,12 @@ m2h_rir_conv_kernel(const ConvParams P, const M2hConvTables* __restrict__ tab) {
 }
 
 // 64 registers / thread (no spills): two 512-thread CTAs per SM, 2 x 86 KB of shared memory
+template <bool F16>
 __global__ void __launch_bounds__(M2H_STFT_THREADS, 2)
 m2h_stft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
-  stft_cta_body(P, s, tab, blockIdx.x, gridDim.x);
+  stft_cta_body<F16>(P, s, tab, blockIdx.x, gridDim.x);
 }
 
 extern "C" int m2h_init(int device) {
@@ -85,9 +86,11 @@ extern "C" int m2h_init(int device) {
   M2H_CUDA_CHECK(cudaMemcpy(d.stft, &hs, sizeof(hs), cudaMemcpyHostToDevice));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
-  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
   // the driver's default carve-out (102 KB, ncu r1b) left room for ONE STFT CTA per SM: ask for the maximum
-  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaSetDevice(prev));
@@ -136,7 +139,12 @@ static int launch_stft(const StftParams& P, int dev, void* stream) {
   if (n_items == 0) return M2H_OK;
   int grid = 2 * g_tables[dev].n_sms;           // 110 KB of shared memory per CTA -> two CTAs per SM
   if (grid > n_items) grid = n_items;
-  m2h_stft_kernel<<<grid, M2H_STFT_THREADS, sizeof(StftSmem), (cudaStream_t)stream>>>(P, g_tables[dev].stft);
+  // outputs are written as (left, right) pairs
+  const void* outs[5] = {P.mix_mag, P.mix_phase, P.gt_mag, P.f_mag, P.f_phase};
+  for (int i = 0; i < 5; ++i)
+    if (((uintptr_t)outs[i] & 7) != 0) { m2h_set_error("stft: output buffers must be 8-byte aligned"); return M2H_ERR_ARG; }
+  if (P.flags & M2H_OUT_F16) m2h_stft_kernel<true><<<grid, M2H_STFT_THREADS, sizeof(StftSmem), (cudaStream_t)stream>>>(P, g_tables[dev].stft);
+  else m2h_stft_kernel<false><<<grid, M2H_STFT_THREADS, sizeof(StftSmem), (cudaStream_t)stream>>>(P, g_tables[dev].stft);
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }

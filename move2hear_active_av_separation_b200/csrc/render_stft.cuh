@@ -48,13 +48,14 @@ struct StftParams {
   void* f_phase;           // fwave mode: [B, 512, T, C] fp32 or null
 };
 
-// samples [512*t0 - 512, 512*t0 + 2048) cover the four frames t0 .. t0+3 (reflection at either end maps back inside)
-#define M2H_STFT_STAGE 2560
 struct StftSmem {
   float2 buf[M2H_STFT_GROUPS][M2H_STFT_BUF];
   float2 bf[2048];          // chirp spectrum, [k3][k1*16+k2] so that consecutive threads read consecutive entries
-  float2 stage[M2H_STFT_STAGE];   // (left, right) samples of the signal being transformed, exactly the reference's fp32 values
 };
+// The samples [512*t - 512, 512*t + 512) of a frame (reflection at either end of the signal maps back inside this window) are
+// staged in the group's own FFT buffer before the first pass: sample j of the window lives at STFT_STAGE_POS(j); the
+// two pad slots per 8 samples keep the 16-byte staging stores of neighbouring threads on distinct banks.
+#define M2H_STFT_STAGE_POS(j) ((j) + (((j) >> 3) << 1))
 #define M2H_STFT_TW(t, which, tid) m2h_ldg2(&(t)->thr[which][(tid) & 127])
 
 M2H_DEV int stft_reflect(int i, int N) { return i < 0 ? -i : (i >= N ? 2 * (N - 1) - i : i); }
@@ -93,12 +94,16 @@ M2H_DEV void stft_acc8(int (&acc)[8], const int16_t* p) {
     acc[2 * u + 1] += (int)(int16_t)(q.w[u] >> 16);
   }
 }
-// P0: stage the samples the four frames t0 .. t0+3 touch.  Rows that allow it are read as 8 x int16 vectors.
+// P0: each 128-thread group stages the 1024-sample window of its own frame (the mixture is formed here, in exactly the
+// reference's fp32 arithmetic).  Rows that allow it are read as 8 x int16 vectors: one vector per thread and row.
 M2H_DEV void stft_stage(const StftParams& P, StftSmem& s, int tid, int b, int sig, int t0) {
-  const int i0 = M2H_HOP * t0 - M2H_HOP;
+  const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
+  if (t >= P.T) return;
+  const int i0 = M2H_HOP * t - M2H_HOP;
+  float2* st = s.buf[grp];
   if (P.waves && (P.N & 7) == 0 && ((uintptr_t)P.waves & 15) == 0) {
-    const int i = i0 + 8 * tid;
-    if (tid < M2H_STFT_STAGE / 8 && i >= 0 && i < P.N) {
+    const int i = i0 + 8 * lt;
+    if (i >= 0 && i < P.N) {
       const int16_t* w = P.waves + (size_t)b * P.K * 2 * P.N + i;
       int al[8], ar[8];
       M2H_UNROLL for (int u = 0; u < 8; ++u) { al[u] = 0; ar[u] = 0; }
@@ -107,13 +112,15 @@ M2H_DEV void stft_stage(const StftParams& P, StftSmem& s, int tid, int b, int si
         stft_acc8(al, w + (size_t)(2 * k) * P.N);
         stft_acc8(ar, w + (size_t)(2 * k + 1) * P.N);
       }
-      M2H_UNROLL for (int u = 0; u < 8; ++u)
-        s.stage[8 * tid + u] = make_float2(stft_scale(al[u], P.K, sig == 0), stft_scale(ar[u], P.K, sig == 0));
+      float4* dst = reinterpret_cast<float4*>(st + M2H_STFT_STAGE_POS(8 * lt));      // 10 float2 per 8 samples: 16-byte aligned
+      M2H_UNROLL for (int u = 0; u < 8; u += 2)
+        dst[u >> 1] = make_float4(stft_scale(al[u], P.K, sig == 0), stft_scale(ar[u], P.K, sig == 0),
+                                  stft_scale(al[u + 1], P.K, sig == 0), stft_scale(ar[u + 1], P.K, sig == 0));
     }
   } else {
-    for (int j = tid; j < M2H_STFT_STAGE; j += M2H_STFT_THREADS) {
+    for (int j = lt; j < 2 * M2H_HOP; j += 128) {
       const int i = i0 + j;
-      if (i >= 0 && i < P.N) s.stage[j] = stft_sample(P, b, sig, i);
+      if (i >= 0 && i < P.N) st[M2H_STFT_STAGE_POS(j)] = stft_sample(P, b, sig, i);
     }
   }
 }
@@ -122,19 +129,37 @@ M2H_DEV void stft_stage(const StftParams& P, StftSmem& s, int tid, int b, int si
 M2H_DEV float stft_log1p_f16(float mag) {    // np.log1p on a float16 array: computed in fp32, rounded to fp16
   return __half2float(__float2half_rn(log1pf(__half2float(__float2half_rn(mag)))));
 }
-M2H_DEV void stft_store(void* base, size_t idx, float v, bool f16) {
-  if (f16) ((__half*)base)[idx] = __float2half_rn(v); else ((float*)base)[idx] = v;
+// two adjacent outputs (left, right ear) as one store; idx is even and the buffers are 8-byte aligned (checked on the host)
+template <bool F16> M2H_DEV void stft_store2(void* base, size_t idx, float a, float b) {
+  if (F16) *reinterpret_cast<__half2*>((__half*)base + idx) = __floats2half2_rn(a, b);
+  else *reinterpret_cast<float2*>((float*)base + idx) = make_float2(a, b);
+}
+// fp32 outputs (tolerance 1e-4 normwise): |x| from the approximate square root (2 ulp) and log1p(m) = log(u) - ((u-1) - m)/u,
+// u = fl(1+m), with the hardware logarithm (absolute error ~5e-7).  The fp16 observation keeps the exact library functions:
+// it is compared bit for bit.
+template <bool F16> M2H_DEV float stft_abs(float2 x) {
+  const float q = x.x * x.x + x.y * x.y;
+  if (F16) return sqrtf(q);
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
+  return r;
+}
+M2H_DEV float stft_log1p_fast(float m) {
+  const float u = 1.0f + m;
+  return __logf(u) - __fdividef((u - 1.0f) - m, u);
 }
 #else
 float m2h_emu_round_f16(float v);            // provided by the emulation harness (numpy-free fp16 rounding)
 M2H_DEV float stft_log1p_f16(float mag) { return m2h_emu_round_f16(log1pf(m2h_emu_round_f16(mag))); }
 void m2h_emu_store(void* base, size_t idx, float v, bool f16);
-M2H_DEV void stft_store(void* base, size_t idx, float v, bool f16) { m2h_emu_store(base, idx, v, f16); }
+template <bool F16> M2H_DEV void stft_store2(void* base, size_t idx, float a, float b) { m2h_emu_store(base, idx, a, F16); m2h_emu_store(base, idx + 1, b, F16); }
+template <bool F16> M2H_DEV float stft_abs(float2 x) { return sqrtf(x.x * x.x + x.y * x.y); }
+M2H_DEV float stft_log1p_fast(float m) { return log1pf(m); }
 #endif
 
+template <bool F16>
 M2H_DEV void stft_emit(const StftParams& P, int b, int sig, int k, int t, float2 xl, float2 xr) {
-  const bool f16 = (P.flags & M2H_OUT_F16) != 0;
-  const float ml = sqrtf(xl.x * xl.x + xl.y * xl.y), mr = sqrtf(xr.x * xr.x + xr.y * xr.y);
+  const float ml = stft_abs<F16>(xl), mr = stft_abs<F16>(xr);
   const size_t bin = (size_t)k * P.T + t;
   if (!P.waves) {
     const int C = P.fwave_channels;
@@ -152,50 +177,46 @@ M2H_DEV void stft_emit(const StftParams& P, int b, int sig, int k, int t, float2
     if (P.mix_mag) {
       float vl = ml, vr = mr;
       if (P.flags & M2H_OUT_MIX_LOG1P) {
-        vl = f16 ? stft_log1p_f16(ml) : log1pf(ml);
-        vr = f16 ? stft_log1p_f16(mr) : log1pf(mr);
+        vl = F16 ? stft_log1p_f16(ml) : stft_log1p_fast(ml);
+        vr = F16 ? stft_log1p_f16(mr) : stft_log1p_fast(mr);
       }
-      stft_store(P.mix_mag, o, vl, f16);
-      stft_store(P.mix_mag, o + 1, vr, f16);
+      stft_store2<F16>(P.mix_mag, o, vl, vr);
     }
-    if (P.mix_phase) {
-      stft_store(P.mix_phase, o, atan2f(xl.y, xl.x), f16);
-      stft_store(P.mix_phase, o + 1, atan2f(xr.y, xr.x), f16);
-    }
+    if (P.mix_phase) stft_store2<F16>(P.mix_phase, o, atan2f(xl.y, xl.x), atan2f(xr.y, xr.x));
   } else if (P.gt_mag) {
     const int g = sig - 1;
     if (P.gt_interleaved_phase) {
       const size_t o = (((size_t)b * P.n_gt + g) * M2H_NBINS * P.T + bin) * 4;
-      stft_store(P.gt_mag, o, ml, f16);
-      stft_store(P.gt_mag, o + 1, atan2f(xl.y, xl.x), f16);
-      stft_store(P.gt_mag, o + 2, mr, f16);
-      stft_store(P.gt_mag, o + 3, atan2f(xr.y, xr.x), f16);
+      stft_store2<F16>(P.gt_mag, o, ml, atan2f(xl.y, xl.x));
+      stft_store2<F16>(P.gt_mag, o + 2, mr, atan2f(xr.y, xr.x));
     } else {
       const size_t o = (((size_t)b * P.n_gt + g) * M2H_NBINS * P.T + bin) * 2;
-      stft_store(P.gt_mag, o, ml, f16);
-      stft_store(P.gt_mag, o + 1, mr, f16);
+      stft_store2<F16>(P.gt_mag, o, ml, mr);
     }
   }
 }
 
 // ---- phases (per thread; grp = tid >> 7 owns frame t, lt = tid & 127) ------------------------------
-// P1: load 8 x 128 samples of the frame pair, window * conj(chirp), radix-16 pass along n1 (upper 8 inputs are the
-//     zero padding of the 2048-point transform), twiddle W_2048^(r*k1).
-M2H_DEV void stft_p1(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int b, int sig, int t0) {
+// P1: load 8 x 128 samples of the frame pair from the staged window, window * conj(chirp) (P1a); after a group barrier -
+// the window lives in the buffer the pass writes - radix-16 pass along n1 (upper 8 inputs are the zero padding of the
+// 2048-point transform), twiddle W_2048^(r*k1) (P1b).
+M2H_DEV void stft_p1_load(const StftParams& P, const StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int t0, float2 (&v)[16]) {
   const int grp = tid >> 7, r = tid & 127, t = t0 + grp;
   if (t >= P.T) return;
-  float2 v[16];
   M2H_UNROLL for (int n1 = 0; n1 < 8; ++n1) {
     const int n = n1 * 128 + r;
     float2 a = make_float2(0.f, 0.f);
     if (n < M2H_NFFT) {
-      const float2 x = s.stage[stft_reflect(M2H_HOP * t - (M2H_NFFT / 2) + n, P.N) - (M2H_HOP * t0 - M2H_HOP)];
-      a = c_mul(x, gt->wc[n]);
+      const int j = stft_reflect(M2H_HOP * t - (M2H_NFFT / 2) + n, P.N) - (M2H_HOP * t - M2H_HOP);
+      a = c_mul(s.buf[grp][M2H_STFT_STAGE_POS(j)], gt->wc[n]);
     }
     v[n1] = a;
   }
-  M2H_UNROLL for (int n1 = 8; n1 < 16; ++n1) v[n1] = make_float2(0.f, 0.f);
-  fft_reg<16, false>(v);
+}
+M2H_DEV void stft_p1_pass(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int t0, float2 (&v)[16]) {
+  const int grp = tid >> 7, r = tid & 127;
+  if (t0 + grp >= P.T) return;
+  fft_reg<16, false, true>(v);
   float2* p = s.buf[grp] + M2H_STFT_POS2(r >> 3) + (r & 7);
   twiddle_powers_out<16, 4, false>(v, M2H_STFT_TW(gt, 0, tid), M2H_STFT_TW(gt, 1, tid), [&](int k1, float2 x) { p[k1 * M2H_STFT_S1] = x; });     // W_2048^(r*k1)
 }
@@ -251,6 +272,7 @@ M2H_DEV void stft_p5(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_
 }
 M2H_DEV int stft_pos(int m) { return (m >> 7) * M2H_STFT_S1 + M2H_STFT_POS2((m >> 3) & 15) + (m & 7); }
 // P6: separate the ears (X_l = (X[k] + conj X[N-k]) / 2, X_r = (X[k] - conj X[N-k]) / 2i; the 1/2 lives in cc) and emit
+template <bool F16>
 M2H_DEV void stft_p6(const StftParams& P, StftSmem& s, int tid, int b, int sig, int t0) {
   const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
   if (t >= P.T) return;
@@ -259,10 +281,11 @@ M2H_DEV void stft_p6(const StftParams& P, StftSmem& s, int tid, int b, int sig, 
     const float2 c = s.buf[grp][stft_pos(k == 0 ? 0 : M2H_NFFT - k)];
     const float2 xl = make_float2(a.x + c.x, a.y - c.y);
     const float2 xr = make_float2(a.y + c.y, c.x - a.x);
-    stft_emit(P, b, sig, k, t, xl, xr);
+    stft_emit<F16>(P, b, sig, k, t, xl, xr);
   }
 }
 
+template <bool F16>     // F16 = simulator dtype (P.flags & M2H_OUT_F16)
 M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int cta, int n_ctas) {
   M2H_FOR_THREADS(tid, M2H_STFT_THREADS) {
     for (int i = tid; i < 2048; i += M2H_STFT_THREADS) s.bf[(i & 7) * 256 + (i >> 3)] = gt->bf[i];
@@ -272,11 +295,23 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
   for (int item = cta; item < n_items; item += n_ctas) {
     const int b = item / P.n_signals, sig = item % P.n_signals;
     for (int t0 = 0; t0 < P.T; t0 += M2H_STFT_GROUPS) {
+      // each 128-thread group owns one frame pair and its buffer: only the group meets between the passes, the four
+      // groups of a CTA drift apart freely
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_stage(P, s, tid, b, sig, t0);
-      M2H_SYNC();
-      // each 128-thread group owns one frame pair and its buffer: only the group meets between the passes
-      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p1(P, s, gt, tid, b, sig, t0);
-      M2H_SYNC();      // CTA-wide: the staged samples may be rewritten (next t0) as soon as every group is past its P1
+      M2H_SYNC_GROUP128();
+#ifdef M2H_HOST_EMU
+      static float2 vs[M2H_STFT_THREADS][16];
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p1_load(P, s, gt, tid, t0, vs[tid]);
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p1_pass(P, s, gt, tid, t0, vs[tid]);
+#else
+      {
+        float2 v[16];
+        stft_p1_load(P, s, gt, threadIdx.x, t0, v);
+        M2H_SYNC_GROUP128();
+        stft_p1_pass(P, s, gt, threadIdx.x, t0, v);
+      }
+#endif
+      M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p2(P, s, gt, tid, t0);
       M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p3(P, s, gt, tid, t0);
@@ -285,8 +320,8 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
       M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p5(P, s, gt, tid, t0);
       M2H_SYNC_GROUP128();
-      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p6(P, s, tid, b, sig, t0);
-      // no barrier: the next staging pass touches neither buffer, and the CTA barrier after it orders P6 before the next P1
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p6<F16>(P, s, tid, b, sig, t0);
+      M2H_SYNC_GROUP128();      // the next window is staged into the buffer P6 reads
     }
   }
 }

@@ -76,7 +76,7 @@ extern "C" int emu_stft_waves(const int16_t* waves, int B, int K, int N, int n_g
   P.waves = waves; P.B = B; P.K = K; P.N = N; P.T = 1 + (N - 1) / M2H_HOP; P.n_gt = n_gt; P.n_signals = 1 + n_gt;
   P.flags = (raw ? 0 : M2H_OUT_MIX_LOG1P) | (f16 ? M2H_OUT_F16 : 0);
   P.mix_mag = mix_mag; P.mix_phase = mix_phase; P.gt_mag = gt; P.gt_interleaved_phase = gt_with_phase;
-  for (int cta = 0; cta < n_ctas; ++cta) stft_cta_body(P, *s, &g_st, cta, n_ctas);
+  for (int cta = 0; cta < n_ctas; ++cta) { if (f16) stft_cta_body<true>(P, *s, &g_st, cta, n_ctas); else stft_cta_body<false>(P, *s, &g_st, cta, n_ctas); }
   delete s;
   return 0;
 }
@@ -88,7 +88,7 @@ extern "C" int emu_stft_f32(const float* wave, int B, int C, int N, float* mag, 
   memset(&P, 0, sizeof(P));
   P.fwave = wave; P.fwave_channels = C; P.B = B; P.N = N; P.T = 1 + (N - 1) / M2H_HOP; P.n_signals = 1;
   P.f_mag = mag; P.f_phase = phase;
-  stft_cta_body(P, *s, &g_st, 0, 1);
+  stft_cta_body<false>(P, *s, &g_st, 0, 1);
   delete s;
   return 0;
 }
