@@ -22,6 +22,7 @@
   #define M2H_FOR_THREADS(tid, nthreads) for (int tid = 0; tid < (nthreads); ++tid)
   #define M2H_SYNC() do {} while (0)
   #define M2H_SYNC_GROUP128() do {} while (0)
+  #define M2H_SYNC_WARP() do {} while (0)
   #define M2H_UNROLL
   #define M2H_RESTRICT
   M2H_DEV float m2h_rintf(float v) { return nearbyintf(v); }
@@ -53,6 +54,7 @@
     }
   }
   #define M2H_SYNC_GROUP128() m2h_sync_group128()
+  #define M2H_SYNC_WARP() __syncwarp()
   #define M2H_UNROLL _Pragma("unroll")
   #define M2H_RESTRICT __restrict__
   M2H_DEV float m2h_rintf(float v) { return rintf(v); }
@@ -90,9 +92,11 @@ template <bool CONJ> M2H_DEV float2 c_mul_sel(float2 a, float2 w) { return CONJ 
 //   thr[0][t] = W_16384^t        thr[1][t] = W_16384^(8t)            passes A / A'   (radix 32, Q = 8)
 //   thr[2][t] = W_512^(t&15)     thr[3][t] = W_512^(8*(t&15))        pass B          (radix 32)
 //   thr[4][t] = W_512^(t&31)     thr[5][t] = W_512^(4*(t&31))        pass C'         (radix 16, Q = 4)
-//   thr[6][t] = W_32768^f0(t), f0(t) = (t>>8) + 32*((t>>3)&31) + 1024*(t&7)   untangle twiddle of the thread's first pair
+//   thr[6][t] = W_32768^(k1 + 32*k2) of the thread's row A in the fused pass (render_conv.cuh::conv_rows)
+//   unit_tw[u]: twiddle of pair unit u on the two self-paired rows: u < 8: W_32768^(1024u); u >= 8: W_32768^(512 + 1024(u-8))
 struct M2hConvTables {
   float2 thr[7][512];
+  float2 unit_tw[16];
 };
 // thr[0][l] = W_2048^l, thr[1][l] = W_2048^(4l)  (P1/P5);  thr[2][l] = W_128^(l&7), thr[3][l] = W_128^(4*(l&7))  (P2);
 // thr[4][l] = W_128^(l&15), thr[5][l] = W_128^(4*(l&15))  (P3)      -- l = thread id within its 128-thread group

@@ -18,9 +18,11 @@ static void build_conv_tables(M2hConvTables& t) {
     t.thr[3][i] = cis((double)(8 * (i & 15)) / 512.0);
     t.thr[4][i] = cis((double)(i & 31) / 512.0);
     t.thr[5][i] = cis((double)(4 * (i & 31)) / 512.0);
-    const int f0 = (i >> 8) + 32 * ((i >> 3) & 31) + 1024 * (i & 7);
-    t.thr[6][i] = cis((double)f0 / 32768.0);
+    const int w = i >> 5, l = i & 31;
+    const int k1 = w ? w : (l < 16 ? 16 : 0), k2 = w ? l : (l < 16 ? l : l - 16);
+    t.thr[6][i] = cis((double)(k1 + 32 * k2) / 32768.0);
   }
+  for (int u = 0; u < 16; ++u) t.unit_tw[u] = cis((double)(u < 8 ? 1024 * u : 512 + 1024 * (u - 8)) / 32768.0);
 }
 
 static void build_stft_tables(M2hStftTables& t) {

@@ -54,46 +54,163 @@ M2H_DEV int conv_pos(int f) {            // position of spectrum index f = k1 + 
 // pair index -> spectrum index f in [0, 8192): k3 fastest so that half-warps touch consecutive positions
 M2H_DEV int conv_pair_f(int idx) { return (idx >> 8) + 32 * ((idx >> 3) & 31) + 1024 * (idx & 7); }
 
-// ---- forward FFT passes B and C (pass A is fused with the loads) ----------------------------
+// ---- warp-local middle of the transforms -------------------------------------------------------------------------
+// Pass A leaves slab k1 (544 elements) holding a 32 x 16 (n2, n3) matrix; passes B (radix 32 along n2), C (radix 16 along
+// n3), the pointwise spectrum product and the mirrored inverse passes C', B' never leave a slab - except that the product
+// pairs spectrum index f with M - f, i.e. slab k1 with slab 32 - k1.  Warp w therefore owns the slab pair (w, 32 - w)
+// (warp 0: the self-paired slabs 0 and 16) from pass B to pass B': inside that stretch warps only need __syncwarp(),
+// and passes C, the product and C' run on a row pair held in registers (no shared-memory round trip between them).
+M2H_DEV int conv_slab_of(int tid, int half) { const int w = tid >> 5; return half == 0 ? w : (w ? 32 - w : 16); }
+
 M2H_DEV void conv_fwd_pass_b(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t) {
-  const int k1 = tid >> 4, n3 = tid & 15;
-  float2* p = s.buf + k1 * M2H_CONV_S1 + n3;
+  const int l = tid & 31, n3 = l & 15;
+  float2* p = s.buf + conv_slab_of(tid, l >> 4) * M2H_CONV_S1 + n3;
   float2 v[32];
   M2H_UNROLL for (int j = 0; j < 32; ++j) v[j] = p[j * M2H_CONV_S2];
   fft_reg<32, false>(v);
   twiddle_powers_out<32, 5, false>(v, M2H_CONV_TW(t, 2, tid), M2H_CONV_TW(t, 3, tid), [&](int k2, float2 x) { p[k2 * M2H_CONV_S2] = x; });   // W_512^(n3*k2)
 }
-M2H_DEV void conv_fwd_pass_c(ConvSmem& s, int tid) {
-  M2H_UNROLL for (int h = 0; h < 2; ++h) {
-    const int q = tid + h * M2H_CONV_THREADS;
-    float2* p = s.buf + (q >> 5) * M2H_CONV_S1 + (q & 31) * M2H_CONV_S2;
-    float2 v[16];
-    M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[j];
-    fft_reg<16, false>(v);
-    M2H_UNROLL for (int k3 = 0; k3 < 16; ++k3) p[k3] = v[bitrev<4>(k3)];
-  }
-}
-// ---- inverse FFT passes C' and B' (pass A' is fused with the output) ---------------------------
-M2H_DEV void conv_inv_pass_c(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t) {
-  M2H_UNROLL for (int h = 0; h < 2; ++h) {
-    const int q = tid + h * M2H_CONV_THREADS;
-    const int k2 = q & 31;
-    float2* p = s.buf + (q >> 5) * M2H_CONV_S1 + k2 * M2H_CONV_S2;
-    float2 v[16];
-    M2H_UNROLL for (int j = 0; j < 16; ++j) v[j] = p[j];
-    fft_reg<16, true>(v);
-    twiddle_powers_out<16, 4, true>(v, M2H_CONV_TW(t, 4, tid), M2H_CONV_TW(t, 5, tid), [&](int n3, float2 x) { p[n3] = x; });                 // conj W_512^(n3*k2)
-  }
-}
 // pass B' stores untwiddled; conj W_16384^((16*n2+n3)*k1) = conj(W_16384^r)^k1 is applied by pass A' on load
 M2H_DEV void conv_inv_pass_b(ConvSmem& s, int tid) {
-  const int k1 = tid >> 4, n3 = tid & 15;
-  float2* p = s.buf + k1 * M2H_CONV_S1 + n3;
+  const int l = tid & 31, n3 = l & 15;
+  float2* p = s.buf + conv_slab_of(tid, l >> 4) * M2H_CONV_S1 + n3;
   float2 v[32];
   M2H_UNROLL for (int j = 0; j < 32; ++j) v[j] = p[j * M2H_CONV_S2];
   fft_reg<32, true>(v);
   M2H_UNROLL for (int n2 = 0; n2 < 32; ++n2) p[n2 * M2H_CONV_S2] = v[bitrev<5>(n2)];
 }
+
+// Row pair of a lane in the fused pass: row A = (slab, k2) at position pa, its mirror row B at pb.  For every lane but
+// lane 16 of warp 0, spectrum index f = (row A, k3) pairs with M - f = (row B, 15 - k3):
+//   warps 1..15: A = (w, l),  B = (32 - w, 31 - l);   warp 0, lanes 0..15: A = (16, l), B = (16, 31 - l);
+//   warp 0, lanes 17..31 (j = l - 16): A = (0, j), B = (0, 32 - j).
+// Lane 16 of warp 0 holds the two self-paired rows (0, 0) [k3 <-> 16 - k3, with f = 0 and f = M/2 on their own] and
+// (0, 16) [k3 <-> 15 - k3].
+struct ConvRows { int pa, pb, k2a, k2b; };
+M2H_DEV ConvRows conv_rows(int tid) {
+  const int w = tid >> 5, l = tid & 31;
+  ConvRows r;
+  if (w) { r.pa = w * M2H_CONV_S1 + l * M2H_CONV_S2; r.pb = (32 - w) * M2H_CONV_S1 + (31 - l) * M2H_CONV_S2; r.k2a = l; r.k2b = 31 - l; }
+  else if (l < 16) { r.pa = 16 * M2H_CONV_S1 + l * M2H_CONV_S2; r.pb = 16 * M2H_CONV_S1 + (31 - l) * M2H_CONV_S2; r.k2a = l; r.k2b = 31 - l; }
+  else { const int j = l - 16; r.k2a = j; r.k2b = j ? 32 - j : 16; r.pa = r.k2a * M2H_CONV_S2; r.pb = r.k2b * M2H_CONV_S2; }
+  return r;
+}
+
+// Untangle the packed-real spectrum at (f, M-f):  returns 2*X[f] in xa and 2*X[M-f] in xb  (w = W_32768^f, any 0 < f < M).
+M2H_DEV void conv_untangle(float2 za, float2 zb, float2 w, float2& xa, float2& xb) {
+  const float2 p = make_float2(za.x + zb.x, za.y - zb.y);       // Za + conj(Zb)         = 2 E[f]
+  const float2 o = make_float2(za.y + zb.y, zb.x - za.x);       // -i (Za - conj(Zb))    = 2 O[f]
+  const float2 q = c_mul(w, o);
+  xa = c_add(p, q);
+  xb = c_conj(c_sub(p, q));
+}
+// H pair (za, zb) at (f, M-f) times the X pair x = {2X[f], 2X[M-f]}, re-tangled for the inverse packed transform (in place)
+M2H_DEV void conv_pair_product(float2& za, float2& zb, float2 w, float4 x) {
+  float2 ha, hb;
+  conv_untangle(za, zb, w, ha, hb);
+  const float2 ya = c_mul(make_float2(x.x, x.y), ha);
+  const float2 yb = c_mul(make_float2(x.z, x.w), hb);
+  const float2 e = make_float2(ya.x + yb.x, ya.y - yb.y);            // Ya + conj(Yb)
+  const float2 d = make_float2(ya.x - yb.x, ya.y + yb.y);            // Ya - conj(Yb)
+  const float2 o = c_mulc(d, w);                                       // conj(w) * d
+  za = make_float2(e.x - o.y, e.y + o.x);                              // E + i O
+  zb = make_float2(e.x + o.y, o.x - e.y);                              // conj(E) + i conj(O)
+}
+
+// Fused pass C (+ pointwise work), in three steps separated by __syncwarp():
+//   1. forward radix-16 pass on the lane's two rows (registers); every lane but lane 16 of warp 0 then does its 16 pair
+//      operations in registers - MONO: store the untangled spectrum pairs of the clip in the CTA's scratch slot
+//      (g[k3*512 + tid] = {2X[f], 2X[M-f]}), else: multiply the RIR spectrum by them.  Lane 16 of warp 0 parks its two
+//      self-paired rows in shared memory instead;
+//   2. lanes 0..15 of warp 0 do one pair operation each on the parked rows (unit u: u = 0 -> f = 0, M, M/2;
+//      u = 1..7 -> row (0,0), k3 = u <-> 16 - u; u = 8..15 -> row (0,16), k3 = u - 8 <-> 23 - u; X slots g[u*512 + 16]);
+//   3. (not MONO) lane 16 reloads its rows; inverse pass C' on both rows of every lane.
+template <bool MONO>
+M2H_DEV void conv_pass_c_step1(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, float4* g, float2 (&va)[16], float2 (&vb)[16]) {
+  const ConvRows R = conv_rows(tid);
+  float4 xs[16];
+  if (!MONO && tid != 16) { M2H_UNROLL for (int i = 0; i < 4; ++i) xs[i] = g[i * M2H_CONV_THREADS + tid]; }      // L2 latency hides behind the transforms
+  M2H_UNROLL for (int j = 0; j < 16; ++j) { va[j] = s.buf[R.pa + j]; vb[j] = s.buf[R.pb + j]; }
+  fft_reg<16, false>(va);
+  fft_reg<16, false>(vb);
+  // Z_A[k3] = va[bitrev(k3)], Z_B[k3] = vb[bitrev(k3)]
+  if (tid != 16) {
+    const float2 wU = M2H_CONV_TW(t, 6, tid);                         // W_32768^(k1 + 32*k2) of row A
+    M2H_UNROLL for (int k3 = 0; k3 < 16; ++k3) {
+      if (!MONO && (k3 & 3) == 0 && k3 + 4 < 16) { M2H_UNROLL for (int i = 0; i < 4; ++i) xs[k3 + 4 + i] = g[(k3 + 4 + i) * M2H_CONV_THREADS + tid]; }
+      float2& za = va[bitrev<4>(k3)];
+      float2& zb = vb[bitrev<4>(15 - k3)];
+      const float2 w = mul_tw32<false>(wU, k3);                       // W_32768^(f), f = k1 + 32*k2 + 1024*k3
+      if (MONO) {
+        float2 xa, xb;
+        conv_untangle(za, zb, w, xa, xb);
+        g[k3 * M2H_CONV_THREADS + tid] = make_float4(xa.x, xa.y, xb.x, xb.y);
+      } else {
+        conv_pair_product(za, zb, w, xs[k3]);
+      }
+    }
+  } else {
+    M2H_UNROLL for (int k3 = 0; k3 < 16; ++k3) { s.buf[R.pa + k3] = va[bitrev<4>(k3)]; s.buf[R.pb + k3] = vb[bitrev<4>(k3)]; }
+  }
+}
+template <bool MONO>
+M2H_DEV void conv_pass_c_step2(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, float4* g) {
+  if (tid >= 16) return;
+  const int u = tid;
+  float4* gx = g + u * M2H_CONV_THREADS + 16;
+  if (u == 0) {           // f = 0 and f = M (real, packed in one complex) and f = M/2
+    const int ph = 8;
+    const float2 z0 = s.buf[0], zh = s.buf[ph];
+    if (MONO) {
+      *gx = make_float4(2.f * (z0.x + z0.y), 2.f * (z0.x - z0.y), 2.f * zh.x, -2.f * zh.y);
+    } else {
+      const float4 x = *gx;
+      const float y0 = x.x * (2.f * (z0.x + z0.y));
+      const float ym = x.y * (2.f * (z0.x - z0.y));
+      s.buf[0] = make_float2(y0 + ym, y0 - ym);
+      const float2 y = c_mul(make_float2(x.z, x.w), make_float2(2.f * zh.x, -2.f * zh.y));
+      s.buf[ph] = make_float2(2.f * y.x, -2.f * y.y);
+    }
+    return;
+  }
+  const int pa = u < 8 ? u : 16 * M2H_CONV_S2 + (u - 8);
+  const int pb = u < 8 ? 16 - u : 16 * M2H_CONV_S2 + (23 - u);
+  const float2 w = m2h_ldg2(&t->unit_tw[u]);
+  float2 za = s.buf[pa], zb = s.buf[pb];
+  if (MONO) {
+    float2 xa, xb;
+    conv_untangle(za, zb, w, xa, xb);
+    *gx = make_float4(xa.x, xa.y, xb.x, xb.y);
+  } else {
+    conv_pair_product(za, zb, w, *gx);
+    s.buf[pa] = za;
+    s.buf[pb] = zb;
+  }
+}
+M2H_DEV void conv_pass_c_step3(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, float2 (&va)[16], float2 (&vb)[16]) {
+  const ConvRows R = conv_rows(tid);
+  // inverse pass C' on both rows: natural-order input = the products, output n3 with the twiddle conj W_512^(n3*k2)
+  float2 ua[16], ub[16];
+  if (tid != 16) {
+    M2H_UNROLL for (int k3 = 0; k3 < 16; ++k3) { ua[k3] = va[bitrev<4>(k3)]; ub[k3] = vb[bitrev<4>(k3)]; }
+  } else {
+    M2H_UNROLL for (int k3 = 0; k3 < 16; ++k3) { ua[k3] = s.buf[R.pa + k3]; ub[k3] = s.buf[R.pb + k3]; }
+  }
+  fft_reg<16, true>(ua);
+  twiddle_powers_out<16, 4, true>(ua, M2H_CONV_TW(t, 4, R.k2a), M2H_CONV_TW(t, 5, R.k2a), [&](int n3, float2 x) { s.buf[R.pa + n3] = x; });
+  fft_reg<16, true>(ub);
+  twiddle_powers_out<16, 4, true>(ub, M2H_CONV_TW(t, 4, R.k2b), M2H_CONV_TW(t, 5, R.k2b), [&](int n3, float2 x) { s.buf[R.pb + n3] = x; });
+}
+// The two rows of a thread live in registers across the three steps (host emulation: one static copy per thread id).
+#ifdef M2H_HOST_EMU
+  #define M2H_CONV_ROWS_DECL static float2 m2h_va[M2H_CONV_THREADS][16], m2h_vb[M2H_CONV_THREADS][16]
+  #define M2H_CONV_VA(tid) m2h_va[tid]
+  #define M2H_CONV_VB(tid) m2h_vb[tid]
+#else
+  #define M2H_CONV_ROWS_DECL float2 m2h_va[16], m2h_vb[16]
+  #define M2H_CONV_VA(tid) m2h_va
+  #define M2H_CONV_VB(tid) m2h_vb
+#endif
 
 // Pass A of the forward transform, split into its global loads and the radix pass so that the caller can put
 // independent work (the previous window's copy-out) under the load latency.  Thread `tid` owns the residue r = tid of
@@ -144,99 +261,6 @@ M2H_DEV void conv_fwd_pass_a(ConvSmem& s, int tid, const M2hConvTables* M2H_REST
 // L2 prefetch of a row that a later phase will load (one 128-byte line per thread and step)
 M2H_DEV void conv_prefetch_row(int tid, const void* row, int bytes) {
   for (int o = tid * 128; o < bytes; o += M2H_CONV_THREADS * 128) m2h_prefetch_l2((const char*)row + o);
-}
-
-// Untangle the packed-real spectrum at (f, M-f):  returns 2*X[f] in xa and 2*X[M-f] in xb.
-M2H_DEV void conv_untangle(float2 za, float2 zb, float2 w, float2& xa, float2& xb) {
-  const float2 p = make_float2(za.x + zb.x, za.y - zb.y);       // Za + conj(Zb)         = 2 E[f]
-  const float2 o = make_float2(za.y + zb.y, zb.x - za.x);       // -i (Za - conj(Zb))    = 2 O[f]
-  const float2 q = c_mul(w, o);
-  xa = c_add(p, q);
-  xb = c_conj(c_sub(p, q));
-}
-
-// The pointwise phases walk the 8192 pairs (f, M-f), f = k1 + 32*k2 + 1024*k3 < 8192, as idx = tid + 512*i:
-// (k2, k3) = ((tid>>3)&31, tid&7) belong to the thread and k1 = (tid>>8) + 2*i, so the buffer position of f advances by
-// 2*S1 per step and that of M-f (digits 32-k1, 31-k2, 15-k3 whenever k1 != 0) retreats by 2*S1: no per-element index
-// arithmetic.  Only the k1 = 0 column (i = 0, tid < 256) borrows differently.
-struct ConvPairWalk {
-  int pa0, pb0, pb_first;
-};
-M2H_DEV ConvPairWalk conv_pair_walk(int tid) {
-  const int t8 = tid >> 8, k2 = (tid >> 3) & 31, k3 = tid & 7;
-  ConvPairWalk w;
-  w.pa0 = t8 * M2H_CONV_S1 + k2 * M2H_CONV_S2 + k3;
-  w.pb0 = (32 - t8) * M2H_CONV_S1 + (31 - k2) * M2H_CONV_S2 + (15 - k3);
-  // i = 0: k1 = t8.  k1 = 0: M - f has digits (0, (32-k2)&31, 16 - k3 - (k2 != 0))   [tid = 0 is handled apart]
-  w.pb_first = t8 ? w.pb0 : ((32 - k2) & 31) * M2H_CONV_S2 + (16 - k3 - (k2 != 0 ? 1 : 0));
-  return w;
-}
-
-// Phase: spectrum of the mono signal -> per-CTA scratch (float4 = {2X[f], 2X[M-f]}).
-M2H_DEV void conv_store_mono_spectrum(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, float4* g) {
-  const float2 wU = M2H_CONV_TW(t, 6, tid);
-  const ConvPairWalk pw = conv_pair_walk(tid);
-  M2H_UNROLL for (int i = 0; i < 8192 / M2H_CONV_THREADS; ++i) {
-    const int idx = tid + i * M2H_CONV_THREADS;
-    if (i == 0 && tid == 0) {
-      const float2 z0 = s.buf[0], zh = s.buf[conv_pos(8192)];
-      g[0] = make_float4(2.f * (z0.x + z0.y), 2.f * (z0.x - z0.y), 2.f * zh.x, -2.f * zh.y);   // X[0], X[M] (real), X[M/2]
-    } else {
-      float2 xa, xb;
-      const float2 w = c_mul(wU, make_float2(conv_w16384_cos(i), conv_w16384_sin(i)));   // W_32768^(f0 + 2i)
-      const int pa = pw.pa0 + i * 2 * M2H_CONV_S1, pb = i == 0 ? pw.pb_first : pw.pb0 - i * 2 * M2H_CONV_S1;
-      conv_untangle(s.buf[pa], s.buf[pb], w, xa, xb);
-      g[idx] = make_float4(xa.x, xa.y, xb.x, xb.y);
-    }
-  }
-}
-
-// Phase: untangle H, multiply by X, re-tangle for the inverse transform (in place).  Four pairs per batch: their
-// shared-memory loads are issued together (in-place stores would otherwise fence every following load).
-M2H_DEV void conv_multiply_spectrum(ConvSmem& s, int tid, const M2hConvTables* M2H_RESTRICT t, const float4* g) {
-  const float2 wU = M2H_CONV_TW(t, 6, tid);
-  const ConvPairWalk pw = conv_pair_walk(tid);
-  constexpr int NI = 8192 / M2H_CONV_THREADS, NB = 4;
-  float4 xs[2][NB];
-  M2H_UNROLL for (int u = 0; u < NB; ++u) xs[0][u] = g[tid + u * M2H_CONV_THREADS];
-  M2H_UNROLL for (int i0 = 0; i0 < NI; i0 += NB) {
-    const int cur = (i0 / NB) & 1;
-    if (i0 + NB < NI) { M2H_UNROLL for (int u = 0; u < NB; ++u) xs[cur ^ 1][u] = g[tid + (i0 + NB + u) * M2H_CONV_THREADS]; }   // X of the next batch (L2)
-    float2 za[NB], zb[NB];
-    int pa[NB], pb[NB];
-    M2H_UNROLL for (int u = 0; u < NB; ++u) {
-      const int i = i0 + u;
-      pa[u] = pw.pa0 + i * 2 * M2H_CONV_S1;
-      pb[u] = i == 0 ? pw.pb_first : pw.pb0 - i * 2 * M2H_CONV_S1;
-      if (i == 0 && tid == 0) pb[u] = conv_pos(8192);
-      za[u] = s.buf[pa[u]];
-      zb[u] = s.buf[pb[u]];
-    }
-    M2H_UNROLL for (int u = 0; u < NB; ++u) {
-      const int i = i0 + u;
-      const float4 x = xs[cur][u];
-      if (i == 0 && tid == 0) {      // X[0], X[M] (real) ride in one complex slot; X[M/2]
-        const float2 z0 = za[u], zh = zb[u];
-        const float y0 = x.x * (2.f * (z0.x + z0.y));
-        const float ym = x.y * (2.f * (z0.x - z0.y));
-        za[u] = make_float2(y0 + ym, y0 - ym);
-        const float2 y = c_mul(make_float2(x.z, x.w), make_float2(2.f * zh.x, -2.f * zh.y));
-        zb[u] = make_float2(2.f * y.x, -2.f * y.y);
-      } else {
-        const float2 w = c_mul(wU, make_float2(conv_w16384_cos(i), conv_w16384_sin(i)));
-        float2 ha, hb;
-        conv_untangle(za[u], zb[u], w, ha, hb);
-        const float2 ya = c_mul(make_float2(x.x, x.y), ha);
-        const float2 yb = c_mul(make_float2(x.z, x.w), hb);
-        const float2 e = make_float2(ya.x + yb.x, ya.y - yb.y);            // Ya + conj(Yb)
-        const float2 d = make_float2(ya.x - yb.x, ya.y + yb.y);            // Ya - conj(Yb)
-        const float2 o = c_mulc(d, w);                                       // conj(w) * d
-        za[u] = make_float2(e.x - o.y, e.y + o.x);                           // E + i O
-        zb[u] = make_float2(e.x + o.y, o.x - e.y);                           // conj(E) + i conj(O)
-      }
-    }
-    M2H_UNROLL for (int u = 0; u < NB; ++u) { s.buf[pa[u]] = za[u]; s.buf[pb[u]] = zb[u]; }
-  }
 }
 
 // numpy: np.round (half to even) then astype(int16) wraps modulo 2^16: round-to-nearest-even conversion to int32
@@ -292,6 +316,7 @@ M2H_HD bool conv_can_vectorise(const ConvParams& P) {
 template <bool VEC>
 M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables* M2H_RESTRICT gtab, int cta, int n_ctas) {
   float4* g = P.scratch + (size_t)cta * M2H_CONV_SCRATCH_F4;
+  M2H_CONV_ROWS_DECL;
   const int N = P.N;
   int16_t* pend_out = nullptr;    // window of the previous inverse transform, still in the staging buffer
   int pend_off = 0;
@@ -323,10 +348,10 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
     pend_out = nullptr;
     M2H_SYNC();
     M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid, gtab);
-    M2H_SYNC();
-    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_c(s, tid);
-    M2H_SYNC();
-    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_store_mono_spectrum(s, tid, gtab, g);
+    M2H_SYNC_WARP();
+    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_pass_c_step1<true>(s, tid, gtab, g, M2H_CONV_VA(tid), M2H_CONV_VB(tid));
+    M2H_SYNC_WARP();
+    M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_pass_c_step2<true>(s, tid, gtab, g);
     M2H_SYNC();
     for (int ear = 0; ear < 2; ++ear) {
       const float* h = P.rir + ((size_t)item * 2 + ear) * P.Lmax + jmin;
@@ -348,13 +373,13 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
       pend_out = nullptr;
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_b(s, tid, gtab);
-      M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_fwd_pass_c(s, tid);
-      M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_multiply_spectrum(s, tid, gtab, g);
-      M2H_SYNC();
-      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_inv_pass_c(s, tid, gtab);
-      M2H_SYNC();
+      M2H_SYNC_WARP();
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_pass_c_step1<false>(s, tid, gtab, g, M2H_CONV_VA(tid), M2H_CONV_VB(tid));
+      M2H_SYNC_WARP();
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_pass_c_step2<false>(s, tid, gtab, g);
+      M2H_SYNC_WARP();
+      M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_pass_c_step3(s, tid, gtab, M2H_CONV_VA(tid), M2H_CONV_VB(tid));
+      M2H_SYNC_WARP();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_inv_pass_b(s, tid);
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_inv_pass_a_stage(s, tid, gtab, N, c_off);
