@@ -37,6 +37,9 @@ BYTES_CONV = 2 * K_SRC * N_SAMPLES + 8 * K_SRC * L_TAPS + 2 * K_SRC * 2 * N_SAMP
 BYTES_STFT = 2 * K_SRC * 2 * N_SAMPLES + 4 * 512 * 32 * 2                                   # int16 waves in, fp32 log-mag out
 BYTES_RENDER = 2 * K_SRC * N_SAMPLES + 8 * K_SRC * L_TAPS + 4 * 512 * 32 * 2                # 451,072 B
 FLOPS_UNET = 220.7e6                                                                         # binSep fwd, nominal 2*MACs
+# kernels of this library launched per timed step: m2h_rir_conv_kernel, m2h_stft_kernel, pack_input_kernel,
+# 3 x unet_slab_kernel (enc0, dec3, dec4 + head), 7 x unet_gemm_tma_kernel (enc1-4, dec0-2)
+OUR_LAUNCHES_PER_STEP = 13
 
 
 def workload_config(extra=None):
@@ -358,19 +361,19 @@ def run_ours(args):
         "roofline": {"kernel": "m2h_rir_conv_kernel", "bound": "hbm", "achieved": conv_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": conv_gbs / pk["hbm_gbs"], "traffic": traffic, "peak_src": pk["src"],
                      "algorithmic_bytes_per_launch": BYTES_CONV * B, "ms_per_launch": t_conv,
-                     "note": "compute/shared-memory bound fp32 FFT (25 MFLOP per mixture): see DESIGN.md section 4"},
+                     "note": "fp32 FFT arithmetic (11.5 MFLOP per mixture, issue-bound on the FP32 pipe), not HBM, bounds this kernel: see DESIGN.md section 4"},
         "roofline_other": [
             {"kernel": "m2h_stft_kernel", "bound": "hbm", "achieved": BYTES_STFT * B / (t_stft * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
              "frac": BYTES_STFT * B / (t_stft * 1e-3) / 1e9 / pk["hbm_gbs"], "ms_per_launch": t_stft},
             {"kernel": "render chain (conv + stft) vs SURVEY 8d bytes", "bound": "hbm", "achieved": BYTES_RENDER * B / ((t_conv + t_stft) * 1e-3) / 1e9,
              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": BYTES_RENDER * B / ((t_conv + t_stft) * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": t_conv + t_stft},
-            {"kernel": "unet_gemm_kernel x11 (+pack)", "bound": "tensor", "achieved": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
+            {"kernel": "U-Net forward: 3 unet_slab_kernel + 7 unet_gemm_tma_kernel + pack_input_kernel", "bound": "tensor", "achieved": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
              "unit": "TFLOP/s", "frac": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], "ms": t_unet},
         ],
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps},
-        "gpu_launches": 14 * args.steps,
+        "gpu_launches": OUR_LAUNCHES_PER_STEP * args.steps,
         "clocks": clocks,
         "train_step": train,
     }
