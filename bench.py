@@ -38,8 +38,8 @@ BYTES_STFT = 2 * K_SRC * 2 * N_SAMPLES + 4 * 512 * 32 * 2                       
 BYTES_RENDER = 2 * K_SRC * N_SAMPLES + 8 * K_SRC * L_TAPS + 4 * 512 * 32 * 2                # 451,072 B
 FLOPS_UNET = 220.7e6                                                                         # binSep fwd, nominal 2*MACs
 # kernels of this library launched per timed step: m2h_rir_conv_kernel, m2h_stft_kernel, pack_input_kernel,
-# 3 x unet_slab_kernel (enc0, dec3, dec4 + head), 7 x unet_gemm_tma_kernel (enc1-4, dec0-2)
-OUR_LAUNCHES_PER_STEP = 13
+# 3 x unet_slab_kernel (enc0, dec3, dec4 + head), 7 x unet_gemm_tma_kernel (enc1-4, dec0-2), bf16_to_f32_kernel (bottleneck)
+OUR_LAUNCHES_PER_STEP = 14
 
 
 def workload_config(extra=None):

@@ -224,7 +224,8 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     if (resident) { ug::mbar_wait(b_full(0), 0); ug::tc_fence_after(); }
     int ss = 0, bs = 0, iter = 0;                 // ring positions of the NEXT slab chunk / weight tile to consume
     uint32_t s_par = 0, b_par = 0;
-    const uint64_t desc_hi = ug::smem_desc_sw128(0);
+    const uint64_t desc_hi32 = ug::smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = (uint32_t)(ug::smem_desc_sw128(0) & 0xFFFFFFFFull);
     for (int t = blockIdx.x; t < L.n_tiles; t += gridDim.x, ++iter) {
       const int buf = iter & 1;
       if (iter >= 2) { ug::mbar_wait(t_empty(buf), (uint32_t)(((iter >> 1) - 1) & 1)); ug::tc_fence_after(); }
@@ -255,23 +256,25 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           if (++bs == NB) { bs = 0; b_par ^= 1u; }
           ug::tc_fence_after();
         }
-        const uint32_t a16 = a_base16 + ca.x;
+        // descriptor = (hi word, constant) : (lo word = LBO bit | start address >> 4); shared-memory addresses are < 2^18, so a
+        // K16 step is one 32-bit add of 2 to the lo word
+        const uint32_t a_lo = (a_base16 + ca.x) | desc_lo0;
         const uint32_t nk = ctl & 0xffu, np = (ctl >> 8) & 0xffu;
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           if (p < (int)np) {
             const uint32_t idesc = p ? cbw.z : cbw.x, pw = p ? cbw.w : cbw.y;
             const uint32_t d = tmem_d + (pw & 0xffffu);
-            const uint32_t b16 = b_base16 + ((pw >> 16) & 0x7fffu);
+            const uint32_t b_lo = (b_base16 + ((pw >> 16) & 0x7fffu)) | desc_lo0;
             const uint32_t acc0 = pw >> 31;
             if (nk == 4) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                us::umma_bf16_elect(d, desc_hi | (uint64_t)((a16 + 2u * k) & 0x3FFFu), desc_hi | (uint64_t)((b16 + 2u * k) & 0x3FFFu), idesc, k ? 1u : acc0);
+                us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u * k), desc_hi32 | (uint64_t)(b_lo + 2u * k), idesc, k ? 1u : acc0);
             } else {
 #pragma unroll
               for (int k = 0; k < 2; ++k)
-                us::umma_bf16_elect(d, desc_hi | (uint64_t)((a16 + 2u * k) & 0x3FFFu), desc_hi | (uint64_t)((b16 + 2u * k) & 0x3FFFu), idesc, k ? 1u : acc0);
+                us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u * k), desc_hi32 | (uint64_t)(b_lo + 2u * k), idesc, k ? 1u : acc0);
             }
           }
         }
