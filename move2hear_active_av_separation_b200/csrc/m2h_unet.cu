@@ -444,8 +444,9 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
   L.slab_rows = 128 + 2 * (Hp + 1);
   L.slab_bytes = (L.slab_rows * 128 + 1023) & ~1023;
   L.tile_cols = L.n_phase * L.Cout;
+  L.n_buf = 4 * L.tile_cols <= 512 ? 4 : 2;
   L.tmem_cols = 32;
-  while (L.tmem_cols < 2 * L.tile_cols) L.tmem_cols *= 2;
+  while (L.tmem_cols < L.n_buf * L.tile_cols) L.tmem_cols *= 2;
   int w_rows = 0;
   for (int i = 0; i < L.n_items; ++i) { L.items[i].w_row = (int16_t)w_rows; w_rows += L.items[i].b_rows; }
   L.w_rows = w_rows;

@@ -25,7 +25,7 @@
 #include <cuda.h>
 #include "unet_gemm.cuh"
 
-#define US_THREADS 352
+#define US_THREADS 384
 #define US_MAX_ITEMS 40
 #define US_B_STAGE_BYTES 16384        // up to 128 weight rows x 64 k (bf16)
 #define US_MAX_STAGES 8
@@ -62,7 +62,8 @@ struct USLayer {
   int Hp, Wp, PI, B;                  // padded geometry of the input grid, positions per image, batch
   int in_coff;                        // first input channel inside the position's channel vector
   int w_box_rows;                     // rows per weight TMA box
-  int tile_cols, tmem_cols;           // accumulator columns per tile (n_phase*Cout), allocation (power of two >= 2*tile_cols)
+  int tile_cols, tmem_cols;           // accumulator columns per tile (n_phase*Cout), allocation (power of two >= n_buf*tile_cols)
+  int n_buf;                          // accumulator buffers in TMEM: 4 when they fit (two per issuing warp), else 2
   int n_phase, Cout;
   // epilogue
   const float* scale; const float* bias; float slope;
@@ -143,10 +144,10 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   auto s_empty = [&](int s) { return bars + 8u * (US_MAX_STAGES + s); };
   auto b_full = [&](int s) { return bars + 8u * (2 * US_MAX_STAGES + s); };      // slot 0 doubles as "resident weights landed"
   auto b_empty = [&](int s) { return bars + 8u * (3 * US_MAX_STAGES + s); };
-  auto t_full = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + s); };
-  auto t_empty = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 2 + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (4 * US_MAX_STAGES + 4));
-  auto h_done = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 5 + s); };   // head MMAs of epilogue group s have completed
+  auto t_full = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + s); };       // 4 accumulator buffers
+  auto t_empty = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 4 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (4 * US_MAX_STAGES + 8));
+  auto h_done = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 9 + s); };   // head MMAs of epilogue group s have completed
   float* sb_smem = reinterpret_cast<float*>(bars_ptr + 512);             // scale[Cout], bias[Cout]
   float* cls_smem = sb_smem + 2 * 128;                                    // [9][Cout]
   float* hb_smem = cls_smem + 9 * 64;                                     // head bias [32]
@@ -156,9 +157,10 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
 
   if (tid == 0) {
     for (int s = 0; s < US_MAX_STAGES; ++s) {
-      ug::mbar_init(s_full(s), 1); ug::mbar_init(s_empty(s), 1); ug::mbar_init(b_full(s), 1); ug::mbar_init(b_empty(s), 1);
+      ug::mbar_init(s_full(s), 1); ug::mbar_init(s_empty(s), 1); ug::mbar_init(b_full(s), 1); ug::mbar_init(b_empty(s), 2);   // both issuers release a weight stage
     }
-    for (int s = 0; s < 2; ++s) { ug::mbar_init(t_full(s), 1); ug::mbar_init(t_empty(s), 4); ug::mbar_init(h_done(s), 1); }
+    for (int s = 0; s < 4; ++s) { ug::mbar_init(t_full(s), 1); ug::mbar_init(t_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) ug::mbar_init(h_done(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (L.out_mode == UG_OUT_HEAD_NCHW_F32) {
@@ -182,16 +184,31 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const int NS = L.n_slab_stages, NB = L.n_b_stages;
 
+  // Tiles of this CTA: t = blockIdx.x + iter * gridDim.x, iter < n_my.  They are processed in PAIRS (iter = 2p, 2p+1): two
+  // MMA-issuing warps (q = 0, 1) work on the two tiles of a pair at the same time - one warp cannot issue faster than
+  // ~600 cycles per item on the uniform datapath - and consume the SAME weight stage for both tiles (streamed weights are
+  // read once per pair from L2); slab chunks are fetched in the order (c, q).  Issuer q / epilogue group q own the
+  // accumulator buffers q, q+2, ...
+  const int n_my = ((int)L.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_pairs = (n_my + 1) >> 1;
+  const int bufs_per_q = L.n_buf >> 1;
+
   if (warp == 10) {
     // ------------------------------ slab loader: one TMA box per (tile, 64-channel chunk) ------------------------------
     if (lane == 0) {
       int cnt = 0;
-      for (int t = blockIdx.x; t < L.n_tiles; t += gridDim.x) {
-        for (int c = 0; c < L.n_chunks; ++c, ++cnt) {
-          const int s = cnt % NS;
-          if (cnt >= NS) ug::mbar_wait(s_empty(s), (uint32_t)((cnt / NS - 1) & 1));
-          us::mbar_expect_tx(s_full(s), (uint32_t)L.slab_rows * 128u);
-          us::tma_load_2d(slab0 + s * L.slab_bytes, &tm_in, L.in_coff + c * 64, t * 128 - (L.Wp + 1), s_full(s));
+      for (int p = 0; p < n_pairs; ++p) {
+        for (int c = 0; c < L.n_chunks; ++c) {
+          for (int q = 0; q < 2; ++q) {
+            const int iter = 2 * p + q;
+            if (iter >= n_my) continue;
+            const int t = blockIdx.x + iter * gridDim.x;
+            const int st = cnt % NS;
+            if (cnt >= NS) ug::mbar_wait(s_empty(st), (uint32_t)((cnt / NS - 1) & 1));
+            us::mbar_expect_tx(s_full(st), (uint32_t)L.slab_rows * 128u);
+            us::tma_load_2d(slab0 + st * L.slab_bytes, &tm_in, L.in_coff + c * 64, t * 128 - (L.Wp + 1), s_full(st));
+            ++cnt;
+          }
         }
       }
     }
@@ -203,34 +220,38 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         for (int r = 0; r < L.w_rows; r += L.w_box_rows) us::tma_load_2d(b0 + r * 128, &tm_w, 0, r, b_full(0));
       } else {
         int cnt = 0;
-        for (int t = blockIdx.x; t < L.n_tiles; t += gridDim.x) {
+        for (int p = 0; p < n_pairs; ++p) {
           for (int i = 0; i < L.n_items; ++i, ++cnt) {
-            const int s = cnt % NB;
-            if (cnt >= NB) ug::mbar_wait(b_empty(s), (uint32_t)((cnt / NB - 1) & 1));
+            const int st = cnt % NB;
+            if (cnt >= NB) ug::mbar_wait(b_empty(st), (uint32_t)((cnt / NB - 1) & 1));
             const int rows = L.items[i].b_rows, row = L.items[i].w_row;
-            us::mbar_expect_tx(b_full(s), (uint32_t)rows * 128u);
+            us::mbar_expect_tx(b_full(st), (uint32_t)rows * 128u);
             for (int r = 0; r < rows; r += L.w_box_rows)
-              us::tma_load_2d(b0 + s * US_B_STAGE_BYTES + r * 128, &tm_w, 0, row + r, b_full(s));
+              us::tma_load_2d(b0 + st * US_B_STAGE_BYTES + r * 128, &tm_w, 0, row + r, b_full(st));
           }
         }
       }
     }
-  } else if (warp == 8) {
-    // ------------------------------ MMA issuer (convergent warp, one elected lane issues) ------------------------------
-    // Everything the issue path needs is a function of kernel parameters and warp-uniform counters: the item table is read
-    // from the constant bank with uniform indices and the K16 steps of a part are unrolled with immediate descriptor
-    // increments, so that an MMA costs two uniform adds + UTCHMMA (the first version walked a shared-memory list through
-    // per-thread registers: ~45 instructions and several R2UR round trips per MMA, ~300 cycles - the tensor pipe idled).
+  } else if (warp == 8 || warp == 11) {
+    // ------------------------------ MMA issuers (convergent warps, one elected lane issues) ------------------------------
+    // Everything the issue path needs is a function of kernel parameters and warp-uniform counters: per-item issue records
+    // are read from the constant bank with uniform indices (one item ahead) and the K16 steps of a part are unrolled, so
+    // that an MMA costs two uniform adds + UTCHMMA (the first version walked a shared-memory list through per-thread
+    // registers: ~45 instructions and several R2UR round trips per MMA, ~300 cycles - the tensor pipe idled).
+    const int q = warp == 8 ? 0 : 1;
     if (resident) { ug::mbar_wait(b_full(0), 0); ug::tc_fence_after(); }
-    int ss = 0, bs = 0, iter = 0;                 // ring positions of the NEXT slab chunk / weight tile to consume
-    uint32_t s_par = 0, b_par = 0;
+    int bs = 0;                                   // weight ring position of the NEXT item (both issuers walk every pair)
+    uint32_t b_par = 0;
     const uint64_t desc_hi32 = ug::smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo0 = (uint32_t)(ug::smem_desc_sw128(0) & 0xFFFFFFFFull);
-    for (int t = blockIdx.x; t < L.n_tiles; t += gridDim.x, ++iter) {
-      const int buf = iter & 1;
-      if (iter >= 2) { ug::mbar_wait(t_empty(buf), (uint32_t)(((iter >> 1) - 1) & 1)); ug::tc_fence_after(); }
+    for (int p = 0; p < n_pairs; ++p) {
+      const bool active = 2 * p + q < n_my;        // the last pair may hold a single tile: issuer 1 then only recycles weight stages
+      const bool full = 2 * p + 1 < n_my;
+      const int buf = q + 2 * (p % bufs_per_q), use = p / bufs_per_q;
+      if (active && use >= 1) { ug::mbar_wait(t_empty(buf), (uint32_t)((use - 1) & 1)); ug::tc_fence_after(); }
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * L.tile_cols);
-      int cs = 0;
+      const int cnt0 = p * 2 * L.n_chunks;          // slab boxes issued before this pair (every earlier pair is full)
+      int cs = 0, chunk = -1;
       uint32_t a_base16 = 0;
       uint4 ra = *reinterpret_cast<const uint4*>(&L.rec[0]), rb = *(reinterpret_cast<const uint4*>(&L.rec[0]) + 1);
       for (int item = 0; item < L.n_items; ++item) {
@@ -241,11 +262,14 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         }
         const uint32_t ctl = ca.z;
         if (ctl & (1u << 16)) {           // first item of a chunk: its slab must have landed
-          ug::mbar_wait(s_full(ss), s_par);
-          cs = ss;
-          a_base16 = (slab0 + (uint32_t)ss * (uint32_t)L.slab_bytes) >> 4;
-          if (++ss == NS) { ss = 0; s_par ^= 1u; }
-          ug::tc_fence_after();
+          ++chunk;
+          if (active) {
+            const int cnt = cnt0 + (full ? 2 * chunk + q : chunk);
+            cs = cnt % NS;
+            ug::mbar_wait(s_full(cs), (uint32_t)((cnt / NS) & 1));
+            a_base16 = (slab0 + (uint32_t)cs * (uint32_t)L.slab_bytes) >> 4;
+            ug::tc_fence_after();
+          }
         }
         int cb = 0;
         uint32_t b_base16 = (b0 >> 4) + ca.y;
@@ -256,46 +280,50 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           if (++bs == NB) { bs = 0; b_par ^= 1u; }
           ug::tc_fence_after();
         }
-        // descriptor = (hi word, constant) : (lo word = LBO bit | start address >> 4); shared-memory addresses are < 2^18, so a
-        // K16 step is one 32-bit add of 2 to the lo word
-        const uint32_t a_lo = (a_base16 + ca.x) | desc_lo0;
-        const uint32_t nk = ctl & 0xffu, np = (ctl >> 8) & 0xffu;
+        if (active) {
+          // descriptor = (hi word, constant) : (lo word = LBO bit | start address >> 4); shared-memory addresses are < 2^18, so a
+          // K16 step is one 32-bit add of 2 to the lo word
+          const uint32_t a_lo = (a_base16 + ca.x) | desc_lo0;
+          const uint32_t nk = ctl & 0xffu, np = (ctl >> 8) & 0xffu;
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          if (p < (int)np) {
-            const uint32_t idesc = p ? cbw.z : cbw.x, pw = p ? cbw.w : cbw.y;
-            const uint32_t d = tmem_d + (pw & 0xffffu);
-            const uint32_t b_lo = (b_base16 + ((pw >> 16) & 0x7fffu)) | desc_lo0;
-            const uint32_t acc0 = pw >> 31;
-            if (nk == 4) {
+          for (int pp = 0; pp < 2; ++pp) {
+            if (pp < (int)np) {
+              const uint32_t idesc = pp ? cbw.z : cbw.x, pw = pp ? cbw.w : cbw.y;
+              const uint32_t d = tmem_d + (pw & 0xffffu);
+              const uint32_t b_lo = (b_base16 + ((pw >> 16) & 0x7fffu)) | desc_lo0;
+              const uint32_t acc0 = pw >> 31;
+              if (nk == 4) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u * k), desc_hi32 | (uint64_t)(b_lo + 2u * k), idesc, k ? 1u : acc0);
-            } else {
+                for (int k = 0; k < 4; ++k)
+                  us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u * k), desc_hi32 | (uint64_t)(b_lo + 2u * k), idesc, k ? 1u : acc0);
+              } else {
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u * k), desc_hi32 | (uint64_t)(b_lo + 2u * k), idesc, k ? 1u : acc0);
+                for (int k = 0; k < 2; ++k)
+                  us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u * k), desc_hi32 | (uint64_t)(b_lo + 2u * k), idesc, k ? 1u : acc0);
+              }
             }
           }
         }
-        if (!resident) us::umma_commit_elect(b_empty(cb));
-        if (ctl & (1u << 17)) us::umma_commit_elect(s_empty(cs));
+        if (!resident) us::umma_commit_elect(b_empty(cb));      // arrives at once when this warp issued nothing
+        if (active && (ctl & (1u << 17))) us::umma_commit_elect(s_empty(cs));
       }
-      us::umma_commit_elect(t_full(buf));
+      if (active) us::umma_commit_elect(t_full(buf));
     }
   } else {
     // ------------------------------ epilogue: two groups of 4 warps alternate tiles / TMEM buffers ------------------------------
     const int grp = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
-    for (int iter = grp;; iter += 2) {
+    for (int j = 0;; ++j) {             // the group's j-th tile: iter = 2j + grp, accumulator buffer grp + 2*(j % bufs_per_q)
+      const int iter = 2 * j + grp;
+      if (iter >= n_my) break;
       const int t = blockIdx.x + iter * gridDim.x;
-      if (t >= L.n_tiles) break;
+      const int buf = grp + 2 * (j % bufs_per_q);
       const int q = t * 128 + row;
       const int b = q / L.PI, r = q - b * L.PI;
       const int y = r / L.Wp, x = r - y * L.Wp;
       const bool ok = b < L.B && y >= 1 && y <= L.Hp - 2 && x >= 1 && x <= L.Wp - 2;
-      ug::mbar_wait(t_full(grp), (uint32_t)((iter >> 1) & 1));
+      ug::mbar_wait(t_full(buf), (uint32_t)((j / bufs_per_q) & 1));
       ug::tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(grp * L.tile_cols);
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * L.tile_cols);
       if (L.out_mode == UG_OUT_NHWC_BF16) {
         float clsv = 0.f;
         const float* clsw = nullptr;
@@ -333,7 +361,7 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         }
         ug::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ug::mbar_arrive(t_empty(grp));
+        if (lane == 0) ug::mbar_arrive(t_empty(buf));
       } else {
         // last up-conv (Cout = 32) + BN + ReLU, then the 1x1 head z = head_b + head_w y (separator_cnn.py:135) as a second
         // tcgen05.mma: the activated pixels (bf16, like the unfused layer pair) of two sub-pixel phases form one K-major
@@ -343,7 +371,7 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         const int Hm = (L.Hp - 2) * 2, Wm = (L.Wp - 2) * 2;
         const uint32_t ytile = head0 + 4096u + (uint32_t)grp * 16384u;
         unsigned char* yrow = head_ptr + 4096 + grp * 16384;
-        const uint32_t tcol = tmem_base + (uint32_t)(grp * L.tile_cols);
+        const uint32_t tcol = tmem_base + (uint32_t)(buf * L.tile_cols);
         const uint64_t desc_hi = ug::smem_desc_sw128(0);
         const uint32_t idesc = us::instr_desc_bf16_n(32);
         uint32_t hpar = 0;                                      // every tile of a group consumes exactly two phases of its barrier
@@ -407,7 +435,7 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         }
         ug::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ug::mbar_arrive(t_empty(grp));
+        if (lane == 0) ug::mbar_arrive(t_empty(buf));
       }
     }
   }

@@ -1,8 +1,8 @@
 #!/bin/bash
 # U-Net iteration on the GPU box: parity tests, bench line, launch list (+ optional full capture of the U-Net kernels)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_unet_gpu.py tests/test_unet_train_gpu.py -x -q 2>&1 | tail -4
-timeout 600 python bench.py --no-train --no-cpu-baseline > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; tail -3 gpurun_out/bench_iter.err
+timeout -k 10 400 python -m pytest tests/test_unet_gpu.py tests/test_unet_train_gpu.py -x -q 2>&1 | tail -4
+timeout -k 10 300 python bench.py --no-train --no-cpu-baseline > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; tail -3 gpurun_out/bench_iter.err
 python - <<'PY'
 import json
 d = json.load(open('gpurun_out/bench_iter.json'))
