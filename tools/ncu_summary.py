@@ -1,4 +1,4 @@
-"""Summarise ncu-rep files (read on the CPU box): python tools_ncu_summary.py <rep> [<rep> ...]"""
+"""Summarise ncu-rep files (read on the CPU box): python tools/ncu_summary.py <rep> [<rep> ...]"""
 import csv, subprocess, sys, json
 KEYS = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','sm__throughput.avg.pct_of_peak_sustained_elapsed','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','lts__throughput.avg.pct_of_peak_sustained_elapsed','l1tex__throughput.avg.pct_of_peak_sustained_elapsed','sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','launch__shared_mem_per_block_dynamic','launch__shared_mem_config_size','launch__occupancy_limit_shared_mem','launch__occupancy_limit_registers','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active','smsp__inst_executed.sum','sm__sass_inst_executed_op_local_ld.sum','sm__sass_inst_executed_op_local_st.sum']
 def summarise(rep):
