@@ -317,6 +317,49 @@ def run_ours(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
+    # ---- the same end-to-end step with the inputs referenced by key: clips and RIRs live in the
+    # device-side LRU caches of ingest.CachedAudioRenderer, so a step moves index arrays in and masks out.  The workload
+    # tiles N_DISTINCT mixtures, i.e. every key is a hit after the first step - reported next to `e2e`, not instead of it.
+    from move2hear_active_av_separation_b200.ingest import CachedAudioRenderer
+    cached = CachedAudioRenderer(dev, n_samples=N_SAMPLES, rir_max_taps=L_TAPS, clip_capacity=2 * K_SRC * N_DISTINCT,
+                                 rir_capacity=2 * K_SRC * N_DISTINCT, renderer=rend)
+    mono_np, rir_np, len_np = h_mono.numpy(), h_rir.numpy(), h_len.numpy()
+    clip_keys = [[("clip", (b % N_DISTINCT), k) for k in range(K_SRC)] for b in range(B)]
+    rir_keys = [[("rir", (b % N_DISTINCT), k) for k in range(K_SRC)] for b in range(B)]
+
+    def clip_loader(key):
+        return mono_np[key[1], key[2]]
+
+    def rir_loader(key):
+        return np.ascontiguousarray(rir_np[key[1], key[2], :, :int(len_np[key[1], key[2]])].T)      # wav layout [L, 2]
+
+    side = torch.cuda.Stream(dev)              # masks go back on a second stream: the D2H of step i runs under step i+1
+
+    def step_cached():
+        out = cached.render_keys(clip_keys, rir_keys, clip_loader, rir_loader)
+        with torch.no_grad():
+            mask = dec(*enc({"mixed_bin_audio_mag": out["mix_mag"], "target_class": d_tc}))
+        done = torch.cuda.Event()
+        done.record(stream)
+        with torch.cuda.stream(side):
+            side.wait_event(done)
+            h_out.copy_(mask.permute(0, 3, 1, 2), non_blocking=True)
+            mask.record_stream(side)
+
+    for _ in range(2):
+        step_cached()
+    stream.wait_stream(side)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    for _ in range(e2e_steps):
+        step_cached()
+    stream.wait_stream(side)
+    g1.record(stream)
+    barrier()
+    ms_cached = g0.elapsed_time(g1)
+    cache_stats = cached.stats()
+
     # ---- BASELINE configs[2]: separator pretraining step (dataset-path render + both U-Nets fwd/bwd + L1 losses + Adam),
     # B = 256 per GPU, gradients all-reduced (mean) across ranks over NCCL, overlapped with backward
     train = None
@@ -324,10 +367,10 @@ def run_ours(args):
     if not args.no_train:
         train, ms_train = run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_len, d_tc, barrier, stream)
 
-    times = torch.tensor([ms_total, ms_e2e, ms_train], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, ms_e2e, ms_train, ms_cached], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_train = float(times[0]), float(times[1]), float(times[2])
+    ms_total, ms_e2e, ms_train, ms_cached = (float(times[i]) for i in range(4))
     if train is not None:
         train["ms_per_step"] = ms_train / train["steps"]
         train["value"] = world * train["batch_per_gpu"] * train["steps"] / (ms_train * 1e-3)
@@ -373,6 +416,11 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps},
+        "e2e_device_cache": {"value": world * B * e2e_steps / (ms_cached * 1e-3), "unit": UNIT, "ms_per_step": ms_cached / e2e_steps,
+                             "h2d_bytes_per_step": 2 * 4 * B * K_SRC, "d2h_bytes_per_step": d2h,
+                             "rir_hit_rate": cache_stats["rir_hits"] / max(1, cache_stats["rir_hits"] + cache_stats["rir_misses"]),
+                             "note": "same step with clips / RIRs referenced by key and resident in the device-side LRU caches (ingest.py, SURVEY 8f row 1); "
+                                     "every key of this tiled workload is a hit after the first step - NOT the headline e2e, which copies every input per step"},
         "gpu_launches": OUR_LAUNCHES_PER_STEP * args.steps,
         "clocks": clocks,
         "train_step": train,

@@ -65,6 +65,37 @@ int m2h_rir_convolve(const int16_t* mono, const float* rir, const int32_t* rir_l
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same convolution with the inputs referenced by row in device-resident pools (device-side
+ * LRU caches of the clips, keyed by sound name like `_cached_mono_waveforms`, simulator_train.py:396-400, and of the RIRs,
+ * keyed by (scene, azimuth, receiver, source), simulator_train.py:402-415): per step only the index arrays cross PCIe.
+ *   clip_pool     int16 [n_clips, N]        clip_index  int32 [B, K]
+ *   rir_pool      float [n_rirs, 2, Lmax]   rir_pool_len int32 [n_rirs]   rir_index int32 [B, K]
+ */
+int m2h_rir_convolve_indexed(const int16_t* clip_pool, const int32_t* clip_index, const float* rir_pool, const int32_t* rir_pool_len,
+                             const int32_t* rir_index, int B, int K, int N, int Lmax, int16_t* waves,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * wav ingest.  Replaces scipy.io.wavfile.read (simulator_train.py:397, 409; dataset.py:157, 170) for the sample formats
+ * it returns without conversion (PCM16 -> int16, PCM32 -> int32, IEEE float32).  m2h_wav_parse is host-only: it locates
+ * the fmt / data chunks of a RIFF/WAVE image.  m2h_rir_ingest / m2h_clip_ingest run on the device: the raw interleaved
+ * frames (device pointer, e.g. an H2D copy of the file body from pinned memory) become one pool row - fp32 ear-planar
+ * [2, Lmax] (the transpose of the wav's [L, 2]; zero tail) or the int16 clip [N] (channel 0, zero tail).
+ */
+enum { M2H_WAV_PCM16 = 1, M2H_WAV_PCM32 = 2, M2H_WAV_FLOAT32 = 3 };
+typedef struct m2h_wav_info {
+  int format;            /* M2H_WAV_* */
+  int channels;
+  int sample_rate;
+  int bits_per_sample;
+  long long frames;      /* samples per channel */
+  size_t data_offset;    /* byte offset of the first frame inside the file image */
+} m2h_wav_info;
+int m2h_wav_parse(const void* file_bytes, size_t n_bytes, m2h_wav_info* out);
+int m2h_rir_ingest(const void* raw_frames, int format, int channels, int frames, float* pool_row, int Lmax, void* stream);
+int m2h_clip_ingest(const void* raw_frames, int format, int channels, int frames, int16_t* pool_row, int N, void* stream);
+
+/*
  * STFT (n_fft 1023, hop 512, periodic Hann, centre/reflect) of the mixture of K quantised sources and,
  * optionally, of the first n_gt sources alone.
  * Replaces: librosa.stft / librosa.magphase / np.angle / np.log1p at

@@ -86,6 +86,10 @@ SIGNATURES = {
     "m2h_init": (_i, [_i]),
     "m2h_render_workspace_bytes": (_sz, [_i]),
     "m2h_rir_convolve": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "m2h_rir_convolve_indexed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "m2h_wav_parse": (_i, [_vp, _sz, _vp]),
+    "m2h_rir_ingest": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
+    "m2h_clip_ingest": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "m2h_stft_waves": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "m2h_render_mixture": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "m2h_stft_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),

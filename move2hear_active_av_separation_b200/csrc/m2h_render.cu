@@ -112,24 +112,117 @@ extern "C" size_t m2h_render_workspace_bytes(int device) {
   return (size_t)n_sms * M2H_CONV_SCRATCH_F4 * sizeof(float4);
 }
 
-extern "C" int m2h_rir_convolve(const int16_t* mono, const float* rir, const int32_t* rir_len,
-                                int B, int K, int N, int Lmax, int16_t* waves,
-                                void* workspace, size_t workspace_bytes, void* stream) {
-  if (B < 0 || K <= 0 || N <= 0 || N > M2H_MAX_SAMPLES || Lmax < 0) { m2h_set_error("m2h_rir_convolve: bad sizes B=%d K=%d N=%d Lmax=%d (N <= %d)", B, K, N, Lmax, M2H_MAX_SAMPLES); return M2H_ERR_ARG; }
+static int launch_conv(const int16_t* mono, const int32_t* mono_index, const float* rir, const int32_t* rir_len, const int32_t* rir_index,
+                       int B, int K, int N, int Lmax, int16_t* waves, void* workspace, size_t workspace_bytes, void* stream, const char* who) {
+  if (B < 0 || K <= 0 || N <= 0 || N > M2H_MAX_SAMPLES || Lmax < 0) { m2h_set_error("%s: bad sizes B=%d K=%d N=%d Lmax=%d (N <= %d)", who, B, K, N, Lmax, M2H_MAX_SAMPLES); return M2H_ERR_ARG; }
   if (B == 0) return M2H_OK;
-  if (!mono || !rir_len || !waves || (!rir && Lmax > 0) || !workspace) { m2h_set_error("m2h_rir_convolve: null pointer"); return M2H_ERR_ARG; }
+  if (!mono || !rir_len || !waves || (!rir && Lmax > 0) || !workspace) { m2h_set_error("%s: null pointer", who); return M2H_ERR_ARG; }
   int dev;
   int rc = ensure_init(&dev);
   if (rc != M2H_OK) return rc;
   const int n_items = B * K;
   int grid = g_tables[dev].n_sms;
   if (grid > n_items) grid = n_items;
-  if (workspace_bytes < (size_t)grid * M2H_CONV_SCRATCH_F4 * sizeof(float4)) { m2h_set_error("m2h_rir_convolve: workspace %zu B < %zu B", workspace_bytes, (size_t)grid * M2H_CONV_SCRATCH_F4 * sizeof(float4)); return M2H_ERR_WORKSPACE; }
+  if (workspace_bytes < (size_t)grid * M2H_CONV_SCRATCH_F4 * sizeof(float4)) { m2h_set_error("%s: workspace %zu B < %zu B", who, workspace_bytes, (size_t)grid * M2H_CONV_SCRATCH_F4 * sizeof(float4)); return M2H_ERR_WORKSPACE; }
   ConvParams P;
-  P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.waves = waves; P.scratch = (float4*)workspace;
+  P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.mono_index = mono_index; P.rir_index = rir_index;
+  P.waves = waves; P.scratch = (float4*)workspace;
   P.n_items = n_items; P.N = N; P.Lmax = Lmax;
   if (conv_can_vectorise(P)) m2h_rir_conv_kernel<true><<<grid, M2H_CONV_THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(P, g_tables[dev].conv);
   else m2h_rir_conv_kernel<false><<<grid, M2H_CONV_THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(P, g_tables[dev].conv);
+  M2H_CUDA_CHECK(cudaGetLastError());
+  return M2H_OK;
+}
+
+extern "C" int m2h_rir_convolve(const int16_t* mono, const float* rir, const int32_t* rir_len,
+                                int B, int K, int N, int Lmax, int16_t* waves,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_conv(mono, nullptr, rir, rir_len, nullptr, B, K, N, Lmax, waves, workspace, workspace_bytes, stream, "m2h_rir_convolve");
+}
+
+extern "C" int m2h_rir_convolve_indexed(const int16_t* clip_pool, const int32_t* clip_index, const float* rir_pool, const int32_t* rir_pool_len,
+                                        const int32_t* rir_index, int B, int K, int N, int Lmax, int16_t* waves,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (B > 0 && (!clip_index || !rir_index)) { m2h_set_error("m2h_rir_convolve_indexed: null index"); return M2H_ERR_ARG; }
+  return launch_conv(clip_pool, clip_index, rir_pool, rir_pool_len, rir_index, B, K, N, Lmax, waves, workspace, workspace_bytes, stream, "m2h_rir_convolve_indexed");
+}
+
+// ---------------------------------------------------------------------------------------------
+// wav ingest: what scipy.io.wavfile.read + the [L, 2] -> per-ear split do on the host in
+// habitat_audio/simulator_train.py:396-415 and audio_separation/pretrain/datasets/dataset.py:155-176
+// ---------------------------------------------------------------------------------------------
+static uint32_t rd_u32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint32_t rd_u16(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+extern "C" int m2h_wav_parse(const void* bytes, size_t n_bytes, m2h_wav_info* out) {
+  if (!bytes || !out) { m2h_set_error("m2h_wav_parse: null pointer"); return M2H_ERR_ARG; }
+  const unsigned char* p = (const unsigned char*)bytes;
+  memset(out, 0, sizeof(*out));
+  if (n_bytes < 12 || memcmp(p, "RIFF", 4) != 0 || memcmp(p + 8, "WAVE", 4) != 0) { m2h_set_error("m2h_wav_parse: not a RIFF/WAVE file"); return M2H_ERR_ARG; }
+  size_t pos = 12;
+  bool have_fmt = false;
+  uint32_t tag = 0, block_align = 0;
+  while (pos + 8 <= n_bytes) {
+    const uint32_t size = rd_u32(p + pos + 4);
+    const unsigned char* body = p + pos + 8;
+    if (memcmp(p + pos, "fmt ", 4) == 0) {
+      if (size < 16 || pos + 8 + 16 > n_bytes) { m2h_set_error("m2h_wav_parse: truncated fmt chunk"); return M2H_ERR_ARG; }
+      tag = rd_u16(body); out->channels = (int)rd_u16(body + 2); out->sample_rate = (int)rd_u32(body + 4);
+      block_align = rd_u16(body + 12); out->bits_per_sample = (int)rd_u16(body + 14);
+      if (tag == 0xFFFEu && size >= 26) tag = rd_u16(body + 24);         // WAVE_FORMAT_EXTENSIBLE: first two bytes of the sub-format GUID
+      have_fmt = true;
+    } else if (memcmp(p + pos, "data", 4) == 0) {
+      if (!have_fmt) { m2h_set_error("m2h_wav_parse: data chunk before fmt chunk"); return M2H_ERR_ARG; }
+      size_t avail = n_bytes - (pos + 8);
+      size_t len = size < avail ? size : avail;                           // scipy tolerates a short final chunk
+      if (tag == 1 && out->bits_per_sample == 16) out->format = M2H_WAV_PCM16;
+      else if (tag == 1 && out->bits_per_sample == 32) out->format = M2H_WAV_PCM32;
+      else if (tag == 3 && out->bits_per_sample == 32) out->format = M2H_WAV_FLOAT32;
+      else { m2h_set_error("m2h_wav_parse: unsupported sample format (tag %u, %d bits)", tag, out->bits_per_sample); return M2H_ERR_ARG; }
+      if (out->channels < 1 || block_align != (uint32_t)(out->channels * out->bits_per_sample / 8)) { m2h_set_error("m2h_wav_parse: inconsistent block alignment"); return M2H_ERR_ARG; }
+      out->data_offset = pos + 8;
+      out->frames = (long long)(len / block_align);
+      return M2H_OK;
+    }
+    pos += 8 + (size_t)size + (size & 1u);
+  }
+  m2h_set_error("m2h_wav_parse: no data chunk");
+  return M2H_ERR_ARG;
+}
+
+// interleaved wav frames [frames][channels] (PCM16 / PCM32 / FLOAT32) -> fp32 ear-planar pool row [2][Lmax]; taps beyond
+// `frames` are zeroed.  One-channel RIRs (never produced by SoundSpaces) feed both ears.
+__global__ void rir_ingest_kernel(const unsigned char* __restrict__ raw, int format, int channels, int frames, float* __restrict__ row, int Lmax) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * Lmax; i += gridDim.x * blockDim.x) {
+    const int ear = i / Lmax, j = i - ear * Lmax;
+    float v = 0.f;
+    if (j < frames) {
+      const size_t e = (size_t)j * channels + (ear < channels ? ear : channels - 1);
+      if (format == M2H_WAV_PCM16) v = (float)reinterpret_cast<const int16_t*>(raw)[e];
+      else if (format == M2H_WAV_PCM32) v = (float)reinterpret_cast<const int32_t*>(raw)[e];
+      else v = reinterpret_cast<const float*>(raw)[e];
+    }
+    row[i] = v;
+  }
+}
+// int16 clip: channel 0 of the wav, truncated / zero-padded to N samples
+__global__ void clip_ingest_kernel(const int16_t* __restrict__ raw, int channels, int frames, int16_t* __restrict__ row, int N) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) row[i] = i < frames ? raw[(size_t)i * channels] : (int16_t)0;
+}
+
+extern "C" int m2h_rir_ingest(const void* raw_frames, int format, int channels, int frames, float* pool_row, int Lmax, void* stream) {
+  if (!pool_row || Lmax <= 0 || frames < 0 || frames > Lmax || channels < 1 || (frames > 0 && !raw_frames) ||
+      (format != M2H_WAV_PCM16 && format != M2H_WAV_PCM32 && format != M2H_WAV_FLOAT32)) { m2h_set_error("m2h_rir_ingest: bad arguments (frames %d, Lmax %d, channels %d, format %d)", frames, Lmax, channels, format); return M2H_ERR_ARG; }
+  if (((uintptr_t)raw_frames & 3) != 0) { m2h_set_error("m2h_rir_ingest: raw frames must be 4-byte aligned"); return M2H_ERR_ARG; }
+  rir_ingest_kernel<<<(2 * Lmax + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)raw_frames, format, channels, frames, pool_row, Lmax);
+  M2H_CUDA_CHECK(cudaGetLastError());
+  return M2H_OK;
+}
+extern "C" int m2h_clip_ingest(const void* raw_frames, int format, int channels, int frames, int16_t* pool_row, int N, void* stream) {
+  if (!pool_row || N <= 0 || frames < 0 || channels < 1 || (frames > 0 && !raw_frames)) { m2h_set_error("m2h_clip_ingest: bad arguments"); return M2H_ERR_ARG; }
+  if (format != M2H_WAV_PCM16) { m2h_set_error("m2h_clip_ingest: the reference's clips are 16-bit PCM (format %d given)", format); return M2H_ERR_ARG; }
+  if (((uintptr_t)raw_frames & 1) != 0) { m2h_set_error("m2h_clip_ingest: raw frames must be 2-byte aligned"); return M2H_ERR_ARG; }
+  clip_ingest_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const int16_t*)raw_frames, channels, frames, pool_row, N);
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }

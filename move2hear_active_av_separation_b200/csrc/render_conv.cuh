@@ -26,9 +26,11 @@
 #define M2H_CONV_SCRATCH_F4 8192        // float4 per CTA of spectrum scratch
 
 struct ConvParams {
-  const int16_t* mono;     // [B, K, N]
-  const float* rir;        // [B, K, 2, Lmax]  (ear-planar)
-  const int32_t* rir_len;  // [B, K]
+  const int16_t* mono;     // [B, K, N]          (or the clip pool [n_clips, N] when mono_index is set)
+  const float* rir;        // [B, K, 2, Lmax]  (ear-planar; or the RIR pool [n_rirs, 2, Lmax] when rir_index is set)
+  const int32_t* rir_len;  // [B, K]            (or [n_rirs])
+  const int32_t* mono_index;  // [B, K] row of each (mixture, source) in the clip pool, or null = identity
+  const int32_t* rir_index;   // [B, K] row in the RIR pool, or null = identity
   int16_t* waves;          // [B, K, 2, N]   rounded per-source binaural waveform (int16 full-scale units)
   float4* scratch;         // [gridDim.x, 8192]
   int n_items;             // B * K
@@ -321,7 +323,10 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
   int16_t* pend_out = nullptr;    // window of the previous inverse transform, still in the staging buffer
   int pend_off = 0;
   for (int item = cta; item < P.n_items; item += n_ctas) {
-    const int L = P.rir_len[item];
+    // device-side caches (ingest.py / m2h_rir_convolve_indexed): items reference pool rows instead of carrying their inputs
+    const int mi = P.mono_index ? P.mono_index[item] : item;
+    const int ri = P.rir_index ? P.rir_index[item] : item;
+    const int L = P.rir_len[ri];
     // taps that can reach the "same" window [c, c+N) of the full convolution: j in [c-N+1, c+N-1]
     const int c = (L - 1) / 2;
     int jmin = c - N + 1 > 0 ? c - N + 1 : 0;
@@ -340,8 +345,8 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
     }
     M2H_FOR_THREADS(tid, M2H_CONV_THREADS) {
       float2 v[32];
-      conv_load_mono<VEC, true>(v, tid, P.mono + (size_t)item * N, N);                  // N <= 16384 always
-      conv_prefetch_row(tid, P.rir + (size_t)item * 2 * P.Lmax + jmin, Leff * 4);       // ear 0, loaded four phases from now
+      conv_load_mono<VEC, true>(v, tid, P.mono + (size_t)mi * N, N);                    // N <= 16384 always
+      conv_prefetch_row(tid, P.rir + (size_t)ri * 2 * P.Lmax + jmin, Leff * 4);         // ear 0, loaded four phases from now
       if (pend_out) conv_copy_out<VEC>(s, tid, pend_out, N, pend_off);                  // under the load latency
       conv_fwd_pass_a<true>(s, tid, gtab, v);
     }
@@ -354,7 +359,7 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
     M2H_FOR_THREADS(tid, M2H_CONV_THREADS) conv_pass_c_step2<true>(s, tid, gtab, g);
     M2H_SYNC();
     for (int ear = 0; ear < 2; ++ear) {
-      const float* h = P.rir + ((size_t)item * 2 + ear) * P.Lmax + jmin;
+      const float* h = P.rir + ((size_t)ri * 2 + ear) * P.Lmax + jmin;
       M2H_FOR_THREADS(tid, M2H_CONV_THREADS) {
         float2 v[32];
         if (Leff <= 16384) {
@@ -368,7 +373,8 @@ M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables
         }
         // rows the next transforms will load: the other ear, or the next item's clip
         if (ear == 0) conv_prefetch_row(tid, h + P.Lmax, Leff * 4);
-        else if (item + n_ctas < P.n_items) conv_prefetch_row(tid, P.mono + (size_t)(item + n_ctas) * N, N * 2);
+        else if (item + n_ctas < P.n_items)
+          conv_prefetch_row(tid, P.mono + (size_t)(P.mono_index ? P.mono_index[item + n_ctas] : item + n_ctas) * N, N * 2);
       }
       pend_out = nullptr;
       M2H_SYNC();

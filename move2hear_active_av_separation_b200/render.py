@@ -197,12 +197,54 @@ def get_current_mixed_bin_audio_mag_spec(self):
     return render_sim_arrays(self, monos, rirs, list(self._current_sound_names), cfg.GT_MONO_MAG_NORM, rend)
 
 
+def get_current_mixed_bin_audio_mag_spec_cached(self):
+    r"""Variant of :func:`get_current_mixed_bin_audio_mag_spec` that keeps the clips and RIRs in device-side LRU caches
+    (``ingest.CachedAudioRenderer``): a RIR wav is read, decoded and uploaded only the first time its
+    ``(scene, azimuth, receiver, source)`` is rendered.  Same return value and side effects."""
+    from scipy.io import wavfile
+    from .ingest import CachedAudioRenderer
+    cfg = self.config.AUDIO
+    cached = getattr(self, "_m2h_cached_renderer", None)
+    if cached is None:
+        cached = self._m2h_cached_renderer = CachedAudioRenderer(renderer=get_renderer(), rir_max_taps=cfg.RIR_SAMPLING_RATE)
+    names = list(self._current_sound_names)
+
+    def clip_loader(name):
+        if name not in self._cached_mono_waveforms:
+            _, wav = wavfile.read(os.path.join(cfg.MONO_DIR, name + ".wav"))
+            self._cached_mono_waveforms[name] = wav
+        return self._cached_mono_waveforms[name]
+
+    def rir_loader(key):
+        scene, azimuth, receiver, source = key
+        path = os.path.join(cfg.RIR_DIR, scene, str(azimuth), str(receiver) + "_" + str(source) + ".wav")
+        with open(path, "rb") as f:
+            data = f.read()
+        from .ingest import parse_wav
+        info = parse_wav(data)                      # ValueError -> "file is not readable" -> zero RIR, like the reference
+        assert info.sample_rate == cfg.RIR_SAMPLING_RATE, "RIR doesn't have sampling frequency of RIR_SAMPLING_RATE kHz"
+        return data
+
+    rir_keys = [(self.current_scene_name, self.azimuth_angle, self._receiver_position_index, src)
+                for src in self._source_position_indices]
+    K = len(names)
+    out = cached.render_keys([names], [rir_keys], clip_loader, rir_loader, n_gt=K, sim_dtypes=True, want_phase=True)
+    monos = [clip_loader(n) for n in names]
+    return _finish_sim_render(self, out, monos, names, cfg.GT_MONO_MAG_NORM, cached.rend)
+
+
 def render_sim_arrays(self, monos, rirs, names, gt_mono_mag_norm, rend=None):
     """Array-level body of the simulator shim (also what the tests drive): sets the side-effect fields on ``self``."""
     rend = rend or get_renderer()
     K = len(monos)
     (mono_d, rir_d, len_d), _ = rend.pack_sources(monos, rirs)
     out = rend.render(mono_d, rir_d, len_d, n_gt=K, sim_dtypes=True, want_phase=True)
+    return _finish_sim_render(self, out, monos, names, gt_mono_mag_norm, rend)
+
+
+def _finish_sim_render(self, out, monos, names, gt_mono_mag_norm, rend):
+    """Side-effect fields + return value of the simulator render from the device results of one mixture."""
+    K = len(monos)
     gt = out["gt"][0].cpu().numpy()                       # [K,512,T,4] fp16
     self._gt_bin_audio_components = [gt[k] for k in range(K)]
     self._gt_mono_audio_components = []

@@ -58,7 +58,7 @@ extern "C" int emu_rir_convolve(const int16_t* mono, const float* rir, const int
   ConvSmem* s = new ConvSmem;
   ConvParams P;
   P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.waves = waves; P.scratch = scratch.data();
-  P.n_items = B * K; P.N = N; P.Lmax = Lmax;
+  P.n_items = B * K; P.N = N; P.Lmax = Lmax; P.mono_index = nullptr; P.rir_index = nullptr;
   const bool vec = conv_can_vectorise(P);      // same dispatch rule as m2h_rir_convolve
   for (int cta = 0; cta < n_ctas; ++cta) {
     if (vec) conv_cta_body<true>(P, *s, &g_ct, cta, n_ctas); else conv_cta_body<false>(P, *s, &g_ct, cta, n_ctas);

@@ -1,0 +1,102 @@
+"""wav ingest + device-side clip / RIR caches against scipy.io.wavfile and the direct render."""
+import io
+
+import numpy as np
+import pytest
+from scipy.io import wavfile
+
+from move2hear_active_av_separation_b200 import _lib
+
+
+def wav_bytes(rate, arr):
+    f = io.BytesIO()
+    wavfile.write(f, rate, arr)
+    return f.getvalue()
+
+
+@pytest.mark.parametrize("dtype,shape", [(np.int16, (16000,)), (np.int16, (777, 2)), (np.int32, (100, 2)), (np.float32, (4001, 2)), (np.float32, (0, 2))])
+def test_parse_wav_matches_scipy(dtype, shape):
+    from move2hear_active_av_separation_b200.ingest import WAV_FLOAT32, WAV_PCM16, WAV_PCM32, parse_wav
+    rng = np.random.default_rng(1)
+    arr = (rng.standard_normal(shape) * 1000).astype(dtype)
+    data = wav_bytes(16000, arr)
+    info = parse_wav(data)
+    sr, want = wavfile.read(io.BytesIO(data))
+    assert info.sample_rate == sr == 16000
+    assert info.frames == want.shape[0] and info.channels == (1 if want.ndim == 1 else want.shape[1])
+    assert info.format == {np.dtype(np.int16): WAV_PCM16, np.dtype(np.int32): WAV_PCM32, np.dtype(np.float32): WAV_FLOAT32}[np.dtype(dtype)]
+    n = want.size * want.dtype.itemsize
+    got = np.frombuffer(data, np.uint8)[info.data_offset: info.data_offset + n].view(dtype).reshape(want.shape)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_parse_wav_rejects_what_the_reference_treats_as_unreadable():
+    from move2hear_active_av_separation_b200.ingest import parse_wav
+    for bad in (b"", b"not a wav file at all", wav_bytes(16000, np.zeros((10, 2), np.int16))[:30],
+                wav_bytes(16000, np.zeros((10, 2), np.uint8))):          # 8-bit PCM: wavfile.read would give uint8, never used by the reference
+        with pytest.raises(ValueError):
+            parse_wav(bad)
+
+
+def test_row_cache_lru_and_pinning():
+    from move2hear_active_av_separation_b200.ingest import RowCache
+    c = RowCache(3)
+    pinned = set()
+    rows = [c.lookup(k, pinned)[0] for k in "abc"]
+    assert sorted(rows) == [0, 1, 2] and c.misses == 3
+    pinned = set()
+    assert c.lookup("a", pinned) == (rows[0], True)              # "a" becomes most recent and is pinned for this batch
+    row_d, hit = c.lookup("d", pinned)
+    assert not hit and row_d == rows[1]                           # "b" was least recently used
+    row_e, hit = c.lookup("e", pinned)
+    assert not hit and row_e == rows[2]
+    with pytest.raises(_lib.M2HError):
+        c.lookup("f", pinned)                                     # every row belongs to the current batch
+
+
+@pytest.mark.gpu
+def test_cached_render_is_bit_identical_to_direct_render():
+    import torch
+    from move2hear_active_av_separation_b200.ingest import CachedAudioRenderer
+    from move2hear_active_av_separation_b200.render import AudioRenderer
+    rng = np.random.default_rng(7)
+    N = 16000
+    clips = {f"s{i}": np.round(3000 * rng.standard_normal(N)).astype(np.int16) for i in range(5)}
+    clips["short"] = np.round(3000 * rng.standard_normal(9000)).astype(np.int16)          # zero-padded to N
+    rirs = {}
+    for i, (L, dt) in enumerate([(16000, np.float32), (4001, np.float32), (12000, np.int16), (7, np.int32), (15999, np.float32), (8000, np.float32)]):
+        a = rng.standard_normal((L, 2)) * np.exp(-np.arange(L) / (L / 6 + 1))[:, None]
+        rirs[("scene", 0, i, i + 1)] = (a * (0.05 if dt == np.float32 else 40)).astype(dt)
+    rirs[("scene", 0, 99, 0)] = None                               # unreadable file -> zero RIR
+    rirs[("scene", 0, 98, 0)] = np.zeros((0, 2), np.float32)       # empty file -> zero RIR
+    as_bytes = {k: (wav_bytes(16000, v) if v is not None and i % 2 == 0 else v) for i, (k, v) in enumerate(rirs.items())}
+    clip_bytes = {k: (wav_bytes(16000, v) if i % 2 else v) for i, (k, v) in enumerate(clips.items())}
+    loads = {"clip": 0, "rir": 0}
+
+    def clip_loader(name):
+        loads["clip"] += 1
+        return clip_bytes[name]
+
+    def rir_loader(key):
+        loads["rir"] += 1
+        return as_bytes[key]
+
+    rend = AudioRenderer()
+    cached = CachedAudioRenderer(renderer=rend, rir_capacity=5, clip_capacity=4)         # smaller than the key sets (8 / 6): evictions happen
+    ckeys, rkeys = list(clips), list(rirs)
+    for step in range(10):
+        B, K = 2, 2
+        ck = [[ckeys[int(rng.integers(len(ckeys)))] for _ in range(K)] for _ in range(B)]
+        rk = [[rkeys[int(rng.integers(len(rkeys)))] for _ in range(K)] for _ in range(B)]
+        out = cached.render_keys(ck, rk, clip_loader, rir_loader, n_gt=1)
+        for b in range(B):
+            monos = [np.pad(clips[c], (0, N - len(clips[c]))) for c in ck[b]]
+            rr = [rirs[r] if rirs[r] is not None else np.zeros((0, 2), np.float32) for r in rk[b]]
+            (m, r, ln), _ = rend.pack_sources(monos, rr)
+            want = rend.render(m, r, ln, n_gt=1)
+            assert torch.equal(out["waves"][b], want["waves"][0])
+            assert torch.equal(out["mix_mag"][b], want["mix_mag"][0])
+            assert torch.equal(out["gt"][b], want["gt"][0])
+    st = cached.stats()
+    assert st["rir_hits"] + st["rir_misses"] == 40 and st["rir_misses"] == loads["rir"] and st["clip_misses"] == loads["clip"]
+    assert st["rir_hits"] > 0 and st["rir_misses"] > len(rkeys) - 1      # hits and evictions both occurred
