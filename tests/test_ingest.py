@@ -100,3 +100,44 @@ def test_cached_render_is_bit_identical_to_direct_render():
     st = cached.stats()
     assert st["rir_hits"] + st["rir_misses"] == 40 and st["rir_misses"] == loads["rir"] and st["clip_misses"] == loads["clip"]
     assert st["rir_hits"] > 0 and st["rir_misses"] > len(rkeys) - 1      # hits and evictions both occurred
+
+
+@pytest.mark.gpu
+def test_cached_simulator_shim_equals_file_reading_shim(tmp_path):
+    """get_current_mixed_bin_audio_mag_spec (wav files read every step, simulator_train.py:386-486) vs the cached variant."""
+    import os
+    from types import SimpleNamespace
+    from move2hear_active_av_separation_b200 import render as MR
+    rng = np.random.default_rng(3)
+    mono_dir, rir_dir = tmp_path / "mono", tmp_path / "rirs"
+    (rir_dir / "sceneA" / "90").mkdir(parents=True)
+    mono_dir.mkdir()
+    for name in ("dog", "speech"):
+        wavfile.write(str(mono_dir / (name + ".wav")), 16000, np.round(3000 * rng.standard_normal(16000)).astype(np.int16))
+    for recv in (4, 5):
+        for src, L in ((11, 16000), (12, 9000)):
+            a = (rng.standard_normal((L, 2)) * np.exp(-np.arange(L) / (L / 6))[:, None] * 0.05).astype(np.float32)
+            wavfile.write(str(rir_dir / "sceneA" / "90" / f"{recv}_{src}.wav"), 16000, a)
+    (rir_dir / "sceneA" / "90" / "6_11.wav").write_bytes(b"garbage")                    # unreadable -> zero RIR in both shims
+    wavfile.write(str(rir_dir / "sceneA" / "90" / "6_12.wav"), 16000, np.zeros((0, 2), np.float32))     # empty -> zero RIR
+
+    def make_sim():
+        cfg = SimpleNamespace(AUDIO=SimpleNamespace(MONO_DIR=str(mono_dir), RIR_DIR=str(rir_dir), RIR_SAMPLING_RATE=16000,
+                                                    GT_MONO_MAG_NORM=1.2, NORM_TYPE="l2"))
+        return SimpleNamespace(config=cfg, _cached_mono_waveforms={}, _cached_mono_specs={}, _current_sound_names=["dog", "speech"],
+                               _source_position_indices=[11, 12], current_scene_name="sceneA", azimuth_angle=90,
+                               _receiver_position_index=4)
+
+    a, b = make_sim(), make_sim()
+    for recv in (4, 5, 4, 6, 5):
+        a._receiver_position_index = b._receiver_position_index = recv
+        obs_a = MR.get_current_mixed_bin_audio_mag_spec(a)
+        obs_b = MR.get_current_mixed_bin_audio_mag_spec_cached(b)
+        assert obs_a.dtype == obs_b.dtype == np.float16 and np.array_equal(obs_a.view(np.uint16), obs_b.view(np.uint16))
+        for x, y in zip(a._gt_bin_audio_components, b._gt_bin_audio_components):
+            assert np.array_equal(x.view(np.uint16), y.view(np.uint16))
+        for x, y in zip(a._gt_mono_audio_components, b._gt_mono_audio_components):
+            assert np.array_equal(x.view(np.uint16), y.view(np.uint16))
+        assert np.array_equal(a._mixed_bin_audio_phase.view(np.uint16), b._mixed_bin_audio_phase.view(np.uint16))
+    st = b._m2h_cached_renderer.stats()
+    assert st["rir_misses"] == 6 and st["rir_hits"] == 4 and st["clip_misses"] == 2
