@@ -360,6 +360,46 @@ def run_ours(args):
     ms_cached = g0.elapsed_time(g1)
     cache_stats = cached.stats()
 
+    # ---- BASELINE configs[3]: the rollout step of one rank (14 environments): render + separator inference, eager launches
+    # vs one CUDA-graph replay (graphs.GraphedSeparation); device-resident inputs, latency per step
+    from move2hear_active_av_separation_b200.graphs import GraphedSeparation
+    B_ROLL = 14
+    rm, rr, rl, rt = d_mono[:B_ROLL], d_rir[:B_ROLL], d_len[:B_ROLL], d_tc[:B_ROLL]
+    graphed = GraphedSeparation(enc, dec, dev, B_ROLL, K_SRC, N_SAMPLES, L_TAPS, renderer=rend)
+
+    def roll_eager():
+        waves = rend.rir_convolve(rm, rr, rl)
+        mix, _, _ = rend.stft_waves(waves)
+        with torch.no_grad():
+            return dec(*enc({"mixed_bin_audio_mag": mix, "target_class": rt}))
+
+    def time_calls(fn, n):
+        for _ in range(5):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            fn()
+        b.record(stream)
+        barrier()
+        return a.elapsed_time(b) / n
+
+    def latency(fn, n):        # what the RL loop sees: the result is needed before the next environment step
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+            torch.cuda.synchronize(dev)
+        return 1e3 * (time.perf_counter() - t0) / n
+
+    ms_roll_eager = time_calls(roll_eager, 50)
+    ms_roll_graph = time_calls(lambda: graphed(rm, rr, rl, rt), 50)
+    lat_roll_eager = latency(roll_eager, 50)
+    lat_roll_graph = latency(lambda: graphed(rm, rr, rl, rt), 50)
+
     # ---- BASELINE configs[2]: separator pretraining step (dataset-path render + both U-Nets fwd/bwd + L1 losses + Adam),
     # B = 256 per GPU, gradients all-reduced (mean) across ranks over NCCL, overlapped with backward
     train = None
@@ -421,6 +461,11 @@ def run_ours(args):
                              "rir_hit_rate": cache_stats["rir_hits"] / max(1, cache_stats["rir_hits"] + cache_stats["rir_misses"]),
                              "note": "same step with clips / RIRs referenced by key and resident in the device-side LRU caches (ingest.py, SURVEY 8f row 1); "
                                      "every key of this tiled workload is a hit after the first step - NOT the headline e2e, which copies every input per step"},
+        "rollout_step": {"workload": "configs[3] per-rank rollout step: 14 mixtures (K=2) rendered + binSep U-Net inference, inputs on the device",
+                         "batch": B_ROLL, "gpu_ms_eager": ms_roll_eager, "gpu_ms_cuda_graph": ms_roll_graph,
+                         "latency_ms_eager": lat_roll_eager, "latency_ms_cuda_graph": lat_roll_graph,
+                         "note": "gpu_ms: back-to-back calls timed with CUDA events; latency_ms: wall clock per call with a device synchronise after each (host launch path included)",
+                         "mixtures_per_s_cuda_graph": world * B_ROLL / (lat_roll_graph * 1e-3)},
         "gpu_launches": OUR_LAUNCHES_PER_STEP * args.steps,
         "clocks": clocks,
         "train_step": train,

@@ -291,10 +291,13 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
     for (int i = tid; i < 2048; i += M2H_STFT_THREADS) s.bf[(i & 7) * 256 + (i >> 3)] = gt->bf[i];
   }
   M2H_SYNC();
-  const int n_items = P.B * P.n_signals;
+  // work item = (mixture, signal, group of four frames): small batches (the 14 environments of a rollout rank) still fill the GPU
+  const int n_quads = (P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS;
+  const int n_items = P.B * P.n_signals * n_quads;
   for (int item = cta; item < n_items; item += n_ctas) {
-    const int b = item / P.n_signals, sig = item % P.n_signals;
-    for (int t0 = 0; t0 < P.T; t0 += M2H_STFT_GROUPS) {
+    const int bs = item / n_quads, t0 = (item - bs * n_quads) * M2H_STFT_GROUPS;
+    const int b = bs / P.n_signals, sig = bs - b * P.n_signals;
+    {
       // each 128-thread group owns one frame pair and its buffer: only the group meets between the passes, the four
       // groups of a CTA drift apart freely
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_stage(P, s, tid, b, sig, t0);

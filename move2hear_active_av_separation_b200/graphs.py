@@ -1,0 +1,70 @@
+"""CUDA-graph replay of the fixed-shape rollout step: render + separator inference for the B environments of a rank.
+
+In the reference's RL loop every environment step renders one mixture per env worker and the trainer runs the separator on
+the stacked observations (audio_separation/rl/ppo/ppo_trainer.py:296-319; BASELINE config 4: 8 ranks x 14 envs).  At
+B = 14 the kernels take ~0.2 ms while ~15 launches plus the Python around them take longer, so the whole step - RIR
+convolution, STFT, encoder, decoder - is captured once into a CUDA graph and replayed: one launch per step.  (CUDA streams
+and graphs, not a tracing compiler: the graph contains exactly the kernels of the eager path.)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .render import AudioRenderer
+
+
+class GraphedSeparation:
+    """``(mono, rir, rir_len, target_class) -> mask`` for a fixed batch shape, replayed from a CUDA graph.
+
+    Inputs are copied into static device buffers (host or device tensors accepted); the returned mask - the reference's
+    ``[B, 512, 32, C]`` view - lives in graph-owned memory and is overwritten by the next call.
+    """
+
+    def __init__(self, enc, dec, device, B: int, K: int = 2, N: int = 16000, Lmax: int = 16000,
+                 renderer: Optional[AudioRenderer] = None, warmup: int = 3):
+        if not torch.cuda.is_available():
+            raise _lib.M2HError("no CUDA device: the B200 path has no CPU fallback")
+        if enc.training or dec.training:
+            raise _lib.M2HError("GraphedSeparation captures the inference path: call .eval() on the separator first")
+        self.device = torch.device(device)
+        self.enc, self.dec = enc, dec
+        self.rend = renderer or AudioRenderer(self.device)
+        dev = self.device
+        self.mono = torch.zeros((B, K, N), dtype=torch.int16, device=dev)
+        self.rir = torch.zeros((B, K, 2, Lmax + (Lmax & 1)), dtype=torch.float32, device=dev)
+        self.rir_len = torch.zeros((B, K), dtype=torch.int32, device=dev)
+        self.target_class = torch.zeros((B, 1), dtype=torch.int64, device=dev)
+        self._waves = torch.empty((B, K, 2, N), dtype=torch.int16, device=dev)
+        self.obs = None
+        self.mask = None
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                 # warm-up outside the capture: weight packing, lazy module state
+            for _ in range(max(1, warmup)):
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.obs, self.mask = self._step()
+
+    def _step(self):
+        waves = self.rend.rir_convolve(self.mono, self.rir, self.rir_len, out=self._waves)
+        mix, _, _ = self.rend.stft_waves(waves)
+        with torch.no_grad():
+            mask = self.dec(*self.enc({"mixed_bin_audio_mag": mix, "target_class": self.target_class}))
+        return mix, mask
+
+    def __call__(self, mono, rir, rir_len, target_class):
+        L = rir.shape[-1]
+        if L > self.rir.shape[-1]:
+            raise _lib.M2HError(f"RIR of {L} taps exceeds the captured Lmax = {self.rir.shape[-1]}")
+        self.mono.copy_(mono, non_blocking=True)
+        self.rir[..., :L].copy_(rir, non_blocking=True)          # taps beyond rir_len are never read
+        self.rir_len.copy_(rir_len, non_blocking=True)
+        self.target_class.copy_(target_class.reshape(self.target_class.shape), non_blocking=True)
+        self.graph.replay()
+        return self.mask
