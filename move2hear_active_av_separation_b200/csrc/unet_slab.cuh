@@ -148,7 +148,7 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   auto t_empty = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 4 + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (4 * US_MAX_STAGES + 8));
   auto h_done = [&](int s) { return bars + 8u * (4 * US_MAX_STAGES + 9 + s); };   // head MMAs of epilogue group s have completed
-  float* sb_smem = reinterpret_cast<float*>(bars_ptr + 512);             // scale[Cout], bias[Cout]
+  float* sb_smem = reinterpret_cast<float*>(bars_ptr + 512);             // (scale, bias) pairs [Cout]: one 16-byte load = two channels
   float* cls_smem = sb_smem + 2 * 128;                                    // [9][Cout]
   float* hb_smem = cls_smem + 9 * 64;                                     // head bias [32]
 
@@ -171,7 +171,7 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     if (tid < 32) hb_smem[tid] = L.head_b[tid];
     us::fence_async_smem();
   }
-  for (int i = tid; i < L.Cout; i += US_THREADS) { sb_smem[i] = L.scale ? L.scale[i] : 1.f; sb_smem[128 + i] = L.bias ? L.bias[i] : 0.f; }
+  for (int i = tid; i < L.Cout; i += US_THREADS) { sb_smem[2 * i] = L.scale ? L.scale[i] : 1.f; sb_smem[2 * i + 1] = L.bias ? L.bias[i] : 0.f; }
   if (L.cls != nullptr)
     for (int i = tid; i < 9 * L.Cout; i += US_THREADS) cls_smem[i] = L.cls_w[i];
   if (warp == 8) {
@@ -341,12 +341,19 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
             ug::tmem_ld32(trow + (uint32_t)(ph * L.Cout + cb), v);
             if (!ok) continue;
             float yv[32];
+            // (Leaky)ReLU with slope in [0, 1]: max(a, slope * a)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float a = __uint_as_float(v[i]);
-              if (clsw) a = fmaf(clsv, clsw[cb + i], a);
-              a = fmaf(a, sb_smem[cb + i], sb_smem[128 + cb + i]);
-              yv[i] = a > 0.f ? a : a * L.slope;
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s01 = *reinterpret_cast<const float4*>(sb_smem + 2 * (cb + i));
+              const float4 s23 = *reinterpret_cast<const float4*>(sb_smem + 2 * (cb + i) + 4);
+              float a0 = __uint_as_float(v[i]), a1 = __uint_as_float(v[i + 1]), a2 = __uint_as_float(v[i + 2]), a3 = __uint_as_float(v[i + 3]);
+              if (clsw) {
+                const float4 c4 = *reinterpret_cast<const float4*>(clsw + cb + i);
+                a0 = fmaf(clsv, c4.x, a0); a1 = fmaf(clsv, c4.y, a1); a2 = fmaf(clsv, c4.z, a2); a3 = fmaf(clsv, c4.w, a3);
+              }
+              a0 = fmaf(a0, s01.x, s01.y); a1 = fmaf(a1, s01.z, s01.w); a2 = fmaf(a2, s23.x, s23.y); a3 = fmaf(a3, s23.z, s23.w);
+              yv[i] = fmaxf(a0, a0 * L.slope); yv[i + 1] = fmaxf(a1, a1 * L.slope);
+              yv[i + 2] = fmaxf(a2, a2 * L.slope); yv[i + 3] = fmaxf(a3, a3 * L.slope);
             }
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
@@ -384,10 +391,11 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
             ug::tmem_ld32(trow + (uint32_t)((rd * 2 + pl) * 32), v);
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              float a0 = fmaf(__uint_as_float(v[i]), sb_smem[i], sb_smem[128 + i]);
-              float a1 = fmaf(__uint_as_float(v[i + 1]), sb_smem[i + 1], sb_smem[128 + i + 1]);
-              a0 = a0 > 0.f ? a0 : a0 * L.slope;
-              a1 = a1 > 0.f ? a1 : a1 * L.slope;
+              const float4 s01 = *reinterpret_cast<const float4*>(sb_smem + 2 * i);
+              float a0 = fmaf(__uint_as_float(v[i]), s01.x, s01.y);
+              float a1 = fmaf(__uint_as_float(v[i + 1]), s01.z, s01.w);
+              a0 = fmaxf(a0, a0 * L.slope);
+              a1 = fmaxf(a1, a1 * L.slope);
               __nv_bfloat162 t2 = __floats2bfloat162_rn(a0, a1);
               pk[pl][i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
             }
