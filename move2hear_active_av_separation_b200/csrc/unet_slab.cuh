@@ -432,11 +432,17 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
           ug::tmem_ld32(trow + (uint32_t)(rd * 64), z0);
           ug::tmem_ld32(trow + (uint32_t)(rd * 64 + 32), z1);
           if (ok) {
+            float* on = o + rd * Wm;
+            const size_t plane = (size_t)Hm * Wm;
 #pragma unroll
-            for (int n = 0; n < 32; ++n) {
-              if (n < L.n_valid) {
-                const float hb = hb_smem[n];
-                *reinterpret_cast<float2*>(o + (size_t)n * Hm * Wm + rd * Wm) = make_float2(__uint_as_float(z0[n]) + hb, __uint_as_float(z1[n]) + hb);
+            for (int n4 = 0; n4 < 32; n4 += 4) {
+              if (n4 < L.n_valid) {              // n_valid is 16 or 32
+                const float4 hb = *reinterpret_cast<const float4*>(hb_smem + n4);
+                *reinterpret_cast<float2*>(on) = make_float2(__uint_as_float(z0[n4]) + hb.x, __uint_as_float(z1[n4]) + hb.x);
+                *reinterpret_cast<float2*>(on + plane) = make_float2(__uint_as_float(z0[n4 + 1]) + hb.y, __uint_as_float(z1[n4 + 1]) + hb.y);
+                *reinterpret_cast<float2*>(on + 2 * plane) = make_float2(__uint_as_float(z0[n4 + 2]) + hb.z, __uint_as_float(z1[n4 + 2]) + hb.z);
+                *reinterpret_cast<float2*>(on + 3 * plane) = make_float2(__uint_as_float(z0[n4 + 3]) + hb.w, __uint_as_float(z1[n4 + 3]) + hb.w);
+                on += 4 * plane;
               }
             }
           }
