@@ -383,20 +383,29 @@ static int make_tmap_nd(CUtensorMap* tm, const void* base, int rank, const cuuin
   return M2H_OK;
 }
 // TMA-fed layer launch (unet_gemm_tma.cuh) for Cin >= 64 layers with bf16 NHWC output; falls back to the gather kernel otherwise
-template <int BN>
-static int launch_tma_bn(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const UGLayer& L, const UTGeom& G, int n_mtiles, cudaStream_t st) {
+template <int BN, bool DEEP>
+static int launch_tma_cfg(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const UGLayer& L, const UTGeom& G, dim3 grid, cudaStream_t st) {
   static bool attr_set[M2H_MAX_DEVICES];
   int dev = 0;
   M2H_CUDA_CHECK(cudaGetDevice(&dev));
   if (!attr_set[dev]) {
-    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, UTCfg<BN>::kSmemBytes));
-    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, UTCfg<BN, DEEP>::kSmemBytes));
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_kernel<BN, DEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[dev] = true;
   }
-  dim3 grid(n_mtiles, L.Cout / BN, L.n_phase);
-  unet_gemm_tma_kernel<BN><<<grid, UT_THREADS, UTCfg<BN>::kSmemBytes, st>>>(tm_a, tm_w, L, G);
+  unet_gemm_tma_kernel<BN, DEEP><<<grid, UT_THREADS, UTCfg<BN, DEEP>::kSmemBytes, st>>>(tm_a, tm_w, L, G);
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
+}
+template <int BN>
+static int launch_tma_bn(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const UGLayer& L, const UTGeom& G, int n_mtiles, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  M2H_CUDA_CHECK(cudaGetDevice(&dev));
+  M2H_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  dim3 grid(n_mtiles, L.Cout / BN, L.n_phase);
+  // at most one CTA per SM anyway: give it the whole shared memory as ring depth
+  if ((long long)grid.x * grid.y * grid.z <= sms) return launch_tma_cfg<BN, true>(tm_a, tm_w, L, G, grid, st);
+  return launch_tma_cfg<BN, false>(tm_a, tm_w, L, G, grid, st);
 }
 static int launch_layer_auto(const UGLayer& L, int bn, int B, cudaStream_t st) {
   static int use_tma = -1;

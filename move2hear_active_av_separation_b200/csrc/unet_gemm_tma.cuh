@@ -20,18 +20,21 @@ struct UTGeom {
   int B;
 };
 
-template <int BN> struct UTCfg {
-  static constexpr int kStages = BN >= 128 ? 3 : 4;
+// DEEP = false: 3-4 stages, two CTAs per SM (grids of several waves).  DEEP = true: a grid that leaves at most one CTA per
+// SM (the 1x1 / 2x2 / 4x4 layers: 32-128 CTAs at B = 1024) keeps 6-7 stages in flight instead - the ring depth, not the
+// tensor pipe, sets the pace of a lone CTA (TMA round trip ~1 us per stage).
+template <int BN, bool DEEP = false> struct UTCfg {
+  static constexpr int kStages = DEEP ? (BN >= 128 ? 6 : 7) : (BN >= 128 ? 3 : 4);
   static constexpr int kABytes = 16384, kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(UT_THREADS, 2)
+template <int BN, bool DEEP = false>
+__global__ void __launch_bounds__(UT_THREADS, DEEP ? 1 : 2)
 unet_gemm_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ UGLayer L,
                      const __grid_constant__ UTGeom G) {
-  using C = UTCfg<BN>;
+  using C = UTCfg<BN, DEEP>;
   extern __shared__ unsigned char ut_smem_raw[];
   const uint32_t raw = ug::smem_u32(ut_smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
