@@ -260,6 +260,8 @@ struct PackInParams {
   __nv_bfloat16* x0_plain;     // optional second copy, plain haloed NHWC [B][34][34][32] (weight-gradient operand)
 };
 __global__ void pack_input_kernel(const PackInParams P) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (b, h, w)
   if (i >= P.B * 1024) return;
   const int w = i & 31, h = (i >> 5) & 31, b = i >> 10;
@@ -288,6 +290,8 @@ __global__ void pack_input_kernel(const PackInParams P) {
   }
 }
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = __bfloat162float(in[i]);
 }
 // zero the one-pixel border of the five haloed feature maps (the kernels only ever write interiors): one thread per
@@ -314,6 +318,22 @@ __global__ void clear_halo_kernel(const HaloParams P) {
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
+// Launch with programmatic stream serialisation (see ug::pdl_wait): the forward pass is a chain of 14 short kernels, and
+// each one's prologue now overlaps the tail of its predecessor.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("M2H_NO_PDL"); enabled = (e && atoi(e)) ? 0 : 1; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static bool g_unet_attr_set[M2H_MAX_DEVICES];
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -393,8 +413,7 @@ static int launch_tma_cfg(const CUtensorMap& tm_a, const CUtensorMap& tm_w, cons
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_kernel<BN, DEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[dev] = true;
   }
-  unet_gemm_tma_kernel<BN, DEEP><<<grid, UT_THREADS, UTCfg<BN, DEEP>::kSmemBytes, st>>>(tm_a, tm_w, L, G);
-  M2H_CUDA_CHECK(cudaGetLastError());
+  M2H_CUDA_CHECK(launch_pdl(unet_gemm_tma_kernel<BN, DEEP>, grid, dim3(UT_THREADS), (size_t)UTCfg<BN, DEEP>::kSmemBytes, st, tm_a, tm_w, L, G));
   return M2H_OK;
 }
 template <int BN>
@@ -501,8 +520,7 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
   M2H_CUDA_CHECK(cudaGetDevice(&dev));
   M2H_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const unsigned grid = (unsigned)(L.n_tiles < sms ? L.n_tiles : sms);
-  unet_slab_kernel<<<grid, US_THREADS, us::smem_bytes(L.slab_bytes, L.n_slab_stages, L.n_b_stages, w_rows, L.head_bytes), st>>>(tm_in, tm_w, L);
-  M2H_CUDA_CHECK(cudaGetLastError());
+  M2H_CUDA_CHECK(launch_pdl(unet_slab_kernel, dim3(grid), dim3(US_THREADS), (size_t)us::smem_bytes(L.slab_bytes, L.n_slab_stages, L.n_b_stages, w_rows, L.head_bytes), st, tm_in, tm_w, L));
   return M2H_OK;
 }
 
@@ -618,7 +636,7 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
   PackInParams pp;
   pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.x0; pp.B = B; pp.x0_plain = nullptr;
   for (int i = 0; i < 4; ++i) pp.ms[i] = convert_bin2mono ? (long long)mask_strides[i] : 0;
-  pack_input_kernel<<<(B * 1024 + 255) / 256, 256, 0, st>>>(pp);
+  M2H_CUDA_CHECK(launch_pdl(pack_input_kernel, dim3((B * 1024 + 255) / 256), dim3(256), (size_t)0, st, pp));
   M2H_CUDA_CHECK(cudaGetLastError());
 
   {  // layer 0 on the slab kernel: x0 (space-to-depth, 18x18 cells x 128 ch) -> cat1[..., 64:128]
@@ -654,7 +672,7 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
     if (rc != M2H_OK) return rc;
   }
   if (bottleneck_f32) {
-    bf16_to_f32_kernel<<<(B * 512 + 255) / 256, 256, 0, st>>>(W.bott, bottleneck_f32, (size_t)B * 512);
+    M2H_CUDA_CHECK(launch_pdl(bf16_to_f32_kernel, dim3((B * 512 + 255) / 256), dim3(256), (size_t)0, st, (const __nv_bfloat16*)W.bott, bottleneck_f32, (size_t)B * 512));
     M2H_CUDA_CHECK(cudaGetLastError());
   }
   return M2H_OK;

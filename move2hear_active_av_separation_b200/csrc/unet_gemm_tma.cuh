@@ -64,6 +64,8 @@ unet_gemm_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   ug::tc_fence_before();
   __syncthreads();
   ug::tc_fence_after();
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 5) {

@@ -181,6 +181,8 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   ug::tc_fence_before();
   __syncthreads();
   ug::tc_fence_after();
+  ug::pdl_wait();                      // everything above touched shared memory, TMEM and packed parameters only
+  ug::pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   const int NS = L.n_slab_stages, NB = L.n_b_stages;
 
