@@ -23,6 +23,7 @@
   #define M2H_SYNC() do {} while (0)
   #define M2H_SYNC_GROUP128() do {} while (0)
   #define M2H_SYNC_WARP() do {} while (0)
+  #define M2H_PDL_WAIT() do {} while (0)
   #define M2H_UNROLL
   #define M2H_RESTRICT
   M2H_DEV float m2h_rintf(float v) { return nearbyintf(v); }
@@ -56,6 +57,8 @@
   }
   #define M2H_SYNC_GROUP128() m2h_sync_group128()
   #define M2H_SYNC_WARP() __syncwarp()
+  // programmatic dependent launch (see unet_gemm.cuh::pdl_wait): wait for the predecessor, then let the successor's prologue start
+  #define M2H_PDL_WAIT() asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory")
   #define M2H_UNROLL _Pragma("unroll")
   #define M2H_RESTRICT __restrict__
   M2H_DEV float m2h_rintf(float v) { return rintf(v); }

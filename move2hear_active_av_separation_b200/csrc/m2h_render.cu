@@ -49,6 +49,22 @@ int m2h_num_sms(int dev) { return g_tables[dev].n_sms; }
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
+// launch with programmatic stream serialisation (M2H_PDL_WAIT in the kernels): the STFT kernel stages its tables while the
+// last convolution items finish
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, void* stream, Args&&... args) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("M2H_NO_PDL"); enabled = (e && atoi(e)) ? 0 : 1; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // VEC = packed row accesses (even N / Lmax, aligned base pointers: conv_can_vectorise); the scalar variant serves the rest
 template <bool VEC>
 __global__ void __launch_bounds__(M2H_CONV_THREADS, 1)
@@ -128,9 +144,9 @@ static int launch_conv(const int16_t* mono, const int32_t* mono_index, const flo
   P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.mono_index = mono_index; P.rir_index = rir_index;
   P.waves = waves; P.scratch = (float4*)workspace;
   P.n_items = n_items; P.N = N; P.Lmax = Lmax;
-  if (conv_can_vectorise(P)) m2h_rir_conv_kernel<true><<<grid, M2H_CONV_THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(P, g_tables[dev].conv);
-  else m2h_rir_conv_kernel<false><<<grid, M2H_CONV_THREADS, sizeof(ConvSmem), (cudaStream_t)stream>>>(P, g_tables[dev].conv);
-  M2H_CUDA_CHECK(cudaGetLastError());
+  const M2hConvTables* tab = g_tables[dev].conv;
+  if (conv_can_vectorise(P)) M2H_CUDA_CHECK(launch_pdl(m2h_rir_conv_kernel<true>, grid, M2H_CONV_THREADS, sizeof(ConvSmem), stream, P, tab));
+  else M2H_CUDA_CHECK(launch_pdl(m2h_rir_conv_kernel<false>, grid, M2H_CONV_THREADS, sizeof(ConvSmem), stream, P, tab));
   return M2H_OK;
 }
 
@@ -236,9 +252,9 @@ static int launch_stft(const StftParams& P, int dev, void* stream) {
   const void* outs[5] = {P.mix_mag, P.mix_phase, P.gt_mag, P.f_mag, P.f_phase};
   for (int i = 0; i < 5; ++i)
     if (((uintptr_t)outs[i] & 7) != 0) { m2h_set_error("stft: output buffers must be 8-byte aligned"); return M2H_ERR_ARG; }
-  if (P.flags & M2H_OUT_F16) m2h_stft_kernel<true><<<grid, M2H_STFT_THREADS, sizeof(StftSmem), (cudaStream_t)stream>>>(P, g_tables[dev].stft);
-  else m2h_stft_kernel<false><<<grid, M2H_STFT_THREADS, sizeof(StftSmem), (cudaStream_t)stream>>>(P, g_tables[dev].stft);
-  M2H_CUDA_CHECK(cudaGetLastError());
+  const M2hStftTables* tab = g_tables[dev].stft;
+  if (P.flags & M2H_OUT_F16) M2H_CUDA_CHECK(launch_pdl(m2h_stft_kernel<true>, grid, M2H_STFT_THREADS, sizeof(StftSmem), stream, P, tab));
+  else M2H_CUDA_CHECK(launch_pdl(m2h_stft_kernel<false>, grid, M2H_STFT_THREADS, sizeof(StftSmem), stream, P, tab));
   return M2H_OK;
 }
 

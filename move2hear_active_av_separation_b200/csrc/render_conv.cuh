@@ -318,6 +318,7 @@ M2H_HD bool conv_can_vectorise(const ConvParams& P) {
 template <bool VEC>
 M2H_DEV void conv_cta_body(const ConvParams& P, ConvSmem& s, const M2hConvTables* M2H_RESTRICT gtab, int cta, int n_ctas) {
   float4* g = P.scratch + (size_t)cta * M2H_CONV_SCRATCH_F4;
+  M2H_PDL_WAIT();
   M2H_CONV_ROWS_DECL;
   const int N = P.N;
   int16_t* pend_out = nullptr;    // window of the previous inverse transform, still in the staging buffer

@@ -290,6 +290,7 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
   M2H_FOR_THREADS(tid, M2H_STFT_THREADS) {
     for (int i = tid; i < 2048; i += M2H_STFT_THREADS) s.bf[(i & 7) * 256 + (i >> 3)] = gt->bf[i];
   }
+  M2H_PDL_WAIT();       // the table staging above overlaps the tail of the convolution kernel
   M2H_SYNC();
   // work item = (mixture, signal, group of four frames): small batches (the 14 environments of a rollout rank) still fill the GPU
   const int n_quads = (P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS;
