@@ -464,11 +464,6 @@ static int launch_layer_auto(const UGLayer& L, int bn, int B, cudaStream_t st) {
 // geometry + tensor maps + launch of one slab layer; items / epilogue fields of L are filled by the caller
 static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, int B, const __nv_bfloat16* w, cudaStream_t st) {
   L.Hp = L.Wp = Hp; L.PI = Hp * Hp; L.B = B;
-  {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("M2H_SLAB_BASE_OFFSET"); mode = e ? atoi(e) : 0; }
-    L.desc_base_offset = mode;
-  }
   L.slab_rows = 128 + 2 * (Hp + 1);
   L.slab_bytes = (L.slab_rows * 128 + 1023) & ~1023;
   L.tile_cols = L.n_phase * L.Cout;

@@ -72,7 +72,6 @@ struct USLayer {
   int out_stride, Hop, Wop, out_ld, out_coff;       // output pixel (y-1)*out_stride + py + 1 in a haloed [Hop][Wop] grid
   int n_valid; const __nv_bfloat16* head_w; const float* head_b;   // head weights: bf16 [32 n][64 k], zero padded (pack_head_kernel)
   int head_bytes;                     // US_HEAD_BYTES when the 1x1 head is fused (out_mode == UG_OUT_HEAD_NCHW_F32), else 0
-  int desc_base_offset;               // debug: 1 = put (start address >> 7) & 7 into the A descriptor's base-offset field
   USItem items[US_MAX_ITEMS];
   USIssue rec[US_MAX_ITEMS];
 };
