@@ -77,6 +77,8 @@ extern "C" size_t m2h_unet_workspace_bytes(int B) {
 // ------------------------------------------------------------------------------------------------
 // Conv2d weight [Cout][CinFull][4][4] -> bf16 [Cout][n_taps*Cin], taps = all 16 (kh*4+kw) or the 4 central ones
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int CinFull, int Cin, int n_taps) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const size_t total = (size_t)Cout * n_taps * Cin;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cin);
@@ -88,6 +90,8 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
 }
 // class plane of encoder layer 0: cls_w[cy][cx][n] = sum over taps that stay inside the image of w[n][32][kh][kw]
 __global__ void pack_cls_w_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int CinFull) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * Cout) return;
   const int n = i % Cout, cx = (i / Cout) % 3, cy = i / (3 * Cout);
@@ -107,6 +111,8 @@ __host__ __device__ inline int deconv_k(int p, int t) { return t == 0 ? (p == 0 
 __host__ __device__ inline int deconv_d(int p, int t) { return t == 0 ? 0 : (p == 0 ? -1 : 1); }
 // ConvTranspose2d weight [Cin][CoutReal][4][4] -> bf16 [4 phases][CoutPad][4 taps * Cin]
 __global__ void pack_deconv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int CoutReal, int CoutPad) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const size_t total = (size_t)4 * CoutPad * 4 * Cin;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cin);
@@ -119,6 +125,8 @@ __global__ void pack_deconv_w_kernel(const float* __restrict__ w, __nv_bfloat16*
 }
 // decoder layer 0 (1x1 input): output pixel (oy, ox) = weight tap (oy+1, ox+1): bf16 [4 pixels * Cout][Cin]
 __global__ void pack_deconv0_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const size_t total = (size_t)4 * Cout * Cin;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cin);
@@ -129,6 +137,8 @@ __global__ void pack_deconv0_w_kernel(const float* __restrict__ w, __nv_bfloat16
 }
 // head Conv2d 1x1 [C][C] -> bf16 [32][64] zero padded; bias -> fp32 [32]
 __global__ void pack_head_kernel(const float* __restrict__ w, const float* __restrict__ b, __nv_bfloat16* __restrict__ wo, float* __restrict__ wf, float* __restrict__ bo, int C) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 32 * 64) {
     const int n = i / 64, c = i % 64;
@@ -140,6 +150,8 @@ __global__ void pack_head_kernel(const float* __restrict__ w, const float* __res
 // BatchNorm (inference): y = x * scale + bias
 __global__ void fold_bn_kernel(const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ mean,
                                const float* __restrict__ var, float eps, float* __restrict__ scale, float* __restrict__ bias, int C, int Cpad) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cpad) return;
   if (i < C) {
@@ -164,6 +176,8 @@ __host__ __device__ inline float slab_deconv_w_value(const float* w, const SlabP
   return n < D.CoutReal ? w[(((size_t)c * D.CoutReal + n) * 4 + b.kh) * 4 + b.kw] : 0.f;
 }
 __global__ void pack_slab_deconv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, const SlabPackDesc D) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const size_t total = (size_t)D.n_blocks * D.Cout * 64;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(slab_deconv_w_value(w, D, i));
@@ -178,6 +192,8 @@ __host__ __device__ inline float slab_conv_w_value(const float* w, const SlabPac
   return kw >= 0 ? w[(((size_t)n * D.CinFull + (k & 31)) * 4 + b.kh) * 4 + kw] : 0.f;
 }
 __global__ void pack_slab_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, const SlabPackDesc D) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const size_t total = (size_t)D.n_blocks * D.Cout * 64;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(slab_conv_w_value(w, D, i));
@@ -342,7 +358,7 @@ static EncodeTiledFn g_encode_tiled = nullptr;
 template <int BN>
 static int launch_bn(const UGLayer& L, cudaStream_t st) {
   dim3 grid((L.M + UG_BM - 1) / UG_BM, L.Cout / BN, L.n_phase);
-  unet_gemm_kernel<BN><<<grid, UG_THREADS, ug::Cfg<BN>::kSmemBytes, st>>>(L);
+  M2H_CUDA_CHECK(launch_pdl(unet_gemm_kernel<BN>, dim3(grid), dim3(UG_THREADS), (size_t)(ug::Cfg<BN>::kSmemBytes), st, L));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }
@@ -532,14 +548,14 @@ extern "C" int m2h_unet_pack_encoder(const m2h_unet_enc_params* p, int convert_b
     if (i == 0) {
       USLayer sl; SlabPackDesc pd;
       build_conv0_items(18, cin_full, sl, pd);
-      pack_slab_conv_w_kernel<<<96, 256, 0, st>>>(p->conv_w[0], (__nv_bfloat16*)(base + L.w[0]), pd);
+      M2H_CUDA_CHECK(launch_pdl(pack_slab_conv_w_kernel, dim3(96), dim3(256), (size_t)(0), st, p->conv_w[0], (__nv_bfloat16*)(base + L.w[0]), pd));
     } else {
-      pack_conv_w_kernel<<<256, 256, 0, st>>>(p->conv_w[i], (__nv_bfloat16*)(base + L.w[i]), kEncCout[i], cin_full, kEncCin[i], kEncTaps[i]);
+      M2H_CUDA_CHECK(launch_pdl(pack_conv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->conv_w[i], (__nv_bfloat16*)(base + L.w[i]), kEncCout[i], cin_full, kEncCin[i], kEncTaps[i]));
     }
     fold_bn_kernel<<<(kEncCout[i] + 127) / 128, 128, 0, st>>>(p->bn_w[i], p->bn_b[i], p->bn_mean[i], p->bn_var[i], bn_eps,
                                                              (float*)(base + L.scale[i]), (float*)(base + L.bias[i]), kEncCout[i], kEncCout[i]);
   }
-  if (!convert_bin2mono) pack_cls_w_kernel<<<(9 * 64 + 127) / 128, 128, 0, st>>>(p->conv_w[0], (float*)(base + L.cls_w), 64, 33);
+  if (!convert_bin2mono) M2H_CUDA_CHECK(launch_pdl(pack_cls_w_kernel, dim3((9 * 64 + 127) / 128), dim3(128), (size_t)(0), st, p->conv_w[0], (float*)(base + L.cls_w), 64, 33));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }
@@ -556,18 +572,18 @@ extern "C" int m2h_unet_pack_decoder(const m2h_unet_dec_params* p, int convert_b
     if (!p->deconv_w[i] || !p->bn_w[i] || !p->bn_b[i] || !p->bn_mean[i] || !p->bn_var[i]) { m2h_set_error("m2h_unet_pack_decoder: null parameter for layer %d", i); return M2H_ERR_ARG; }
     const int cout_real = i == 4 ? c_last : kDecCoutBase[i];
     if (i == 0) {
-      pack_deconv0_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[0], (__nv_bfloat16*)(base + L.w[0]), 512, 512);
+      M2H_CUDA_CHECK(launch_pdl(pack_deconv0_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[0], (__nv_bfloat16*)(base + L.w[0]), 512, 512));
     } else if (i >= 3) {     // slab layers
       USLayer sl; SlabPackDesc pd;
       build_deconv_items(kDecCin[i], kDecCoutBase[i], cout_real, i == 3 ? 10 : 18, sl, pd);
-      pack_slab_deconv_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[i], (__nv_bfloat16*)(base + L.w[i]), pd);
+      M2H_CUDA_CHECK(launch_pdl(pack_slab_deconv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[i], (__nv_bfloat16*)(base + L.w[i]), pd));
     } else {
-      pack_deconv_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[i], (__nv_bfloat16*)(base + L.w[i]), kDecCin[i], cout_real, kDecCoutBase[i]);
+      M2H_CUDA_CHECK(launch_pdl(pack_deconv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[i], (__nv_bfloat16*)(base + L.w[i]), kDecCin[i], cout_real, kDecCoutBase[i]));
     }
     fold_bn_kernel<<<(kDecCoutBase[i] + 127) / 128, 128, 0, st>>>(p->bn_w[i], p->bn_b[i], p->bn_mean[i], p->bn_var[i], bn_eps,
                                                                  (float*)(base + L.scale[i]), (float*)(base + L.bias[i]), cout_real, kDecCoutBase[i]);
   }
-  pack_head_kernel<<<(32 * 64 + 127) / 128, 128, 0, st>>>(p->head_w, p->head_b, (__nv_bfloat16*)(base + L.head_w), (float*)(base + L.head_wf), (float*)(base + L.head_b), c_last);
+  M2H_CUDA_CHECK(launch_pdl(pack_head_kernel, dim3((32 * 64 + 127) / 128), dim3(128), (size_t)(0), st, p->head_w, p->head_b, (__nv_bfloat16*)(base + L.head_w), (float*)(base + L.head_wf), (float*)(base + L.head_b), c_last));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }

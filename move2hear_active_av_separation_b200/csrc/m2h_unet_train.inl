@@ -81,9 +81,9 @@ static int bn_forward(const TW& W, int layer, const FMap& z, const FMap& a, int 
                       float* run_mean, float* run_var, long long* nbt, float eps, float momentum, float slope, cudaStream_t st) {
   double* stats = W.stats(layer);
   M2H_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)4 * 512 * 8, st));
-  bn_stats_kernel<<<grid_for(z.P, 4 * (256 / (C / 8))), 256, 2 * 256 * 8 * sizeof(float), st>>>(z, C, stats);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, n, gamma, beta, eps, momentum, run_mean, run_var, nbt, W.aux(layer), Creal, C);
-  bn_apply_kernel<<<grid_for(z.P * (C / 8), 256), 256, 0, st>>>(z, a, C, W.aux(layer), slope);
+  M2H_CUDA_CHECK(launch_pdl(bn_stats_kernel, dim3(grid_for(z.P, 4 * (256 / (C / 8)))), dim3(256), (size_t)(2 * 256 * 8 * sizeof(float)), st, z, C, stats));
+  M2H_CUDA_CHECK(launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, stats, n, gamma, beta, eps, momentum, run_mean, run_var, nbt, W.aux(layer), Creal, C));
+  M2H_CUDA_CHECK(launch_pdl(bn_apply_kernel, dim3(grid_for(z.P * (C / 8), 256)), dim3(256), (size_t)(0), st, z, a, C, W.aux(layer), slope));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }
@@ -93,8 +93,8 @@ static int bn_backward(const TW& W, int layer, const FMap& da1, const FMap& da2,
   double* red = W.stats(layer) + 2 * 512;
   M2H_CUDA_CHECK(cudaMemsetAsync(red, 0, (size_t)2 * 512 * 8, st));
   // reductions use [C] strides inside the 512-wide slots: kernels index red[c] and red[C + c]
-  bn_bwd_reduce_kernel<<<grid_for(z.P, 4 * (256 / (C / 8))), 256, 2 * 256 * 8 * sizeof(float), st>>>(da1, da2, a, z, C, W.aux(layer), slope, red);
-  bn_bwd_apply_kernel<<<grid_for(z.P * (C / 8), 256), 256, 0, st>>>(da1, da2, a, z, C, Creal, W.aux(layer), slope, red, n, dgamma, dbeta);
+  M2H_CUDA_CHECK(launch_pdl(bn_bwd_reduce_kernel, dim3(grid_for(z.P, 4 * (256 / (C / 8)))), dim3(256), (size_t)(2 * 256 * 8 * sizeof(float)), st, da1, da2, a, z, C, W.aux(layer), slope, red));
+  M2H_CUDA_CHECK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(z.P * (C / 8), 256)), dim3(256), (size_t)(0), st, da1, da2, a, z, C, Creal, W.aux(layer), slope, red, n, dgamma, dbeta));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }
@@ -159,7 +159,7 @@ static int launch_wgrad(const __nv_bfloat16* dense, int d_ld, int d_coff, int Cd
     if (rc != M2H_OK) return rc;
   }
   dim3 grid(16, m_tiles * n_tiles, ksplit);
-  unet_wgrad_kernel<<<grid, WG_THREADS, wg::kSmemBytes, st>>>(tm_d, tm_s, L);
+  M2H_CUDA_CHECK(launch_pdl(unet_wgrad_kernel, dim3(grid), dim3(WG_THREADS), (size_t)(wg::kSmemBytes), st, tm_d, tm_s, L));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }
@@ -191,16 +191,16 @@ extern "C" int m2h_unet_encoder_forward_train(const m2h_unet_enc_params* p, int6
     if (i == 0) {
       USLayer sl; SlabPackDesc pd;
       build_conv0_items(18, cin_full, sl, pd);
-      pack_slab_conv_w_kernel<<<96, 256, 0, st>>>(p->conv_w[0], (__nv_bfloat16*)(pk + PL.w[0]), pd);
+      M2H_CUDA_CHECK(launch_pdl(pack_slab_conv_w_kernel, dim3(96), dim3(256), (size_t)(0), st, p->conv_w[0], (__nv_bfloat16*)(pk + PL.w[0]), pd));
     } else {
-      pack_conv_w_kernel<<<256, 256, 0, st>>>(p->conv_w[i], (__nv_bfloat16*)(pk + PL.w[i]), kEncCout[i], cin_full, kEncCin[i], kEncTaps[i]);
+      M2H_CUDA_CHECK(launch_pdl(pack_conv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->conv_w[i], (__nv_bfloat16*)(pk + PL.w[i]), kEncCout[i], cin_full, kEncCin[i], kEncTaps[i]));
     }
   }
-  if (!convert_bin2mono) pack_cls_w_kernel<<<(9 * 64 + 127) / 128, 128, 0, st>>>(p->conv_w[0], (float*)(pk + PL.cls_w), 64, 33);
+  if (!convert_bin2mono) M2H_CUDA_CHECK(launch_pdl(pack_cls_w_kernel, dim3((9 * 64 + 127) / 128), dim3(128), (size_t)(0), st, p->conv_w[0], (float*)(pk + PL.cls_w), 64, 33));
   PackInParams pp;
   pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.bf(TW_X0S); pp.B = B; pp.x0_plain = W.bf(TW_X0P);
   for (int i = 0; i < 4; ++i) pp.ms[i] = convert_bin2mono ? (long long)mask_strides[i] : 0;
-  pack_input_kernel<<<(B * 1024 + 255) / 256, 256, 0, st>>>(pp);
+  M2H_CUDA_CHECK(launch_pdl(pack_input_kernel, dim3((B * 1024 + 255) / 256), dim3(256), (size_t)(0), st, pp));
   M2H_CUDA_CHECK(cudaGetLastError());
 
   const int cat_slot[5] = {0, TW_CAT1, TW_CAT2, TW_CAT3, TW_CAT4}, zcat_slot[5] = {0, TW_ZCAT1, TW_ZCAT2, TW_ZCAT3, TW_ZCAT4};
@@ -243,7 +243,7 @@ extern "C" int m2h_unet_encoder_forward_train(const m2h_unet_enc_params* p, int6
     if (rc != M2H_OK) return rc;
   }
   if (bottleneck_f32) {
-    bf16_to_f32_kernel<<<(B * 512 + 255) / 256, 256, 0, st>>>(W.bf(TW_BOTT), bottleneck_f32, (size_t)B * 512);
+    M2H_CUDA_CHECK(launch_pdl(bf16_to_f32_kernel, dim3((B * 512 + 255) / 256), dim3(256), (size_t)(0), st, W.bf(TW_BOTT), bottleneck_f32, (size_t)B * 512));
     M2H_CUDA_CHECK(cudaGetLastError());
   }
   return M2H_OK;
@@ -270,12 +270,12 @@ extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int6
   const int c_last = convert_bin2mono ? 16 : 32;
   for (int i = 0; i < 5; ++i) {
     const int cout_real = i == 4 ? c_last : kDecCoutBase[i];
-    if (i == 0) pack_deconv0_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[0], (__nv_bfloat16*)(pk + PL.w[0]), 512, 512);
+    if (i == 0) M2H_CUDA_CHECK(launch_pdl(pack_deconv0_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[0], (__nv_bfloat16*)(pk + PL.w[0]), 512, 512));
     else if (i >= 3) {
       USLayer sl; SlabPackDesc pd;
       build_deconv_items(kDecCin[i], kDecCoutBase[i], cout_real, i == 3 ? 10 : 18, sl, pd);
-      pack_slab_deconv_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[i], (__nv_bfloat16*)(pk + PL.w[i]), pd);
-    } else pack_deconv_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[i], (__nv_bfloat16*)(pk + PL.w[i]), kDecCin[i], cout_real, kDecCoutBase[i]);
+      M2H_CUDA_CHECK(launch_pdl(pack_slab_deconv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[i], (__nv_bfloat16*)(pk + PL.w[i]), pd));
+    } else M2H_CUDA_CHECK(launch_pdl(pack_deconv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[i], (__nv_bfloat16*)(pk + PL.w[i]), kDecCin[i], cout_real, kDecCoutBase[i]));
   }
   M2H_CUDA_CHECK(cudaGetLastError());
   const int cat_slot[5] = {0, TW_CAT1, TW_CAT2, TW_CAT3, TW_CAT4}, zcat_slot[5] = {0, TW_ZCAT1, TW_ZCAT2, TW_ZCAT3, TW_ZCAT4};
@@ -320,7 +320,7 @@ extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int6
                     num_batches_tracked ? (long long*)num_batches_tracked[i] : nullptr, bn_eps, bn_momentum, 0.f, st);
     if (rc != M2H_OK) return rc;
   }
-  head_fwd_kernel<<<(B * 1024 + 127) / 128, 128, 0, st>>>(W.bf(TW_A4), p->head_w, p->head_b, mask_out, B, c_last);
+  M2H_CUDA_CHECK(launch_pdl(head_fwd_kernel, dim3((B * 1024 + 127) / 128), dim3(128), (size_t)(0), st, W.bf(TW_A4), p->head_w, p->head_b, mask_out, B, c_last));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }
@@ -343,12 +343,12 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
   // data-gradient operands: ConvTranspose2d weight [Cin][Cout][4][4] read as a Conv2d weight [out = Cin][in = Cout]
   for (int i = 0; i < 5; ++i) {
     const int cout_real = i == 4 ? c_last : kDecCoutBase[i];
-    pack_conv_w_kernel<<<256, 256, 0, st>>>(p->deconv_w[i], (__nv_bfloat16*)(pk + dec_dg_off(i)), kDecCin[i], cout_real, kDecCoutBase[i], i == 0 ? 4 : 16);
+    M2H_CUDA_CHECK(launch_pdl(pack_conv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[i], (__nv_bfloat16*)(pk + dec_dg_off(i)), kDecCin[i], cout_real, kDecCoutBase[i], i == 0 ? 4 : 16));
     M2H_CUDA_CHECK(cudaMemsetAsync(grads->deconv_w[i], 0, (size_t)kDecCin[i] * cout_real * 16 * 4, st));
   }
   M2H_CUDA_CHECK(cudaMemsetAsync(grads->head_w, 0, (size_t)c_last * c_last * 4, st));
   M2H_CUDA_CHECK(cudaMemsetAsync(grads->head_b, 0, (size_t)c_last * 4, st));
-  head_bwd_kernel<<<(B * 1024 + 127) / 128, 128, 0, st>>>(W.bf(TW_A4), p->head_w, dmask, W.bf(TW_DA4), grads->head_w, grads->head_b, B, c_last);
+  M2H_CUDA_CHECK(launch_pdl(head_bwd_kernel, dim3((B * 1024 + 127) / 128), dim3(128), (size_t)(0), st, W.bf(TW_A4), p->head_w, dmask, W.bf(TW_DA4), grads->head_w, grads->head_b, B, c_last));
   M2H_CUDA_CHECK(cudaGetLastError());
   const FMap none = fmap(nullptr, 0, 0, 0, 0);
   for (int i = 4; i >= 0; --i) {
@@ -397,8 +397,8 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
   const int cat_ld[5] = {0, 128, 256, 512, 1024}, hp[5] = {0, 18, 10, 6, 4};
   // data-gradient operands: Conv2d weight [Cout][Cin][4][4] read as a ConvTranspose2d weight [in = Cout][out = Cin]
   for (int i = 1; i < 5; ++i) {
-    if (i == 4) pack_deconv0_w_kernel<<<256, 256, 0, st>>>(p->conv_w[4], (__nv_bfloat16*)(pk + enc_dg_off(4)), 512, 512);
-    else pack_deconv_w_kernel<<<256, 256, 0, st>>>(p->conv_w[i], (__nv_bfloat16*)(pk + enc_dg_off(i)), kEncCout[i], kEncCin[i], kEncCin[i]);
+    if (i == 4) M2H_CUDA_CHECK(launch_pdl(pack_deconv0_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->conv_w[4], (__nv_bfloat16*)(pk + enc_dg_off(4)), 512, 512));
+    else M2H_CUDA_CHECK(launch_pdl(pack_deconv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->conv_w[i], (__nv_bfloat16*)(pk + enc_dg_off(i)), kEncCout[i], kEncCin[i], kEncCin[i]));
   }
   for (int i = 0; i < 5; ++i) {
     const int cin_full = i == 0 ? (convert_bin2mono ? 32 : 33) : kEncCin[i];
@@ -421,7 +421,7 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
       rc = launch_wgrad(z.p, z.ld, z.coff, 64, true, W.bf(TW_X0P), 32, 0, 32, convert_bin2mono ? 32 : 33, 16, B, grads->conv_w[0], st);
       if (rc != M2H_OK) return rc;
       if (!convert_bin2mono) {
-        wgrad_cls_kernel<<<dim3(64, 16), 256, 0, st>>>(z.p, z.ld, z.coff, target_class_plus1, B, grads->conv_w[0], 33);
+        M2H_CUDA_CHECK(launch_pdl(wgrad_cls_kernel, dim3(dim3(64, 16)), dim3(256), (size_t)(0), st, z.p, z.ld, z.coff, target_class_plus1, B, grads->conv_w[0], 33));
         M2H_CUDA_CHECK(cudaGetLastError());
       }
     } else {
@@ -460,7 +460,7 @@ extern "C" int m2h_l1_mask_loss(const float* mask, const float* obs, const float
   if (rc != M2H_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   M2H_CUDA_CHECK(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
-  l1_mask_loss_kernel<<<grid_for((long long)B * C * 16384, 1024), 256, 0, st>>>(mask, obs, gt, B, C, use_mix, grad_scale, loss_sum, dmask);
+  M2H_CUDA_CHECK(launch_pdl(l1_mask_loss_kernel, dim3(grid_for((long long)B * C * 16384, 1024)), dim3(256), (size_t)(0), st, mask, obs, gt, B, C, use_mix, grad_scale, loss_sum, dmask));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }

@@ -147,6 +147,8 @@ template <int BN> struct Cfg {
 
 template <int BN>
 __global__ void __launch_bounds__(UG_THREADS, ug::Cfg<BN>::kMinBlocks) unet_gemm_kernel(const UGLayer L) {
+  ug::pdl_wait();                 // launched with programmatic stream serialisation like the rest of the chain
+  ug::pdl_launch_dependents();
   using C = ug::Cfg<BN>;
   extern __shared__ unsigned char ug_smem_raw[];
   const uint32_t raw = ug::smem_u32(ug_smem_raw);

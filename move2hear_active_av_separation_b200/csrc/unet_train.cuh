@@ -54,6 +54,8 @@ __device__ __forceinline__ void block_reduce_2xC(float* sm, int C, int ppi, int 
   }
 }
 __global__ void bn_stats_kernel(const FMap z, int C, double* __restrict__ stats) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   extern __shared__ float bn_sm[];
   const int chunks = C / 8, ppi = blockDim.x / chunks;            // positions per block iteration
   const int c8 = threadIdx.x % chunks, pl = threadIdx.x / chunks;
@@ -71,6 +73,8 @@ __global__ void bn_stats_kernel(const FMap z, int C, double* __restrict__ stats)
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double n, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float eps, float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
                                    long long* __restrict__ num_batches, float* __restrict__ aux, int Creal, int Cpad) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && num_batches) *num_batches += 1;
   if (c >= Cpad) return;
@@ -92,6 +96,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double n, c
 }
 // a = act(z * scale + shift) at interior positions
 __global__ void bn_apply_kernel(const FMap z, const FMap a, int C, const float* __restrict__ aux, float slope) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const int chunks = C / 8;
   const long long total = z.P * chunks;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -113,6 +119,8 @@ __global__ void bn_apply_kernel(const FMap z, const FMap a, int C, const float* 
 // dy = (da1 + da2) * act'(a);  red[0][C] = sum dy * xhat, red[1][C] = sum dy      (xhat = (z - mean) * invstd)
 __global__ void bn_bwd_reduce_kernel(const FMap da1, const FMap da2, const FMap a, const FMap z, int C, const float* __restrict__ aux,
                                      float slope, double* __restrict__ red) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   extern __shared__ float bn_sm[];
   const int chunks = C / 8, ppi = blockDim.x / chunks;
   const int c8 = threadIdx.x % chunks, pl = threadIdx.x / chunks;
@@ -139,6 +147,8 @@ __global__ void bn_bwd_reduce_kernel(const FMap da1, const FMap da2, const FMap 
 // dz = scale * (dy - dbeta/n - xhat * dgamma/n), written over z (interior positions); block 0 also emits the fp32 parameter grads
 __global__ void bn_bwd_apply_kernel(const FMap da1, const FMap da2, const FMap a, const FMap z, int C, int Creal, const float* __restrict__ aux,
                                     float slope, const double* __restrict__ red, double n, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < Creal; c += blockDim.x) { dgamma[c] = (float)red[c]; dbeta[c] = (float)red[C + c]; }
   const int chunks = C / 8;
@@ -170,6 +180,8 @@ __global__ void bn_bwd_apply_kernel(const FMap da1, const FMap da2, const FMap a
 // a4: haloed [B][34][34][32] bf16; w: fp32 [Creal][Creal]; operands rounded to bf16 like the inference kernels
 __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a4, const float* __restrict__ w, const float* __restrict__ bias,
                                 float* __restrict__ mask, int B, int Creal) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   __shared__ float ws[32 * 33];
   for (int i = threadIdx.x; i < Creal * Creal; i += blockDim.x) ws[(i / Creal) * 33 + i % Creal] = __bfloat162float(__float2bfloat16_rn(w[i]));
   __syncthreads();
@@ -195,6 +207,8 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a4, const floa
 // da4 = W^T dmask (bf16, haloed), dW += dmask a4^T, db += sum dmask   (dW / db fp32, zeroed by the caller)
 __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ a4, const float* __restrict__ w, const float* __restrict__ dmask,
                                 __nv_bfloat16* __restrict__ da4, float* __restrict__ dw, float* __restrict__ db, int B, int Creal) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   __shared__ float ws[32 * 33];
   for (int i = threadIdx.x; i < Creal * Creal; i += blockDim.x) ws[(i / Creal) * 33 + i % Creal] = __bfloat162float(__float2bfloat16_rn(w[i]));
   __syncthreads();
@@ -261,6 +275,8 @@ __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ a4, const floa
 // dmask = sign(pred - gt) * mix * grad_scale  (grad_scale = 1 / numel for the mean reduction)
 __global__ void l1_mask_loss_kernel(const float* __restrict__ mask, const float* __restrict__ obs, const float* __restrict__ gt,
                                     int B, int C, int use_mix, float grad_scale, double* __restrict__ loss_sum, float* __restrict__ dmask) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   const long long total = (long long)B * C * 16384;
   float part = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -282,6 +298,8 @@ __global__ void l1_mask_loss_kernel(const float* __restrict__ mask, const float*
 // dz: haloed [B][18][18][ld] (+coff).  One block per (co), threads over (b, oy, ox); 16 taps reduced in shared memory.
 __global__ void wgrad_cls_kernel(const __nv_bfloat16* __restrict__ dz, int ld, int coff, const float* __restrict__ cls, int B,
                                  float* __restrict__ dw, int CinFull) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   // grid = (64 output channels, batch slices); per-tap sums reduced over the block, then one atomic per tap (dw pre-zeroed)
   __shared__ float acc[16];
   if (threadIdx.x < 16) acc[threadIdx.x] = 0.f;
@@ -371,6 +389,8 @@ constexpr int kSmemBytes = WG_STAGES * kStageBytes + 1024 + 256;
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 unet_wgrad_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ CUtensorMap tm_s, const __grid_constant__ WGLayer L) {
+  ug::pdl_wait();
+  ug::pdl_launch_dependents();
   extern __shared__ unsigned char wg_smem_raw[];
   const uint32_t raw = ug::smem_u32(wg_smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
