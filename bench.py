@@ -400,6 +400,38 @@ def run_ours(args):
     lat_roll_eager = latency(roll_eager, 50)
     lat_roll_graph = latency(lambda: graphed(rm, rr, rl, rt), 50)
 
+    # ---- BASELINE configs[4] flavour (farTarget / unheard stress): 4 sources, 48000-tap RIRs (3 x the clip: the kernel's
+    # "taps that reach the window" clipping and the un-pruned first radix stage are exercised), B = 1024 mixtures, render only.
+    # Parity of this shape is covered by tests (golden cases k3_long / k4_48000); inputs are generated on the device.
+    K_ST, L_ST = 4, 48000
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(17 + rank)
+    st_mono = (3000.0 * torch.randn((B, K_ST, N_SAMPLES), device=dev, generator=gen)).round().clamp(-32767, 32767).to(torch.int16)
+    decay = torch.exp(-torch.arange(L_ST, device=dev, dtype=torch.float32) / (L_ST / 6.0))
+    st_rir = torch.randn((B, K_ST, 2, L_ST), device=dev, generator=gen) * decay * 0.03
+    st_len = torch.full((B, K_ST), L_ST, dtype=torch.int32, device=dev)
+
+    def step_stress(tm=None):
+        if tm is not None:
+            tm[0].record(stream)
+        w = rend.rir_convolve(st_mono, st_rir, st_len)
+        if tm is not None:
+            tm[1].record(stream)
+        rend.stft_waves(w)
+        if tm is not None:
+            tm[2].record(stream)
+
+    for _ in range(3):
+        step_stress()
+    st_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(5)]
+    barrier()
+    for tm in st_ev:
+        step_stress(tm)
+    barrier()
+    ms_st_conv = sum(t[0].elapsed_time(t[1]) for t in st_ev) / len(st_ev)
+    ms_st_stft = sum(t[1].elapsed_time(t[2]) for t in st_ev) / len(st_ev)
+    del st_mono, st_rir, st_len
+
     # ---- BASELINE configs[2]: separator pretraining step (dataset-path render + both U-Nets fwd/bwd + L1 losses + Adam),
     # B = 256 per GPU, gradients all-reduced (mean) across ranks over NCCL, overlapped with backward
     train = None
@@ -466,6 +498,9 @@ def run_ours(args):
                          "latency_ms_eager": lat_roll_eager, "latency_ms_cuda_graph": lat_roll_graph,
                          "note": "gpu_ms: back-to-back calls timed with CUDA events; latency_ms: wall clock per call with a device synchronise after each (host launch path included)",
                          "mixtures_per_s_cuda_graph": world * B_ROLL / (lat_roll_graph * 1e-3)},
+        "stress_render": {"workload": "configs[4] flavour: render of 1024 mixtures with K = 4 sources and 48000-tap RIRs (per GPU)",
+                          "ms_conv": ms_st_conv, "ms_stft": ms_st_stft, "mixtures_per_s": world * B / ((ms_st_conv + ms_st_stft) * 1e-3),
+                          "algorithmic_gb_per_s": (2 * K_ST * N_SAMPLES + 8 * K_ST * L_ST + 4 * 512 * 32 * 2) * B / ((ms_st_conv + ms_st_stft) * 1e-3) / 1e9},
         "gpu_launches": OUR_LAUNCHES_PER_STEP * args.steps,
         "clocks": clocks,
         "train_step": train,

@@ -14,10 +14,6 @@ The reference calls ``clip_grad_norm_`` between ``zero_grad()`` and ``backward()
 """
 from __future__ import annotations
 
-from typing import Optional
-
-import torch
-
 from .separator_cnn import l1_mask_loss
 
 
