@@ -130,6 +130,18 @@ int m2h_render_mixture(const int16_t* mono, const float* rir, const int32_t* rir
 int m2h_stft_f32(const float* wave, int B, int C, int N, float* mag, float* phase, void* stream);
 
 
+/*
+ * Inverse STFT as the reference's evaluation calls it:
+ * Replaces librosa.istft(mag * exp(1j * phase), hop_length=512, length=16000) in eval_metrics.istft
+ *   (audio_separation/common/eval_metrics.py:232-252).  librosa infers n_fft = 2*(512-1) = 1022 from the 512 bins (not the
+ *   forward transform's 1023): 1022-point inverse real DFT per frame, periodic Hann(1022) synthesis window, overlap-add at
+ *   hop 512, division by the window's sum of squares, first 511 samples dropped, cut / zero-padded to `length`.
+ *   mag, phase  float [B, 512, T, C]  (C = 1: monaural, C = 2: both ears in one pass)
+ *   out         float [B, C, length]  OUT
+ */
+int m2h_istft(const float* mag, const float* phase, int B, int C, int T, int length, float* out, void* stream);
+
+
 /* ------------------------------------------------------------------------------------------------
  * Passive-separator U-Net, inference statistics (eval-mode BatchNorm).
  * Replaces PassiveSepEncCNN.forward / PassiveSepDecCNN.forward

@@ -93,6 +93,7 @@ SIGNATURES = {
     "m2h_stft_waves": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "m2h_render_mixture": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "m2h_stft_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "m2h_istft": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "m2h_unet_enc_packed_bytes": (_sz, [_i]),
     "m2h_unet_dec_packed_bytes": (_sz, [_i]),
     "m2h_unet_pack_encoder": (_i, [_vp, _i, ctypes.c_float, _vp, _vp]),

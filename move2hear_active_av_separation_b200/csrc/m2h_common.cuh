@@ -36,6 +36,7 @@
   }
   M2H_DEV uint32_t m2h_funnel_r(uint32_t lo, uint32_t hi, int sh) { return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
   M2H_DEV void m2h_prefetch_l2(const void*) {}
+  M2H_DEV float m2h_sinpif(float x) { return (float)sin(3.14159265358979323846 * (double)x); }
   M2H_DEV void m2h_prefetch_l1(const void*) {}
 #else
   #include <cuda_runtime.h>
@@ -68,6 +69,7 @@
   M2H_DEV int m2h_f2i_rn(float v) { return __float2int_rn(v); }
   M2H_DEV uint32_t m2h_funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }
   M2H_DEV void m2h_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+  M2H_DEV float m2h_sinpif(float x) { return sinpif(x); }
   M2H_DEV void m2h_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 

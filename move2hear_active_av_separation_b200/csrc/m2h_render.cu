@@ -31,6 +31,7 @@ extern "C" int m2h_abi_version(void) { return M2H_ABI_VERSION; }
 struct DeviceTables {
   M2hConvTables* conv = nullptr;
   M2hStftTables* stft = nullptr;
+  M2hStftTables* istft = nullptr;       // Bluestein tables of the 1022-point inverse DFT (librosa.istft's inferred n_fft)
   int n_sms = 0;
   bool ready = false;
 };
@@ -75,6 +76,13 @@ m2h_rir_conv_kernel(const ConvParams P, const M2hConvTables* __restrict__ tab) {
 }
 
 // 64 registers / thread (no spills): two 512-thread CTAs per SM, 2 x 86 KB of shared memory
+__global__ void __launch_bounds__(M2H_STFT_THREADS, 2)
+m2h_istft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
+  istft_cta_body(P, s, tab, blockIdx.x, gridDim.x);
+}
+
 template <bool F16>
 __global__ void __launch_bounds__(M2H_STFT_THREADS, 2)
 m2h_stft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
@@ -93,13 +101,17 @@ extern "C" int m2h_init(int device) {
   M2H_CUDA_CHECK(cudaSetDevice(device));
   M2H_CUDA_CHECK(cudaDeviceGetAttribute(&d.n_sms, cudaDevAttrMultiProcessorCount, device));
   static M2hConvTables hc;
-  static M2hStftTables hs;
+  static M2hStftTables hs, hi;
   static bool host_built = false;
-  if (!host_built) { build_conv_tables(hc); build_stft_tables(hs); host_built = true; }
+  if (!host_built) { build_conv_tables(hc); build_stft_tables(hs); build_istft_tables(hi); host_built = true; }
   M2H_CUDA_CHECK(cudaMalloc(&d.conv, sizeof(M2hConvTables)));
   M2H_CUDA_CHECK(cudaMalloc(&d.stft, sizeof(M2hStftTables)));
   M2H_CUDA_CHECK(cudaMemcpy(d.conv, &hc, sizeof(hc), cudaMemcpyHostToDevice));
   M2H_CUDA_CHECK(cudaMemcpy(d.stft, &hs, sizeof(hs), cudaMemcpyHostToDevice));
+  M2H_CUDA_CHECK(cudaMalloc(&d.istft, sizeof(M2hStftTables)));
+  M2H_CUDA_CHECK(cudaMemcpy(d.istft, &hi, sizeof(hi), cudaMemcpyHostToDevice));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_istft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
@@ -287,6 +299,25 @@ extern "C" int m2h_stft_f32(const float* wave, int B, int C, int N, float* mag, 
   P.fwave = wave; P.fwave_channels = C; P.B = B; P.K = 0; P.N = N; P.T = 1 + (N - 1) / M2H_HOP;
   P.n_signals = 1; P.f_mag = mag; P.f_phase = phase;
   return launch_stft(P, dev, stream);
+}
+
+extern "C" int m2h_istft(const float* mag, const float* phase, int B, int C, int T, int length, float* out, void* stream) {
+  if (B < 0 || (C != 1 && C != 2) || T < 1 || T > 4096 || length < 1) { m2h_set_error("m2h_istft: bad sizes B=%d C=%d T=%d length=%d", B, C, T, length); return M2H_ERR_ARG; }
+  if (B == 0) return M2H_OK;
+  if (!mag || !phase || !out) { m2h_set_error("m2h_istft: null pointer"); return M2H_ERR_ARG; }
+  int dev;
+  int rc = ensure_init(&dev);
+  if (rc != M2H_OK) return rc;
+  M2H_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)B * C * length * sizeof(float), (cudaStream_t)stream));     // frames are overlap-added
+  StftParams P;
+  memset(&P, 0, sizeof(P));
+  P.B = B; P.T = T; P.i_mag = mag; P.i_phase = phase; P.i_out = out; P.i_channels = C; P.i_length = length;
+  const int n_items = B * ((T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS);
+  int grid = 2 * g_tables[dev].n_sms;
+  if (grid > n_items) grid = n_items;
+  m2h_istft_kernel<<<grid, M2H_STFT_THREADS, sizeof(StftSmem), (cudaStream_t)stream>>>(P, g_tables[dev].istft);
+  M2H_CUDA_CHECK(cudaGetLastError());
+  return M2H_OK;
 }
 
 extern "C" int m2h_render_mixture(const int16_t* mono, const float* rir, const int32_t* rir_len,

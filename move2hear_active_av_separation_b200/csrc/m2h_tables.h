@@ -25,8 +25,13 @@ static void build_conv_tables(M2hConvTables& t) {
   for (int u = 0; u < 16; ++u) t.unit_tw[u] = cis((double)(u < 8 ? 1024 * u : 512 + 1024 * (u - 8)) / 32768.0);
 }
 
-static void build_stft_tables(M2hStftTables& t) {
-  const int N = M2H_NFFT, F = 2048;
+// Bluestein tables of an N-point DFT evaluated as a 2048-point circular convolution (c[n] = exp(+i pi n^2 / N)):
+//   forward (the STFT, N = 1023):  X[k] = conj(c[k]) sum_n (x[n] w[n] conj(c[n])) c[k-n]
+//        wc = hann_N * conj(c),  bf = FFT_2048(c on the circle),  cc = conj(c) / 4096   (1/2048 inverse-FFT scale, 1/2 ear untangle)
+//   inverse (librosa.istft's frames, N = 1022):  x[n] = (1/N) c[n] sum_k (X[k] c[k]) conj(c)[n-k]
+//        wc = c,  bf = FFT_2048(conj(c) on the circle),  cc = hann_N * c / (N * 2048)     (the synthesis window rides in cc)
+static void build_bluestein_tables(M2hStftTables& t, int N, bool inverse) {
+  const int F = 2048;
   for (int i = 0; i < 128; ++i) {
     t.thr[0][i] = cis((double)i / 2048.0);
     t.thr[1][i] = cis((double)(4 * i) / 2048.0);
@@ -41,21 +46,27 @@ static void build_stft_tables(M2hStftTables& t) {
     cr[n] = cos(M_PI * (double)m / N);
     ci[n] = sin(M_PI * (double)m / N);
   }
+  const double sgn = inverse ? -1.0 : 1.0;      // the convolution kernel is c (forward) or conj(c) (inverse)
   for (int n = 0; n < 1024; ++n) {
     if (n < N) {
       const double w = 0.5 - 0.5 * cos(2.0 * M_PI * n / N);       // periodic Hann (fftbins=True)
-      t.wc[n] = make_float2((float)(w * cr[n]), (float)(-w * ci[n]));
-      t.cc[n] = make_float2((float)(cr[n] / 4096.0), (float)(-ci[n] / 4096.0));
+      if (!inverse) {
+        t.wc[n] = make_float2((float)(w * cr[n]), (float)(-w * ci[n]));
+        t.cc[n] = make_float2((float)(cr[n] / 4096.0), (float)(-ci[n] / 4096.0));
+      } else {
+        t.wc[n] = make_float2((float)cr[n], (float)ci[n]);
+        t.cc[n] = make_float2((float)(w * cr[n] / (2048.0 * N)), (float)(w * ci[n] / (2048.0 * N)));
+      }
     } else {
       t.wc[n] = make_float2(0.f, 0.f);
       t.cc[n] = make_float2(0.f, 0.f);
     }
   }
-  // b[j] = c[|j|] on the circle of 2048, Bf = DFT_2048(b) in double
+  // b[j] = c[|j|] (or its conjugate) on the circle of 2048, Bf = DFT_2048(b) in double
   std::vector<double> br(F, 0.0), bi(F, 0.0);
   for (int j = 0; j < N; ++j) {
-    br[j] = cr[j]; bi[j] = ci[j];
-    if (j > 0) { br[F - j] = cr[j]; bi[F - j] = ci[j]; }
+    br[j] = cr[j]; bi[j] = sgn * ci[j];
+    if (j > 0) { br[F - j] = cr[j]; bi[F - j] = sgn * ci[j]; }
   }
   std::vector<double> wr(F), wi(F);
   for (int i = 0; i < F; ++i) { wr[i] = cos(-2.0 * M_PI * i / F); wi[i] = sin(-2.0 * M_PI * i / F); }
@@ -70,4 +81,5 @@ static void build_stft_tables(M2hStftTables& t) {
     t.bf[(k1 * 16 + k2) * 8 + k3] = make_float2((float)sr, (float)si);
   }
 }
-
+static void build_stft_tables(M2hStftTables& t) { build_bluestein_tables(t, M2H_NFFT, false); }
+static void build_istft_tables(M2hStftTables& t) { build_bluestein_tables(t, 1022, true); }

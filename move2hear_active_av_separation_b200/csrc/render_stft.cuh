@@ -46,6 +46,11 @@ struct StftParams {
   int gt_interleaved_phase;// 1: simulator layout (mag_l, phase_l, mag_r, phase_r)
   void* f_mag;             // fwave mode: [B, 512, T, C] fp32
   void* f_phase;           // fwave mode: [B, 512, T, C] fp32 or null
+  // inverse transform (m2h_istft_kernel): magnitude / phase [B, 512, T, C] fp32 -> waveforms [B, C, i_length] (pre-zeroed)
+  const float* i_mag;
+  const float* i_phase;
+  float* i_out;
+  int i_channels, i_length;
 };
 
 struct StftSmem {
@@ -327,5 +332,107 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p6<F16>(P, s, tid, b, sig, t0);
       M2H_SYNC_GROUP128();      // the next window is staged into the buffer P6 reads
     }
+  }
+}
+
+
+// ================================================================================================
+// Inverse STFT as the reference's evaluation calls it: librosa.istft(spec, hop_length=512, length=16000)
+// (audio_separation/common/eval_metrics.py:232-252).  librosa infers n_fft = 2*(512-1) = 1022 from the 512 bins - not the
+// 1023 of the forward transform - so a frame is the 1022-point inverse real DFT of its column (imaginary parts of bins 0
+// and 511 ignored), times the periodic Hann window of 1022, overlap-added at 512*t, divided by the window's sum of
+// squares, with the first 511 samples dropped.  1022 = 2*7*73: the inverse DFT runs through the same Bluestein machinery
+// (2048-point circular convolution, passes P2-P5 above with the tables of N = 1022, inverse); the two ears ride as
+// real and imaginary part of one complex signal.
+// ================================================================================================
+#define M2H_ISTFT_N 1022
+
+// P1 of the inverse: Z[k] = X_l[k] + i X_r[k] with the Hermitian extension X[1022-k] = conj(X[k]), times the chirp, radix-16
+// pass along n1 (upper half of the 2048 points is zero padding)
+M2H_DEV void istft_p1(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int tid, int b, int t0) {
+  const int grp = tid >> 7, r = tid & 127, t = t0 + grp;
+  if (t >= P.T) return;
+  const int C = P.i_channels;
+  float2 v[16];
+  M2H_UNROLL for (int n1 = 0; n1 < 8; ++n1) {
+    const int k = n1 * 128 + r;
+    float2 z = make_float2(0.f, 0.f);
+    if (k < M2H_ISTFT_N) {
+      const int kk = k < M2H_NBINS ? k : M2H_ISTFT_N - k;              // source bin; mirrored bins are conjugated
+      const float sgn = k < M2H_NBINS ? 1.f : -1.f;
+      const bool real_only = kk == 0 || kk == M2H_NBINS - 1;            // irfft ignores the imaginary part of DC and Nyquist
+      const size_t o = (((size_t)b * M2H_NBINS + kk) * P.T + t) * C;
+      float sl, cl;
+      sincosf(P.i_phase[o], &sl, &cl);
+      const float ml = P.i_mag[o];
+      float2 xl = make_float2(ml * cl, real_only ? 0.f : sgn * ml * sl);
+      float2 xr = make_float2(0.f, 0.f);
+      if (C > 1) {
+        float sr, cr;
+        sincosf(P.i_phase[o + 1], &sr, &cr);
+        const float mr = P.i_mag[o + 1];
+        xr = make_float2(mr * cr, real_only ? 0.f : sgn * mr * sr);
+      }
+      z = c_mul(make_float2(xl.x - xr.y, xl.y + xr.x), gt->wc[k]);
+    }
+    v[n1] = z;
+  }
+  fft_reg<16, false, true>(v);
+  float2* p = s.buf[grp] + M2H_STFT_POS2(r >> 3) + (r & 7);
+  twiddle_powers_out<16, 4, false>(v, M2H_STFT_TW(gt, 0, tid), M2H_STFT_TW(gt, 1, tid), [&](int k1, float2 x) { p[k1 * M2H_STFT_S1] = x; });
+}
+#ifdef M2H_HOST_EMU
+M2H_DEV void istft_add(float* p, float v) { *p += v; }
+#else
+M2H_DEV void istft_add(float* p, float v) { atomicAdd(p, v); }
+#endif
+// Periodic Hann window of 1022 points, squared
+M2H_DEV float istft_win2(int m) {
+  const float sn = m2h_sinpif((float)m * (1.0f / (float)M2H_ISTFT_N));      // hann = sin^2(pi m / N): no cancellation near the window's ends
+  const float w = sn * sn;
+  return w * w;
+}
+// P6 of the inverse: the frame arrives windowed and scaled (both folded into the table's output multiplier); divide by the
+// window's sum of squares over the frames that cover the sample and overlap-add.  At most two frames meet in a sample, so
+// the two fp32 additions commute: the result does not depend on their order.
+M2H_DEV void istft_p6(const StftParams& P, StftSmem& s, int tid, int b, int t0) {
+  const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
+  if (t >= P.T) return;
+  const int C = P.i_channels;
+  for (int m = lt; m < M2H_ISTFT_N; m += 128) {
+    const int smp = M2H_HOP * t + m - M2H_ISTFT_N / 2;                 // centre=True: the first n_fft/2 samples are dropped
+    if (smp < 0 || smp >= P.i_length) continue;
+    float wss = istft_win2(m);
+    if (m >= M2H_HOP && t + 1 < P.T) wss += istft_win2(m - M2H_HOP);
+    if (m + M2H_HOP < M2H_ISTFT_N && t >= 1) wss += istft_win2(m + M2H_HOP);
+    const float inv = wss > 1.17549435e-38f ? 1.0f / wss : 1.0f;       // librosa: divide where the sum exceeds tiny
+    const float2 z = s.buf[grp][stft_pos(m)];
+    float* o = P.i_out + (size_t)b * C * P.i_length + smp;
+    istft_add(o, z.x * inv);
+    if (C > 1) istft_add(o + P.i_length, z.y * inv);
+  }
+}
+
+M2H_DEV void istft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int cta, int n_ctas) {
+  M2H_FOR_THREADS(tid, M2H_STFT_THREADS) {
+    for (int i = tid; i < 2048; i += M2H_STFT_THREADS) s.bf[(i & 7) * 256 + (i >> 3)] = gt->bf[i];
+  }
+  M2H_SYNC();
+  const int n_quads = (P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS;
+  const int n_items = P.B * n_quads;
+  for (int item = cta; item < n_items; item += n_ctas) {
+    const int b = item / n_quads, t0 = (item - b * n_quads) * M2H_STFT_GROUPS;
+    M2H_FOR_THREADS(tid, M2H_STFT_THREADS) istft_p1(P, s, gt, tid, b, t0);
+    M2H_SYNC_GROUP128();
+    M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p2(P, s, gt, tid, t0);
+    M2H_SYNC_GROUP128();
+    M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p3(P, s, gt, tid, t0);
+    M2H_SYNC_GROUP128();
+    M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p4(P, s, tid, t0);
+    M2H_SYNC_GROUP128();
+    M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p5(P, s, gt, tid, t0);
+    M2H_SYNC_GROUP128();
+    M2H_FOR_THREADS(tid, M2H_STFT_THREADS) istft_p6(P, s, tid, b, t0);
+    M2H_SYNC_GROUP128();
   }
 }

@@ -112,6 +112,20 @@ class AudioRenderer:
         _lib.check(rc, "m2h_stft_f32")
         return mag, ph
 
+    def istft(self, mag: torch.Tensor, phase: torch.Tensor, length: int = 16000) -> torch.Tensor:
+        """fp32 magnitude / phase ``[B,512,T,C]`` (C = 1 or 2) -> waveforms ``[B,C,length]``: ``librosa.istft(mag * exp(1j *
+        phase), hop_length=512, length=length)`` per channel, i.e. with librosa's inferred n_fft = 1022."""
+        mag = _need_cuda(mag, "mag", torch.float32)
+        phase = _need_cuda(phase, "phase", torch.float32)
+        if mag.dim() != 4 or mag.shape != phase.shape or mag.shape[1] != N_BINS or mag.shape[3] not in (1, 2):
+            raise _lib.M2HError(f"istft: expected mag / phase [B,512,T,1|2], got {tuple(mag.shape)} / {tuple(phase.shape)}")
+        B, _, T, C = mag.shape
+        out = torch.empty((B, C, length), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.m2h_istft(mag.data_ptr(), phase.data_ptr(), B, C, T, length, out.data_ptr(), _stream_ptr(self.device))
+        _lib.check(rc, "m2h_istft")
+        return out
+
     # ---- host-array convenience (what the shims use) -------------------------------------------------
     def pack_sources(self, monos: Sequence[np.ndarray], rirs: Sequence[np.ndarray]):
         """K int16 ``[N]`` clips + K wav-layout ``[L_k, 2]`` RIRs -> device tensors for a batch of one."""
@@ -156,6 +170,21 @@ def get_renderer(device=None) -> AudioRenderer:
 # ================================================================================================
 # Drop-in replacements for the reference's methods (bind with `Class.method = function`)
 # ================================================================================================
+
+def istft(mag_l, phase_l, mag_r=None, phase_r=None, rend=None):
+    r"""Drop-in for ``eval_metrics.istft`` (audio_separation/common/eval_metrics.py:232-252): ``[512, T]`` magnitude / phase
+    arrays of a monaural or a binaural spectrogram -> list of one or two ``float32 [16000]`` waveforms.  Both ears are
+    inverted in one pass on the GPU."""
+    rend = rend or get_renderer()
+    chans = [(mag_l, phase_l)]
+    if mag_r is not None:
+        assert phase_r is not None
+        chans.append((mag_r, phase_r))
+    mag = torch.from_numpy(np.stack([np.asarray(m, dtype=np.float32) for m, _ in chans], axis=-1)[None]).to(rend.device)
+    ph = torch.from_numpy(np.stack([np.asarray(p, dtype=np.float32) for _, p in chans], axis=-1)[None]).to(rend.device)
+    out = rend.istft(mag, ph, length=16000)[0].cpu().numpy()
+    return [out[c] for c in range(len(chans))]
+
 
 def _read_rir(path, sampling_rate):
     """wavfile.read with the reference's error convention (simulator_train.py:407-415, dataset.py:170-176)."""

@@ -62,6 +62,45 @@ def stft_librosa(y: np.ndarray, n_fft: int = N_FFT, hop_length: int = HOP_LENGTH
     return out
 
 
+def istft_librosa(stft_matrix: np.ndarray, hop_length: int = HOP_LENGTH, length: int = SAMPLE_RATE) -> np.ndarray:
+    """librosa-0.8.0 ``istft(stft_matrix, hop_length=512, length=16000)`` as called by
+    audio_separation/common/eval_metrics.py:232-252.
+
+    librosa infers ``n_fft = 2 * (n_bins - 1)`` = **1022** from the 512 bins (not the 1023 the forward transform used),
+    ``win_length = n_fft``, periodic Hann, ``center=True``: every frame is ``irfft(column, n=1022)`` (float64; the imaginary
+    parts of bins 0 and 511 are ignored) times the window, overlap-added at ``512 * t``; the sum is divided by the window's
+    sum of squares where that exceeds ``tiny``, the first ``n_fft // 2`` samples are dropped and the result is cut /
+    zero-padded to ``length``; float32 output for a complex64 input.
+    """
+    stft_matrix = np.asarray(stft_matrix)
+    n_fft = 2 * (stft_matrix.shape[0] - 1)
+    n_fr = stft_matrix.shape[1]
+    window = get_window("hann", n_fft, fftbins=True)
+    expected = n_fft + hop_length * (n_fr - 1)
+    y = np.zeros(expected, dtype=np.float32)
+    for t in range(n_fr):
+        y[t * hop_length: t * hop_length + n_fft] += (window * np.fft.irfft(stft_matrix[:, t], n=n_fft)).astype(np.float32)
+    wss = np.zeros(expected, dtype=np.float64)
+    for t in range(n_fr):
+        wss[t * hop_length: t * hop_length + n_fft] += window ** 2
+    wss = wss.astype(np.float32)                       # librosa.filters.window_sumsquare(dtype = the output dtype)
+    nz = wss > np.finfo(np.float32).tiny
+    y[nz] /= wss[nz]
+    y = y[n_fft // 2:]
+    out = np.zeros(length, dtype=np.float32)
+    out[: min(length, len(y))] = y[:length]
+    return out
+
+
+def istft_eval(mag_l, phase_l, mag_r=None, phase_r=None):
+    """``eval_metrics.istft`` (audio_separation/common/eval_metrics.py:232-252): list of 1 or 2 float32 waveforms."""
+    sig = [istft_librosa(np.asarray(mag_l) * np.exp(1j * np.asarray(phase_l)))]
+    if mag_r is not None:
+        assert phase_r is not None
+        sig.append(istft_librosa(np.asarray(mag_r) * np.exp(1j * np.asarray(phase_r))))
+    return sig
+
+
 def magphase_librosa(D: np.ndarray):
     """librosa-0.8.0 ``magphase(D, power=1)``: ``(|D|, exp(1j * angle(D)))``."""
     mag = np.abs(D)

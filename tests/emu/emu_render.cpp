@@ -92,3 +92,17 @@ extern "C" int emu_stft_f32(const float* wave, int B, int C, int N, float* mag, 
   delete s;
   return 0;
 }
+
+extern "C" int emu_istft(const float* mag, const float* phase, int B, int C, int T, int length, float* out, int n_ctas) {
+  static M2hStftTables it;
+  static bool ready = false;
+  if (!ready) { build_istft_tables(it); ready = true; }
+  StftSmem* s = new StftSmem;
+  StftParams P;
+  memset(&P, 0, sizeof(P));
+  P.B = B; P.T = T; P.i_mag = mag; P.i_phase = phase; P.i_out = out; P.i_channels = C; P.i_length = length;
+  memset(out, 0, sizeof(float) * (size_t)B * C * length);
+  for (int cta = 0; cta < n_ctas; ++cta) istft_cta_body(P, *s, &it, cta, n_ctas);
+  delete s;
+  return 0;
+}

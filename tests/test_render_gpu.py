@@ -175,3 +175,33 @@ def test_dataset_shim(rend, golden_dir):
     assert rel_l2(gt_bin[0], g["ds_gt_bin_mag_f32"]) < 1e-4
     assert gt_mono[0].shape == (512, 32, 1) and rel_l2(gt_mono[0], g["ds_gt_mono_mag_f32"]) < 1e-4
     assert tc.dtype == np.int64 and tc.tolist() == [3] and "x.wav" in ds._gt_mono_mag_cache
+
+
+def test_istft_matches_librosa_restatement(rend):
+    """m2h_istft (eval_metrics.istft) against the oracle's librosa.istft restatement, incl. the drop-in."""
+    import torch
+    from move2hear_active_av_separation_b200 import render as MR
+    rng = np.random.default_rng(9)
+    y = (rng.standard_normal((2, 16000)) * 0.1).astype(np.float32)
+    D = np.stack([R.stft_librosa(y[c]) for c in range(2)], axis=-1)                 # [512, 32, 2] complex64
+    mag, ph = np.abs(D).astype(np.float32), np.angle(D).astype(np.float32)
+    out = rend.istft(torch.from_numpy(mag[None]).cuda(), torch.from_numpy(ph[None]).cuda())[0].cpu().numpy()
+    for c in range(2):
+        want = R.istft_librosa(mag[..., c] * np.exp(1j * ph[..., c]))
+        assert rel_l2(out[c], want) < 1e-4 and max_rel(out[c], want) < 1e-4
+    sig = MR.istft(mag[..., 0], ph[..., 0], mag[..., 1], ph[..., 1], rend=rend)
+    want = R.istft_eval(mag[..., 0], ph[..., 0], mag[..., 1], ph[..., 1])
+    assert len(sig) == 2 and sig[0].dtype == np.float32 and sig[0].shape == (16000,)
+    for a, b in zip(sig, want):
+        assert rel_l2(a, b) < 1e-4
+    mono = MR.istft(mag[..., 0], ph[..., 0], rend=rend)
+    assert len(mono) == 1 and rel_l2(mono[0], want[0]) < 1e-4
+    # batch of random (inconsistent) spectra, odd frame count, longer output
+    B, T = 5, 13
+    m = np.abs(rng.standard_normal((B, 512, T, 2))).astype(np.float32)
+    p = rng.uniform(-np.pi, np.pi, (B, 512, T, 2)).astype(np.float32)
+    o = rend.istft(torch.from_numpy(m).cuda(), torch.from_numpy(p).cuda(), length=7000).cpu().numpy()
+    for b in range(B):
+        for c in range(2):
+            want = R.istft_librosa(m[b, :, :, c] * np.exp(1j * p[b, :, :, c]), length=7000)
+            assert rel_l2(o[b, c], want) < 1e-4
