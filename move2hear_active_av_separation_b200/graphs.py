@@ -24,13 +24,24 @@ class GraphedSeparation:
     """
 
     def __init__(self, enc, dec, device, B: int, K: int = 2, N: int = 16000, Lmax: int = 16000,
-                 renderer: Optional[AudioRenderer] = None, warmup: int = 3):
+                 renderer: Optional[AudioRenderer] = None, warmup: int = 3, bin2mono_enc=None, bin2mono_dec=None,
+                 post=None):
+        """``bin2mono_enc`` / ``bin2mono_dec`` (optional) add the second U-Net of the rollout step,
+        ``pred_mono = convert_bin2mono(mask, mixed_audio=obs)`` (rl/ppo/ppo_trainer.py:304-308), to the graph;
+        ``post`` (optional callable ``(obs, mask, pred_mono) -> anything``, e.g. the AcousticMem refiner of
+        rl/models/memory_nets.py on static buffers) is captured after it; results in ``.pred_mono`` / ``.post_out``."""
         if not torch.cuda.is_available():
             raise _lib.M2HError("no CUDA device: the B200 path has no CPU fallback")
-        if enc.training or dec.training:
+        mods = [m for m in (enc, dec, bin2mono_enc, bin2mono_dec) if m is not None]
+        if any(m.training for m in mods):
             raise _lib.M2HError("GraphedSeparation captures the inference path: call .eval() on the separator first")
+        if (bin2mono_enc is None) != (bin2mono_dec is None):
+            raise _lib.M2HError("bin2mono_enc and bin2mono_dec come as a pair")
         self.device = torch.device(device)
         self.enc, self.dec = enc, dec
+        self.enc2, self.dec2, self.post = bin2mono_enc, bin2mono_dec, post
+        self.pred_mono = None
+        self.post_out = None
         self.rend = renderer or AudioRenderer(self.device)
         dev = self.device
         self.mono = torch.zeros((B, K, N), dtype=torch.int16, device=dev)
@@ -49,14 +60,19 @@ class GraphedSeparation:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.obs, self.mask = self._step()
+            self.obs, self.mask, self.pred_mono, self.post_out = self._step()
 
     def _step(self):
         waves = self.rend.rir_convolve(self.mono, self.rir, self.rir_len, out=self._waves)
         mix, _, _ = self.rend.stft_waves(waves)
+        pred_mono = post_out = None
         with torch.no_grad():
             mask = self.dec(*self.enc({"mixed_bin_audio_mag": mix, "target_class": self.target_class}))
-        return mix, mask
+            if self.enc2 is not None:
+                pred_mono = self.dec2(*self.enc2(mask, mixed_audio=mix))
+            if self.post is not None:
+                post_out = self.post(mix, mask, pred_mono)
+        return mix, mask, pred_mono, post_out
 
     def __call__(self, mono, rir, rir_len, target_class):
         L = rir.shape[-1]

@@ -36,3 +36,37 @@ def test_graphed_rollout_step_equals_eager():
         assert mask.shape == want.shape and mask.stride() == want.stride() and torch.equal(mask, want)
     with pytest.raises(Exception):
         GraphedSeparation(enc.train(), dec, dev, B, K, renderer=rend)
+
+
+def test_graphed_rollout_step_with_bin2mono_and_memory_refiner():
+    """Both U-Nets of the rollout step (rl/ppo/ppo_trainer.py:298-319) plus a torch post-module in one graph."""
+    from move2hear_active_av_separation_b200.graphs import GraphedSeparation
+    from move2hear_active_av_separation_b200.policy import Move2HearPassiveWoMemoryPolicy
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(5)
+    pol = Move2HearPassiveWoMemoryPolicy().to(dev).eval()
+    refiner = torch.nn.Sequential(torch.nn.Conv2d(32, 32, 3, padding=1, bias=False), torch.nn.ReLU(),
+                                  torch.nn.Conv2d(32, 16, 3, padding=1, bias=False)).to(dev).eval()     # AcousticMem's layers (use_ddppo)
+    B, K = 14, 2
+    prev = torch.zeros((B, 512, 32, 1), device=dev)
+
+    def post(obs, mask, pred_mono):                      # memory_nets.AcousticMem.forward on (pred_mono, previous memory)
+        def sl(x):
+            x = x.permute(0, 3, 1, 2)
+            return x.reshape(x.size(0), x.size(1), 16, -1, x.size(3)).reshape(x.size(0), -1, 32, x.size(3))
+        out = refiner(torch.cat((sl(pred_mono), sl(prev)), dim=1))
+        return out.reshape(out.size(0), -1, 16, out.size(2), out.size(3)).reshape(out.size(0), 1, 512, out.size(3)).permute(0, 2, 3, 1)
+
+    g = GraphedSeparation(pol.binSep_enc, pol.binSep_dec, dev, B, K, bin2mono_enc=pol.bin2mono_enc, bin2mono_dec=pol.bin2mono_dec, post=post)
+    monos = torch.from_numpy(R.synth_monos(B, K, seed=4))
+    rirs, lens = R.synth_rirs(B, K, L=16000, seed=14)
+    tc = torch.from_numpy(np.random.default_rng(4).integers(0, 102, (B, 1)))
+    g(monos, torch.from_numpy(rirs), torch.from_numpy(lens), tc)
+    obs = g.obs.clone()
+    with torch.no_grad():
+        mask = pol.get_binSepMasks({"mixed_bin_audio_mag": obs, "target_class": tc.to(dev)})
+        pred_mono = pol.convert_bin2mono(mask, mixed_audio=obs)
+        mem = post(obs, mask, pred_mono)
+    assert torch.equal(g.mask, mask) and torch.equal(g.pred_mono, pred_mono)
+    assert g.pred_mono.shape == (B, 512, 32, 1) and g.post_out.shape == (B, 512, 32, 1)
+    assert torch.allclose(g.post_out, mem, rtol=1e-4, atol=1e-5)
