@@ -433,10 +433,32 @@ static int launch_tma_cfg(const CUtensorMap& tm_a, const CUtensorMap& tm_w, cons
   return M2H_OK;
 }
 template <int BN>
+static int launch_tma_persistent(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const UGLayer& L, const UTGeom& G, int n_mtiles, int sms, cudaStream_t st) {
+  static bool attr_set[M2H_MAX_DEVICES];
+  int dev = 0;
+  M2H_CUDA_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, UTPCfg<BN>::kSmemBytes));
+    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_tma_persistent_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set[dev] = true;
+  }
+  const int n_mpairs = n_mtiles / 2, n_ntiles = L.Cout / BN, n_tiles = n_mpairs * n_ntiles * L.n_phase;
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  M2H_CUDA_CHECK(launch_pdl(unet_gemm_tma_persistent_kernel<BN>, dim3(grid), dim3(UT_THREADS), (size_t)UTPCfg<BN>::kSmemBytes, st, tm_a, tm_w, L, G,
+                            n_mpairs, n_ntiles, n_tiles));
+  return M2H_OK;
+}
+template <int BN>
 static int launch_tma_bn(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const UGLayer& L, const UTGeom& G, int n_mtiles, cudaStream_t st) {
   int dev = 0, sms = 0;
   M2H_CUDA_CHECK(cudaGetDevice(&dev));
   M2H_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("M2H_TMA_PERSISTENT"); persistent = e ? atoi(e) : 1; }
+  // 256-row super-tiles (shared weight tile) when there is at least one pair per SM (enc1, dec2 at B = 1024: 35 -> 34 us, 48 -> 43 us);
+  // with fewer pairs than SMs the one-tile kernels are faster (enc2: 26 us vs 28 us)
+  if (persistent && (n_mtiles & 1) == 0 && (long long)(n_mtiles / 2) * (L.Cout / BN) * L.n_phase >= sms)
+    return launch_tma_persistent<BN>(tm_a, tm_w, L, G, n_mtiles, sms, st);
   dim3 grid(n_mtiles, L.Cout / BN, L.n_phase);
   // at most one CTA per SM anyway: give it the whole shared memory as ring depth
   if ((long long)grid.x * grid.y * grid.z <= sms) return launch_tma_cfg<BN, true>(tm_a, tm_w, L, G, grid, st);
