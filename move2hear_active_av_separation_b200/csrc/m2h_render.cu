@@ -76,7 +76,7 @@ m2h_rir_conv_kernel(const ConvParams P, const M2hConvTables* __restrict__ tab) {
 }
 
 // 64 registers / thread (no spills): two 512-thread CTAs per SM, 2 x 86 KB of shared memory
-__global__ void __launch_bounds__(M2H_STFT_THREADS, 2)
+__global__ void __launch_bounds__(M2H_STFT_THREADS, M2H_STFT_CTAS_PER_SM)
 m2h_istft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
@@ -84,7 +84,7 @@ m2h_istft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
 }
 
 template <bool F16>
-__global__ void __launch_bounds__(M2H_STFT_THREADS, 2)
+__global__ void __launch_bounds__(M2H_STFT_THREADS, M2H_STFT_CTAS_PER_SM)
 m2h_stft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
@@ -258,7 +258,7 @@ extern "C" int m2h_clip_ingest(const void* raw_frames, int format, int channels,
 static int launch_stft(const StftParams& P, int dev, void* stream) {
   const int n_items = P.B * P.n_signals * ((P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS);      // (mixture, signal, four frames)
   if (n_items == 0) return M2H_OK;
-  int grid = 2 * g_tables[dev].n_sms;           // 110 KB of shared memory per CTA -> two CTAs per SM
+  int grid = M2H_STFT_CTAS_PER_SM * g_tables[dev].n_sms;
   if (grid > n_items) grid = n_items;
   // outputs are written as (left, right) pairs
   const void* outs[5] = {P.mix_mag, P.mix_phase, P.gt_mag, P.f_mag, P.f_phase};
@@ -313,7 +313,7 @@ extern "C" int m2h_istft(const float* mag, const float* phase, int B, int C, int
   memset(&P, 0, sizeof(P));
   P.B = B; P.T = T; P.i_mag = mag; P.i_phase = phase; P.i_out = out; P.i_channels = C; P.i_length = length;
   const int n_items = B * ((T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS);
-  int grid = 2 * g_tables[dev].n_sms;
+  int grid = M2H_STFT_CTAS_PER_SM * g_tables[dev].n_sms;
   if (grid > n_items) grid = n_items;
   m2h_istft_kernel<<<grid, M2H_STFT_THREADS, sizeof(StftSmem), (cudaStream_t)stream>>>(P, g_tables[dev].istft);
   M2H_CUDA_CHECK(cudaGetLastError());

@@ -16,8 +16,9 @@
 #pragma once
 #include "fft_radix.cuh"
 
-#define M2H_STFT_THREADS 512
-#define M2H_STFT_GROUPS 4
+#define M2H_STFT_GROUPS 2
+#define M2H_STFT_THREADS (128 * M2H_STFT_GROUPS)
+#define M2H_STFT_CTAS_PER_SM 3         // 768 threads per SM at 80 registers: no spills (two 512-thread CTAs at 64 registers spilled)
 // padded [16][16][8] layout: position(i1,i2,i3) = i1*136 + i2*8 + (i2 >> 1) + i3  (one pad slot per 16 elements and
 // 8 per i1 block): every pass's half-warp touches 16 distinct bank pairs
 #define M2H_STFT_S1 136
