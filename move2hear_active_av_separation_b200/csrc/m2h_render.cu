@@ -256,7 +256,7 @@ extern "C" int m2h_clip_ingest(const void* raw_frames, int format, int channels,
 }
 
 static int launch_stft(const StftParams& P, int dev, void* stream) {
-  const int n_items = P.B * P.n_signals * ((P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS);      // (mixture, signal, four frames)
+  const int n_items = P.B * P.n_signals * ((P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS);      // (mixture, signal, M2H_STFT_GROUPS frames)
   if (n_items == 0) return M2H_OK;
   int grid = M2H_STFT_CTAS_PER_SM * g_tables[dev].n_sms;
   if (grid > n_items) grid = n_items;

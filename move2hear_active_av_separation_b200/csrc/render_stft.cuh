@@ -7,7 +7,7 @@
 // 1023 = 3*11*31 has no radix-2 factor: each frame's 1023-point DFT is evaluated with Bluestein's chirp-z
 // identity as a 2048-point circular convolution.  The two ears of a frame ride together as one complex signal
 // (left + i*right) and are separated by conjugate symmetry afterwards, so one frame pair costs two complex
-// FFT-2048s.  A CTA of 512 threads = 4 groups of 128 threads; each group transforms one frame pair at a time in
+// FFT-2048s.  A CTA = M2H_STFT_GROUPS groups of 128 threads; each group transforms one frame pair at a time in
 // a padded [16][16][8] shared buffer (position(i1,i2,i3) = i1*136 + i2*8 + (i2>>1) + i3, conflict-free for all passes).
 //
 // Signals: s = 0 is the mixture ((sum_k wave_k) * 2^-15 / K, exactly the fp32 arithmetic of
@@ -298,11 +298,11 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
   }
   M2H_PDL_WAIT();       // the table staging above overlaps the tail of the convolution kernel
   M2H_SYNC();
-  // work item = (mixture, signal, group of four frames): small batches (the 14 environments of a rollout rank) still fill the GPU
-  const int n_quads = (P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS;
-  const int n_items = P.B * P.n_signals * n_quads;
+  // work item = (mixture, signal, M2H_STFT_GROUPS frames): small batches (the 14 environments of a rollout rank) still fill the GPU
+  const int n_fgroups = (P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS;
+  const int n_items = P.B * P.n_signals * n_fgroups;
   for (int item = cta; item < n_items; item += n_ctas) {
-    const int bs = item / n_quads, t0 = (item - bs * n_quads) * M2H_STFT_GROUPS;
+    const int bs = item / n_fgroups, t0 = (item - bs * n_fgroups) * M2H_STFT_GROUPS;
     const int b = bs / P.n_signals, sig = bs - b * P.n_signals;
     {
       // each 128-thread group owns one frame pair and its buffer: only the group meets between the passes, the four
@@ -419,10 +419,10 @@ M2H_DEV void istft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTable
     for (int i = tid; i < 2048; i += M2H_STFT_THREADS) s.bf[(i & 7) * 256 + (i >> 3)] = gt->bf[i];
   }
   M2H_SYNC();
-  const int n_quads = (P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS;
-  const int n_items = P.B * n_quads;
+  const int n_fgroups = (P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS;
+  const int n_items = P.B * n_fgroups;
   for (int item = cta; item < n_items; item += n_ctas) {
-    const int b = item / n_quads, t0 = (item - b * n_quads) * M2H_STFT_GROUPS;
+    const int b = item / n_fgroups, t0 = (item - b * n_fgroups) * M2H_STFT_GROUPS;
     M2H_FOR_THREADS(tid, M2H_STFT_THREADS) istft_p1(P, s, gt, tid, b, t0);
     M2H_SYNC_GROUP128();
     M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p2(P, s, gt, tid, t0);
