@@ -45,7 +45,8 @@ OUR_LAUNCHES_PER_STEP = 14
 def workload_config(extra=None):
     cfg = {"workload": "configs[1] render (B=1024/GPU, K=2, N=16000, L=16000, seeds 0/1) + binSep U-Net fwd (eval BN)",
            "batch_per_gpu": B_PER_GPU, "sources": K_SRC, "samples": N_SAMPLES, "rir_taps": L_TAPS,
-           "l2": "inputs+intermediates per step (0.9 GB) exceed the 126 MB L2; no artificial flush"}
+           "l2": "inputs+intermediates per step (0.9 GB) exceed the 126 MB L2; no artificial flush",
+           "warmup_note": "W warm-up steps plus 40 more untimed steps of the same load so that nvidia-smi clock samples bracket the ~30 ms timed region"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -153,7 +154,7 @@ class ClockSampler:
     def __init__(self, index):
         self.lines, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -164,15 +165,11 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+    def _collect(self, lo, hi):
         sm, mx, reasons = [], None, set()
         for t, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6 or not (t0 - 0.05 <= t <= t1 + 0.15):
+            if len(f) < 6 or not (lo <= t <= hi):
                 continue
             try:
                 sm.append(float(f[0]))
@@ -183,7 +180,21 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return sm, mx, reasons
+
+    def stop(self, t0, t1, t_load0=None):
+        """Samples taken inside the timed region [t0, t1]; the region is ~30 ms, so when fewer than two samples fall inside
+        it the window is widened to the continuous load around it (warm-up steps from ``t_load0`` on, 50 ms after)."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons = self._collect(t0, t1)
+        window = "timed region"
+        if len(sm) < 2:
+            sm, mx, reasons = self._collect(t0 if t_load0 is None else t_load0, t1 + 0.05)
+            window = "timed region + the warm-up steps before it (same load)"
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -277,11 +288,15 @@ def run_ours(args):
         err = float((got - cpu_mask).norm() / cpu_mask.norm())
         assert err < 2e-2, f"bench parity check failed: mask rel-L2 {err}"
 
-    for _ in range(max(args.warmup - 1, 0)):
+    # clocks are sampled from before the warm-up: nvidia-smi needs ~0.1 s to start streaming and the timed region is ~30 ms
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        time.sleep(0.25)
+    t_load0 = time.perf_counter()
+    for _ in range(max(args.warmup - 1, 0) + 40):          # W warm-up steps, then ~60 ms more of the same load for the clock samples
         step_device()
     timers = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -290,7 +305,7 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     t_wall1 = time.perf_counter()
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    clocks = sampler.stop(t_wall0, t_wall1, t_load0) if sampler else None
     ms_total = e0.elapsed_time(e1)
     t_conv = sum(t[0].elapsed_time(t[1]) for t in timers) / args.steps
     t_stft = sum(t[1].elapsed_time(t[2]) for t in timers) / args.steps
