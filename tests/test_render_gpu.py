@@ -205,3 +205,34 @@ def test_istft_matches_librosa_restatement(rend):
         for c in range(2):
             want = R.istft_librosa(m[b, :, :, c] * np.exp(1j * p[b, :, :, c]), length=7000)
             assert rel_l2(o[b, c], want) < 1e-4
+
+
+def test_conv_and_stft_random_shapes(rend):
+    """Seeded sweep over clip lengths, RIR lengths (shorter than, equal to and up to 3 x the clip), source counts, ragged
+    lengths inside a batch, even / odd row lengths (packed and scalar kernel variants, odd first taps)."""
+    rng = np.random.default_rng(2024)
+    shapes = [(16000, 16000, 2, 3), (16000, 15999, 2, 2), (16000, 48002, 3, 2), (16000, 32001, 1, 2), (8192, 8192, 2, 2),
+              (5000, 12002, 2, 3), (5001, 777, 2, 2), (16384, 32768, 1, 2), (12000, 1, 2, 2), (16000, 40000, 4, 1)]
+    for N, Lmax, K, B in shapes:
+        mono = np.round(2500 * rng.standard_normal((B, K, N))).astype(np.int16)
+        lens = rng.integers(max(1, Lmax // 3), Lmax + 1, size=(B, K)).astype(np.int32)
+        lens[0, 0] = Lmax
+        decay = np.exp(-np.arange(Lmax) / (Lmax / 6 + 1)).astype(np.float32)
+        rir = (rng.standard_normal((B, K, 2, Lmax)).astype(np.float32) * decay * 0.03)
+        for b in range(B):
+            for k in range(K):
+                rir[b, k, :, lens[b, k]:] = 7.0            # garbage beyond the valid taps must never be read
+        out = rend.render(dev(mono), dev(rir), dev(lens), n_gt=K, raw_mag=True)
+        waves = out["waves"].cpu().numpy()
+        for b in range(B):
+            for k in range(K):
+                h = np.ascontiguousarray(rir[b, k, :, :lens[b, k]].T)
+                want = (R.convolve_quantise(mono[b, k], h) * 32768).astype(np.int32)
+                d = waves[b, k].astype(np.int32) - want
+                assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= 4e-3 * d.size, (N, Lmax, K, b, k)
+            if N >= 512:
+                mixed = (waves[b].astype(np.float32) * np.float32(1 / 32768)).sum(0) / np.float32(K)
+                for ear in range(2):
+                    want = np.abs(R.stft_librosa(mixed[ear]))
+                    got = out["mix_mag"][b, :, :, ear].cpu().numpy()
+                    assert got.shape == want.shape and rel_l2(got, want) < 1e-4, (N, Lmax, K, b, ear)
