@@ -499,6 +499,15 @@ def run_ours(args):
              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": BYTES_RENDER * B / ((t_conv + t_stft) * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": t_conv + t_stft},
             {"kernel": "U-Net forward: 3 unet_slab_kernel + 7 unet_gemm_tma_kernel + pack_input_kernel", "bound": "tensor", "achieved": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
              "unit": "TFLOP/s", "frac": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], "ms": t_unet},
+            # informational: both render kernels are bound by FP32 instruction issue, not by HBM.  Warp
+            # instructions per launch are the ncu counts of this workload (profiles/r1g/ncu_full_summary.json, B = 1024 per GPU);
+            # peak = 4 schedulers x 148 SMs x the sampled SM clock, one warp instruction per scheduler and cycle.
+            {"kernel": "m2h_rir_conv_kernel (informational)", "bound": "fp32-issue", "achieved": 391.05e6 * B / 1024 / (t_conv * 1e-3) / 1e9,
+             "peak": 4 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G warp-instr/s",
+             "frac": 391.05e6 * B / 1024 / (t_conv * 1e-3) / 1e9 / (4 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3)},
+            {"kernel": "m2h_stft_kernel (informational)", "bound": "fp32-issue", "achieved": 336.09e6 * B / 1024 / (t_stft * 1e-3) / 1e9,
+             "peak": 4 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G warp-instr/s",
+             "frac": 336.09e6 * B / 1024 / (t_stft * 1e-3) / 1e9 / (4 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3)},
         ],
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
