@@ -348,7 +348,8 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
   }
   M2H_CUDA_CHECK(cudaMemsetAsync(grads->head_w, 0, (size_t)c_last * c_last * 4, st));
   M2H_CUDA_CHECK(cudaMemsetAsync(grads->head_b, 0, (size_t)c_last * 4, st));
-  M2H_CUDA_CHECK(launch_pdl(head_bwd_kernel, dim3((B * 1024 + 127) / 128), dim3(128), (size_t)(0), st, W.bf(TW_A4), p->head_w, dmask, W.bf(TW_DA4), grads->head_w, grads->head_b, B, c_last));
+  const int hb_chunks = (B * 1024 + 127) / 128;       // persistent: ~4 blocks per SM, each accumulates dW over its chunks
+  M2H_CUDA_CHECK(launch_pdl(head_bwd_kernel, dim3(hb_chunks < 592 ? hb_chunks : 592), dim3(128), (size_t)(0), st, W.bf(TW_A4), p->head_w, dmask, W.bf(TW_DA4), grads->head_w, grads->head_b, B, c_last));
   M2H_CUDA_CHECK(cudaGetLastError());
   const FMap none = fmap(nullptr, 0, 0, 0, 0);
   for (int i = 4; i >= 0; --i) {

@@ -210,62 +210,65 @@ __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ a4, const floa
   ug::pdl_wait();
   ug::pdl_launch_dependents();
   __shared__ float ws[32 * 33];
+  __shared__ float gs[128 * 33], vs[128 * 33];
   for (int i = threadIdx.x; i < Creal * Creal; i += blockDim.x) ws[(i / Creal) * 33 + i % Creal] = __bfloat162float(__float2bfloat16_rn(w[i]));
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // launched with 128 threads per block
-  const bool ok = i < B * 1024;
-  const int x = i & 31, y = (i >> 5) & 31, b = i >> 10;
-  float v[32], g[32];
-  if (ok) {
-    const uint4* src = reinterpret_cast<const uint4*>(a4 + (((size_t)b * 34 + y + 1) * 34 + x + 1) * 32);
+  // dW[n][c] = sum_pix g[n] v[c], db[n] = sum_pix g[n]: each thread owns 8 (n, c) pairs and keeps them in registers over all the
+  // 128-pixel chunks of its block - one round of atomics per block (one per chunk serialised 2 M atomics on 1056 addresses)
+  const int wn = threadIdx.x >> 2, wc0 = (threadIdx.x & 3) * 8;
+  float t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tb = 0.f;
+  const int n_chunks = (B * 1024 + 127) / 128;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int i = chunk * 128 + threadIdx.x;      // launched with 128 threads per block
+    const bool ok = i < B * 1024;
+    const int x = i & 31, y = (i >> 5) & 31, b = i >> 10;
+    float v[32], g[32];
+    if (ok) {
+      const uint4* src = reinterpret_cast<const uint4*>(a4 + (((size_t)b * 34 + y + 1) * 34 + x + 1) * 32);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint4 u = src[k];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      for (int k = 0; k < 4; ++k) {
+        const uint4 u = src[k];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[k * 8 + 2 * j] = f.x; v[k * 8 + 2 * j + 1] = f.y; }
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[k * 8 + 2 * j] = f.x; v[k * 8 + 2 * j + 1] = f.y; }
+      }
     }
-  }
 #pragma unroll
-  for (int n = 0; n < 32; ++n) g[n] = (ok && n < Creal) ? dmask[(((size_t)b * Creal + n) * 32 + y) * 32 + x] : 0.f;
-  if (ok) {
-    float d[32];
+    for (int n = 0; n < 32; ++n) g[n] = (ok && n < Creal) ? dmask[(((size_t)b * Creal + n) * 32 + y) * 32 + x] : 0.f;
+    if (ok) {
+      float d[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      float s = 0.f;
-      for (int n = 0; n < Creal; ++n) s = fmaf(ws[n * 33 + c], g[n], s);
-      d[c] = c < Creal ? s : 0.f;
+      for (int c = 0; c < 32; ++c) {
+        float s = 0.f;
+        for (int n = 0; n < Creal; ++n) s = fmaf(ws[n * 33 + c], g[n], s);
+        d[c] = c < Creal ? s : 0.f;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(da4 + (((size_t)b * 34 + y + 1) * 34 + x + 1) * 32);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(d[k * 8 + 2 * j], d[k * 8 + 2 * j + 1]);
+        dst[k] = u;
+      }
     }
-    uint4* dst = reinterpret_cast<uint4*>(da4 + (((size_t)b * 34 + y + 1) * 34 + x + 1) * 32);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      uint4 u;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(d[k * 8 + 2 * j], d[k * 8 + 2 * j + 1]);
-      dst[k] = u;
-    }
-  }
-  // dW[n][c] = sum_pix g[n] v[c], db[n] = sum_pix g[n]: stage the block's 128 pixels in shared memory, each thread owns 8 (n, c) pairs
-  __shared__ float gs[128 * 33], vs[128 * 33];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) { gs[threadIdx.x * 33 + k] = g[k]; vs[threadIdx.x * 33 + k] = ok ? v[k] : 0.f; }
-  __syncthreads();
-  {
-    const int n = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 8;
-    float t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tb = 0.f;
+    for (int k = 0; k < 32; ++k) { gs[threadIdx.x * 33 + k] = g[k]; vs[threadIdx.x * 33 + k] = ok ? v[k] : 0.f; }
+    __syncthreads();
     for (int px = 0; px < 128; ++px) {
-      const float gn = gs[px * 33 + n];
+      const float gn = gs[px * 33 + wn];
       tb += gn;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t[k] = fmaf(gn, vs[px * 33 + c0 + k], t[k]);
+      for (int k = 0; k < 8; ++k) t[k] = fmaf(gn, vs[px * 33 + wc0 + k], t[k]);
     }
-    if (n < Creal) {
+    __syncthreads();
+  }
+  if (wn < Creal) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (c0 + k < Creal) atomicAdd(dw + n * Creal + c0 + k, t[k]);
-      if (c0 == 0) atomicAdd(db + n, tb);
-    }
+    for (int k = 0; k < 8; ++k)
+      if (wc0 + k < Creal) atomicAdd(dw + wn * Creal + wc0 + k, t[k]);
+    if (wc0 == 0) atomicAdd(db + wn, tb);
   }
 }
 
