@@ -5,6 +5,8 @@ import subprocess
 import sys
 import textwrap
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WORKER = textwrap.dedent("""
@@ -70,7 +72,7 @@ GRAD_WORKER = textwrap.dedent("""
     torch.manual_seed(100 + rank)                       # ranks start from different weights ...
     net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.BatchNorm1d(16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
     broadcast_module_state(net)                         # ... and follow rank 0 afterwards
-    red = GradientAllReducer(net.parameters(), bucket_bytes=256)      # tiny buckets: several per step
+    red = GradientAllReducer(net.parameters(), bucket_bytes=256, overlap=os.environ.get("M2H_TEST_OVERLAP") == "1")      # tiny buckets: several per step
     g = torch.Generator().manual_seed(7)
     x_all, y_all = torch.randn(12, 8, generator=g), torch.randn(12, 4, generator=g)
     x, y = x_all[rank * 6:(rank + 1) * 6], y_all[rank * 6:(rank + 1) * 6]
@@ -93,12 +95,13 @@ GRAD_WORKER = textwrap.dedent("""
 """) % ROOT
 
 
-def test_two_rank_gloo_gradient_allreduce(tmp_path):
+@pytest.mark.parametrize("overlap", ["0", "1"], ids=["after_backward", "hooked_overlap"])
+def test_two_rank_gloo_gradient_allreduce(tmp_path, overlap):
     script = tmp_path / "grad_worker.py"
     script.write_text(GRAD_WORKER)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), str(script)],
-                         capture_output=True, text=True, timeout=240)
+                         capture_output=True, text=True, timeout=240, env=dict(os.environ, M2H_TEST_OVERLAP=overlap))
     assert out.returncode == 0, out.stderr[-2000:]
     import json
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
