@@ -141,3 +141,33 @@ def test_cached_simulator_shim_equals_file_reading_shim(tmp_path):
         assert np.array_equal(a._mixed_bin_audio_phase.view(np.uint16), b._mixed_bin_audio_phase.view(np.uint16))
     st = b._m2h_cached_renderer.stats()
     assert st["rir_misses"] == 6 and st["rir_hits"] == 4 and st["clip_misses"] == 2
+
+
+def test_row_cache_invariants_random_traffic():
+    """Model check of the LRU row cache: a key keeps its row until evicted, rows are never shared, a batch's rows are stable."""
+    from move2hear_active_av_separation_b200.ingest import RowCache
+    rng = np.random.default_rng(11)
+    cap = 7
+    c = RowCache(cap)
+    model = {}                       # key -> row, as the cache should see it
+    order = []                       # least recently used first
+    for _ in range(400):
+        batch = [int(k) for k in rng.integers(0, 15, size=int(rng.integers(1, cap + 1)))]
+        pinned, rows_in_batch = set(), {}
+        for k in batch:
+            row, hit = c.lookup(k, pinned)
+            assert hit == (k in model)
+            if hit:
+                assert row == model[k]
+                order.remove(k)
+            else:
+                if len(model) == cap:                         # evict the least recently used key that this batch does not use
+                    victim = next(v for v in order if model[v] not in pinned - {row})
+                    assert model[victim] == row
+                    del model[victim]
+                    order.remove(victim)
+                model[k] = row
+            order.append(k)
+            assert rows_in_batch.setdefault(k, row) == row       # stable inside the batch
+        assert len(set(model.values())) == len(model) <= cap
+    assert c.hits > 0 and c.misses > cap
