@@ -1,8 +1,14 @@
 """CPU oracle: binaural mixture render (RIR convolution + quantise + mix + STFT).
 
-TEST INFRASTRUCTURE ONLY - see ``oracle/__init__.py``.  Parity unpinned by the
-reference's own tests (there are none); pinned here against scipy / float64
-``np.convolve`` / ``torch.stft`` (``tests/test_oracle.py``).
+TEST INFRASTRUCTURE ONLY - see ``oracle/__init__.py``.  The reference has no
+tests of its own; this restatement is pinned against OUTPUTS OF THE REFERENCE'S
+OWN FUNCTION BODIES (``simulator_train.py:386-486`` + getters, the eval twin,
+``dataset.py:162-228``), executed unmodified under ``sys.modules`` stubs on real
+wav files by ``oracle/gen_ref_golden.py`` -> ``tests/golden/ref_render_*.npz``,
+reproduced bit for bit by ``tests/test_oracle.py::test_oracle_matches_reference_functions``
+(the only stand-in on that route is the librosa shim = :func:`stft_librosa`,
+itself pinned against ``torch.stft`` in float64), and against float64
+``np.convolve`` as an independent route for the convolution.
 
 Restates, with in-memory arrays instead of ``wavfile.read``:
 
@@ -141,17 +147,22 @@ def convolve_quantise(mono: np.ndarray, rir: np.ndarray) -> np.ndarray:
     return conv
 
 
-def mono_gt_mag(mono: np.ndarray, gt_mono_mag_norm: float = 1.2, with_phase: bool = False):
+def mono_gt_mag(mono: np.ndarray, gt_mono_mag_norm: float = 1.2, with_phase: bool = False,
+                dataset_semantics: bool = False):
     """GT monaural spectrogram of a source clip (cached per sound in the reference).
 
     simulator_train.py:443-459 / dataset.py:201-212: STFT of ``mono/32768``
-    (float32), magnitude RMS-normalised to ``GT_MONO_MAG_NORM`` when non-zero.
+    (float32), magnitude RMS-normalised to ``GT_MONO_MAG_NORM``.  The two call
+    sites differ when the norm is 0 (the config default): the simulator skips
+    the normalisation (``:452``), the dataset multiplies by it unconditionally
+    (``dataset.py:208-209``: zeros) - found by running the reference's own code
+    (``tests/golden/ref_render_k2_short_nonorm.npz``).
     """
     m = mono.astype("float32") / 32768
     D = stft_librosa(m)
     mag, ph = magphase_librosa(D)
     rms = np.power(np.mean(np.power(mag, 2)), 0.5)
-    if gt_mono_mag_norm != 0.0 and rms != 0.0:
+    if (dataset_semantics or gt_mono_mag_norm != 0.0) and rms != 0.0:
         mag = mag * gt_mono_mag_norm / rms
     if with_phase:
         return mag, np.angle(ph)
@@ -218,7 +229,7 @@ def render_dataset(monos, rirs, target_class: int, gt_mono_mag_norm: float = 1.2
                 mag, _ = magphase_librosa(stft_librosa(np.asfortranarray(conv[ch])))
                 mags.append(mag)
             gt_bin_mag.append(np.stack(mags, axis=-1).astype("float32"))
-            mm = mono_gt_mag(mono, gt_mono_mag_norm)
+            mm = mono_gt_mag(mono, gt_mono_mag_norm, dataset_semantics=True)
             gt_mono_mag.append(np.expand_dims(mm, axis=2).astype("float32"))
         mixed = mixed + conv
     mixed = mixed / np.float32(len(monos))

@@ -8,6 +8,7 @@ import torch
 from oracle import render as R
 from oracle import unet as U
 from oracle.gen_golden import RENDER_CASES, render_case_inputs, unet_case_inputs
+from util import f16_ulp_diff
 
 
 def rel_l2(a, b):
@@ -132,3 +133,51 @@ def test_istft_restatement_against_torch_istft():
     want = torch.istft(torch.from_numpy((mag * np.exp(1j * ph)).astype(np.complex128)), n_fft=1022, hop_length=512, win_length=1022,
                        window=torch.hann_window(1022, periodic=True, dtype=torch.float64), center=True, length=16000).numpy()
     assert np.linalg.norm(sig[0] - want) <= 1e-6 * np.linalg.norm(want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The oracle against the reference's OWN function bodies: tests/golden/ref_render_*.npz hold what the unmodified
+# habitat_audio/simulator_train.py:386-486 (+ getters :363-384, eval twin simulator_eval.py:396-500) and
+# audio_separation/pretrain/datasets/dataset.py:162-228 returned when executed under sys.modules stubs on real wav
+# files (oracle/gen_ref_golden.py; cache-hit second calls and the eval twin were asserted identical there).
+# ---------------------------------------------------------------------------------------------------------------
+from oracle.gen_ref_golden import REF_CASES  # noqa: E402
+
+
+def _ref_case_inputs(K, lens, seed):
+    eff = [max(l, 0) for l in lens]
+    monos, rirs, _, _ = render_case_inputs(K, eff, seed)
+    for k, l in enumerate(lens):
+        if l < 0:                                       # unreadable file -> the zero-RIR fallback, like a zero-length wav
+            rirs[k] = np.zeros((0, 2), np.float32)
+    return monos, rirs
+
+
+@pytest.mark.parametrize("case", REF_CASES, ids=[c[0] for c in REF_CASES])
+def test_oracle_matches_reference_functions(case, golden_dir):
+    name, K, lens, seed, norm = case
+    g = np.load(os.path.join(golden_dir, f"ref_render_{name}.npz"))
+    assert list(g["lens"]) == list(lens) and g["seed_norm"][0] == seed and g["seed_norm"][1] == norm
+    monos, rirs = _ref_case_inputs(K, lens, seed)
+    # ---- simulator path (fp16 observation, phases, all-source GT, mono GT)
+    sim = R.render_sim(list(monos), rirs, gt_mono_mag_norm=norm)
+    arg = g["sim_log1p_arg_f16"]                       # what the reference handed to np.log1p (fp16 magnitude)
+    assert arg.dtype == np.float16 and arg.shape == (512, 32, 2)
+    np.testing.assert_array_equal(sim["_mixed_mag_f32"].astype(np.float16), arg)
+    np.testing.assert_array_equal(sim["mixed_bin_audio_mag"], R.log1p_f16(arg))
+    # the reference's return value as the generating host's numpy evaluated log1p(half): within one fp16 ulp
+    ret = g["sim_return_hostnumpy"]
+    assert ret.dtype == np.float16 and ret.shape == sim["mixed_bin_audio_mag"].shape
+    assert f16_ulp_diff(sim["mixed_bin_audio_mag"], ret).max() <= 1
+    np.testing.assert_array_equal(sim["mixed_bin_audio_phase"], g["sim_mixed_phase_f16"])
+    np.testing.assert_array_equal(np.concatenate(sim["gt_bin_audio_components"], axis=2), g["sim_gt_bin_f16"])
+    np.testing.assert_array_equal(np.concatenate(sim["gt_mono_audio_components"], axis=2), g["sim_gt_mono_f16"])
+    # ---- dataset path (fp32)
+    ds = R.render_dataset(list(monos), rirs, target_class=3, gt_mono_mag_norm=norm)
+    np.testing.assert_array_equal(ds[4]["_mixed_mag_f32"], g["ds_log1p_arg_f32"])
+    # float32 log1p may be a SIMD kernel on the generating host: one float32 ulp, not bits
+    np.testing.assert_allclose(ds[0], g["ds_return_hostnumpy"], rtol=2.5e-7, atol=0)
+    np.testing.assert_array_equal(ds[1][0], g["ds_gt_bin_mag_f32"])
+    np.testing.assert_array_equal(ds[2][0], g["ds_gt_mono_mag_f32"])
+    np.testing.assert_array_equal(ds[3], g["ds_target_class"])
+    assert ds[0].dtype == g["ds_return_hostnumpy"].dtype and ds[2][0].shape == g["ds_gt_mono_mag_f32"].shape
