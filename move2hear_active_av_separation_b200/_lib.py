@@ -6,6 +6,7 @@ CPU fallback: every compute entry point needs a CUDA device and raises :class:`M
 from __future__ import annotations
 
 import ctypes
+import fcntl
 import glob
 import os
 import shutil
@@ -44,12 +45,27 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every ``csrc/*.cu`` into ``libm2h_b200.so`` (sm_100a, -lineinfo)."""
+    """Compile every ``csrc/*.cu`` into ``libm2h_b200.so`` (sm_100a, -lineinfo).
+
+    Many processes may import the package at once (8 ranks x 14 env workers, DataLoader workers): the build runs under
+    an inter-process file lock and re-checks staleness once it holds the lock, so exactly one process compiles.
+    """
     if not force and not _stale():
         return LIB_PATH
-    objs = []
     build_dir = os.path.join(PKG_DIR, "build")
     os.makedirs(build_dir, exist_ok=True)
+    with open(os.path.join(build_dir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():      # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(build_dir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(build_dir: str, verbose: bool) -> str:
+    objs = []
     procs = []
     for src in sources():
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")

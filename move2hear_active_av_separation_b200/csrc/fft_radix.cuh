@@ -26,17 +26,16 @@ template <bool INV>
 M2H_DEV float2 mul_tw32(float2 d, int k) {
   if (k == 0) return d;
   if (k == 8) return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
-  if (k == 4) {
+  if (k == 4) {      // (1 -/+ i) / sqrt 2
     const float s = 0.7071067811865476f;
-    return INV ? make_float2((d.x - d.y) * s, (d.x + d.y) * s) : make_float2((d.x + d.y) * s, (d.y - d.x) * s);
+    return c_scale(INV ? c_add(d, make_float2(-d.y, d.x)) : c_add(d, make_float2(d.y, -d.x)), s);
   }
-  if (k == 12) {
+  if (k == 12) {     // (-1 -/+ i) / sqrt 2
     const float s = 0.7071067811865476f;
-    return INV ? make_float2(-(d.x + d.y) * s, (d.x - d.y) * s) : make_float2((d.y - d.x) * s, -(d.x + d.y) * s);
+    return c_scale(INV ? c_add(make_float2(-d.y, d.x), make_float2(-d.x, -d.y)) : c_add(make_float2(d.y, -d.x), make_float2(-d.x, -d.y)), s);
   }
   const float c = tw32_cos(k), s = tw32_sin(k);
-  return INV ? make_float2(d.x * c - d.y * s, d.y * c + d.x * s)
-             : make_float2(d.x * c + d.y * s, d.y * c - d.x * s);
+  return INV ? c_rot_inv(d, c, s) : c_rot_fwd(d, c, s);
 }
 
 // ZERO_UPPER: v[R/2 .. R) is zero padding on entry (never read): the first stage degenerates to twiddle multiplies.

@@ -74,11 +74,31 @@
 #endif
 
 // ---- complex arithmetic on float2 ---------------------------------------------------------
+// Device build: Blackwell's packed fp32 pipe (add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2).  A float2 is one 64-bit
+// register pair; the SASS operands carry a half swap (.LO_HI), a per-half negation (.NP / .PN) and a 32-bit broadcast
+// (.F32) for free, so a complex add is ONE instruction, a complex multiply TWO (FMUL2 + FFMA2) and a rotation by +-i none
+// (it folds into the consumer's operand modifiers) - half the issue slots of the scalar forms, which is what bounds these
+// kernels (ncu r1g: FP32 issue, not HBM).  Rounding is the same as the scalar code nvcc contracts (one product rounded,
+// the other fused).  The host emulation keeps the scalar spelling.
+#ifdef M2H_HOST_EMU
 M2H_DEV float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 M2H_DEV float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 M2H_DEV float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 M2H_DEV float2 c_mulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+// a * (c - i s) and a * (c + i s) for real scalars c, s
+M2H_DEV float2 c_rot_fwd(float2 a, float c, float s) { return make_float2(a.x * c + a.y * s, a.y * c - a.x * s); }
+M2H_DEV float2 c_rot_inv(float2 a, float c, float s) { return make_float2(a.x * c - a.y * s, a.y * c + a.x * s); }
+M2H_DEV float2 c_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+#else
+M2H_DEV float2 c_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+M2H_DEV float2 c_sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+M2H_DEV float2 c_mul(float2 a, float2 b) { return __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x))); }
+M2H_DEV float2 c_mulc(float2 a, float2 b) { return __ffma2_rn(make_float2(a.y, a.x), make_float2(b.y, -b.y), __fmul2_rn(a, make_float2(b.x, b.x))); }
+M2H_DEV float2 c_rot_fwd(float2 a, float c, float s) { return __ffma2_rn(make_float2(a.y, a.x), make_float2(s, -s), __fmul2_rn(a, make_float2(c, c))); }
+M2H_DEV float2 c_rot_inv(float2 a, float c, float s) { return __ffma2_rn(make_float2(a.y, a.x), make_float2(-s, s), __fmul2_rn(a, make_float2(c, c))); }
+M2H_DEV float2 c_scale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+#endif
 M2H_DEV float2 c_conj(float2 a) { return make_float2(a.x, -a.y); }
 template <bool CONJ> M2H_DEV float2 c_mul_sel(float2 a, float2 w) { return CONJ ? c_mulc(a, w) : c_mul(a, w); }
 

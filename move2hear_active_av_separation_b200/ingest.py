@@ -83,6 +83,12 @@ class RowCache:
         pinned.add(row)
         return row, False
 
+    def forget(self, key: Hashable):
+        """Undo a miss whose row was never filled: the key is unmapped and its row returns to the free list."""
+        row = self.rows.pop(key, None)
+        if row is not None:
+            self.free.append(row)
+
 
 RirSource = Union[None, bytes, bytearray, memoryview, np.ndarray]
 
@@ -174,6 +180,30 @@ class CachedAudioRenderer:
             raise _lib.M2HError("render_keys: clip_keys and rir_keys must be non-empty [B][K] lists of equal shape")
         ci = np.empty((B, K), dtype=np.int32)
         ri = np.empty((B, K), dtype=np.int32)
+        # Misses are transactional: a key is mapped to its row before the row is filled, so if anything below raises
+        # (a loader's FileNotFoundError / OSError, a sample-rate assertion, a non-PCM16 clip, a cache smaller than the
+        # batch) every key inserted by this call is unmapped again - a caller that catches the error and carries on
+        # must never get a cache hit on a row that was not written.
+        new_c, new_r = [], []
+        try:
+            return self._render_keys(clip_keys, rir_keys, clip_loader, rir_loader, n_gt, sim_dtypes, want_phase, raw_mag,
+                                     B, K, ci, ri, new_c, new_r)
+        except BaseException:
+            for key in new_c:
+                self.clips.forget(key)
+            for key in new_r:
+                self.rirs.forget(key)
+            raise
+
+    def _grow_rir_pool(self, frames: int):
+        """RIRs longer than the pool rows (the reference accepts any length): re-allocate the pool with longer rows."""
+        new_L = ((frames + 3999) // 4000) * 4000
+        pool = torch.zeros((self.rir_pool.size(0), 2, new_L), dtype=torch.float32, device=self.device)
+        pool[:, :, :self.Lmax].copy_(self.rir_pool)
+        self.rir_pool, self.Lmax = pool, new_L
+
+    def _render_keys(self, clip_keys, rir_keys, clip_loader, rir_loader, n_gt, sim_dtypes, want_phase, raw_mag,
+                     B, K, ci, ri, new_c, new_r):
         jobs, used = [], 0
         pinned_c, pinned_r = set(), set()
         len_dirty = False
@@ -181,6 +211,7 @@ class CachedAudioRenderer:
             for k in range(K):
                 row, hit = self.clips.lookup(clip_keys[b][k], pinned_c)
                 if not hit:
+                    new_c.append(clip_keys[b][k])
                     u8, fmt, ch, frames = self._frames_of(clip_loader(clip_keys[b][k]), "clip")
                     if fmt != WAV_PCM16:
                         raise _lib.M2HError("clips must be 16-bit PCM (the reference's 1 s / 16 kHz int16 sounds)")
@@ -188,6 +219,7 @@ class CachedAudioRenderer:
                 ci[b, k] = row
                 row, hit = self.rirs.lookup(rir_keys[b][k], pinned_r)
                 if not hit:
+                    new_r.append(rir_keys[b][k])
                     try:
                         src = rir_loader(rir_keys[b][k])
                     except ValueError:
@@ -201,7 +233,9 @@ class CachedAudioRenderer:
                             logging.warning("{} file is not readable".format(rir_keys[b][k]))
                             frames = 0
                     if frames > self.Lmax:
-                        raise _lib.M2HError(f"RIR of {frames} taps exceeds rir_max_taps = {self.Lmax}")
+                        self._flush_stage(jobs, used)       # staged rows were addressed in the old pool
+                        jobs, used = [], 0
+                        self._grow_rir_pool(frames)
                     if frames > 0:                # frames == 0: unreadable / empty -> zero RIR = length 0 (simulator_train.py:411-415)
                         used = self._stage(jobs, used, "rir", u8, fmt, ch, frames, row)
                     self._rir_len_host[row] = frames

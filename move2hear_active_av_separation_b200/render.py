@@ -132,6 +132,11 @@ class AudioRenderer:
         K = len(monos)
         N = len(monos[0])
         Lmax = max(1, max(len(r) for r in rirs))
+        for m in monos:
+            if np.asarray(m).dtype != np.int16:
+                # the reference convolves whatever wavfile.read returned; its clips are int16 PCM - a silent cast of a
+                # float clip would truncate it before the convolution
+                raise _lib.M2HError(f"source clips must be int16 PCM (wavfile.read of the reference's sounds), got {np.asarray(m).dtype}")
         mono = np.stack([np.asarray(m, dtype=np.int16) for m in monos])[None]
         rir = np.zeros((1, K, 2, Lmax), dtype=np.float32)
         lens = np.zeros((1, K), dtype=np.int32)
@@ -143,13 +148,16 @@ class AudioRenderer:
         dev = self.device
         return (torch.from_numpy(mono).to(dev), torch.from_numpy(rir).to(dev), torch.from_numpy(lens).to(dev)), N
 
-    def mono_gt_spec(self, mono: np.ndarray, gt_mono_mag_norm: float, want_phase: bool):
-        """Cached-per-sound monaural GT spectrogram (simulator_train.py:443-459, dataset.py:201-212)."""
+    def mono_gt_spec(self, mono: np.ndarray, gt_mono_mag_norm: float, want_phase: bool, dataset_semantics: bool = False):
+        """Cached-per-sound monaural GT spectrogram (simulator_train.py:443-459, dataset.py:201-212).
+
+        The simulator skips the RMS normalisation when ``GT_MONO_MAG_NORM == 0`` (``:452``); the dataset multiplies by it
+        unconditionally (``dataset.py:208-209``: an all-zero target for the config default 0) - ``dataset_semantics``."""
         wave = torch.from_numpy(np.asarray(mono).astype("float32") / 32768).to(self.device)[None, None]
         mag, ph = self.stft_f32(wave, want_phase)
         mag = mag[0, :, :, 0]
         rms = torch.sqrt(torch.mean(mag * mag))
-        if gt_mono_mag_norm != 0.0 and float(rms) != 0.0:
+        if (dataset_semantics or gt_mono_mag_norm != 0.0) and float(rms) != 0.0:
             mag = mag * gt_mono_mag_norm / rms
         mag = mag.cpu().numpy()
         return (mag, ph[0, :, :, 0].cpu().numpy()) if want_phase else (mag, None)
@@ -308,7 +316,7 @@ def compute_audiospects_arrays(self, monos, rirs, names, target_class, gt_mono_m
     out = rend.render(mono_d, rir_d, len_d, n_gt=1, sim_dtypes=False, want_phase=False)
     gt_bin_mag = [out["gt"][0, 0].cpu().numpy()]
     if names[0] not in self._gt_mono_mag_cache:
-        mag, _ = rend.mono_gt_spec(monos[0], gt_mono_mag_norm if gt_mono_mag_norm else 0.0, want_phase=False)
+        mag, _ = rend.mono_gt_spec(monos[0], gt_mono_mag_norm, want_phase=False, dataset_semantics=True)
         self._gt_mono_mag_cache[names[0]] = mag
     gt_mono_mag = [np.expand_dims(self._gt_mono_mag_cache[names[0]], axis=2).astype("float32")]
     return out["mix_mag"][0].cpu().numpy(), gt_bin_mag, gt_mono_mag, np.array([target_class]).astype("int64")

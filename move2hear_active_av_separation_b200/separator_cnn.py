@@ -162,6 +162,8 @@ class _TrainWorkspace:
         offs = (ctypes.c_size_t * 32)()
         _lib.check(lib.m2h_unet_train_workspace_layout(B, offs), "m2h_unet_train_workspace_layout")
         self.offsets = list(offs)
+        # bumped by every train-mode forward that writes this workspace; backward refuses to run on overwritten activations
+        self.generation = 0
         with torch.cuda.device(device):
             rc = lib.m2h_unet_train_workspace_init(B, self.buf.data_ptr(), self.nbytes, torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "m2h_unet_train_workspace_init")
@@ -186,6 +188,24 @@ class _TrainWorkspace:
         return out
 
 
+def _check_generation(ctx, ws):
+    """The saved activations of a train-mode forward live in the module's workspace, not in autograd's graph: a second
+    train-mode forward of the same module (gradient accumulation, a logging forward under no_grad) would overwrite them
+    and backward would silently produce wrong gradients - refuse instead (the reference's nn.Module has value semantics)."""
+    if ctx.generation != ws.generation:
+        raise _lib.M2HError("backward through a train-mode separator forward whose activations were overwritten by a later "
+                            "train-mode forward of the same module: call backward() before the next forward (or use a "
+                            "second module / eval mode for the extra forward)")
+
+
+def _check_device(device, **tensors):
+    """Raw pointers go to the kernels: a tensor on the host or on another GPU would fault the whole CUDA context."""
+    for name, t in tensors.items():
+        if t is not None and t.device != device:
+            raise _lib.M2HError(f"{name} is on {t.device} but the separator input is on {device}: move the module and all of "
+                                "its inputs to the same CUDA device")
+
+
 def _ptr_array(tensors):
     arr = (ctypes.c_void_p * 5)()
     for i, t in enumerate(tensors):
@@ -202,6 +222,7 @@ class _EncTrainFn(torch.autograd.Function):
         device = obs.device
         B = obs.size(0)
         ws = module._train_workspace(B, device)
+        ws.generation += 1
         p, keep = module._param_struct()
         nbt = _ptr_array([module.cnn[i][1].num_batches_tracked for i in range(5)])
         bott = torch.empty((B, 512), dtype=torch.float32, device=device)
@@ -214,6 +235,7 @@ class _EncTrainFn(torch.autograd.Function):
                 ws.buf.data_ptr(), ws.nbytes, bott.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "m2h_unet_encoder_forward_train")
         ctx.module, ctx.ws, ctx.cls, ctx.B, ctx.device = module, ws, cls, B, device
+        ctx.generation = ws.generation
         skips = ws.skips()
         bott._m2h_ws = ws
         return (bott, *skips)
@@ -222,6 +244,7 @@ class _EncTrainFn(torch.autograd.Function):
     def backward(ctx, d_bott, *d_skips):
         lib = _lib.load()
         module, ws, B, device = ctx.module, ctx.ws, ctx.B, ctx.device
+        _check_generation(ctx, ws)
         # gradients of the outputs must sit in the workspace slots the kernels read (they already do when they come from _DecTrainFn)
         own = ws.skips(base=14)
         for g, slot in zip(d_skips, own):
@@ -263,12 +286,14 @@ class _DecTrainFn(torch.autograd.Function):
                                                     torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "m2h_unet_decoder_forward_train")
         ctx.module, ctx.ws, ctx.B, ctx.device = module, ws, B, device
+        ctx.generation = ws.generation
         return out
 
     @staticmethod
     def backward(ctx, dmask):
         lib = _lib.load()
         module, ws, B, device = ctx.module, ctx.ws, ctx.B, ctx.device
+        _check_generation(ctx, ws)
         dmask = _f32(dmask)
         p, keep = module._param_struct()
         grads, gstruct = module._grad_struct(device)
@@ -289,6 +314,7 @@ class _L1MaskLossFn(torch.autograd.Function):
         lib = _lib.load()
         device = mask.device
         B, C = mask.size(0), mask.size(3)
+        _check_device(device, gt=gt, mixed_audio=obs if use_mix else None)
         nchw = mask.permute(0, 3, 1, 2)
         if not nchw.is_contiguous() or nchw.dtype != torch.float32:
             nchw = nchw.float().contiguous()
@@ -344,6 +370,12 @@ class _PackedModule(nn.Module):
         if len(self.cnn) > 5:
             ps += [self.cnn[5][0].weight, self.cnn[5][0].bias]
         return ps
+
+    def _check_params_on(self, device):
+        for name, t in list(self.named_parameters()) + list(self.named_buffers()):
+            if t.device != device:
+                raise _lib.M2HError(f"parameter / buffer {name} is on {t.device} but the input is on {device}: call "
+                                    f".to({str(device)!r}) on the module first")
 
     def _check_train_dtypes(self):
         for t in list(self.parameters()) + [b for b in self.buffers() if b.dtype.is_floating_point]:
@@ -434,6 +466,8 @@ class PassiveSepEncCNN(_PackedModule):
             masks = None
         device = obs.device
         self._require_cuda(device)
+        self._check_params_on(device)
+        _check_device(device, masks=masks, target_class=None if self._convert_bin2mono else observations["target_class"])
         obs = _f32(obs)
         B = obs.size(0)
         if tuple(obs.shape[1:]) != (512, 32, 2):
@@ -541,6 +575,7 @@ class PassiveSepDecCNN(_PackedModule):
         if not isinstance(ws, _TrainWorkspace) or ws.B != B or ws.buf.device != device:
             # features did not come straight from the partner encoder in train mode: stage them into a fresh training workspace
             ws = self._train_workspace(B, device)
+            ws.generation += 1
             ws.view(5, (B, 512)).copy_(bottleneck_feats.detach().reshape(B, 512))
             for idx, feat, (hw, c) in zip((4, 3, 2, 1), lst_skip_feats, ((2, 512), (4, 256), (8, 128), (16, 64))):
                 ws.view(idx, (B, hw, hw, 2 * c))[..., c:].copy_(feat.detach().permute(0, 2, 3, 1))
@@ -551,6 +586,8 @@ class PassiveSepDecCNN(_PackedModule):
         lib = _lib.load()
         device = bottleneck_feats.device
         self._require_cuda(device)
+        self._check_params_on(device)
+        _check_device(device, **{"skip%d" % i: t for i, t in enumerate(lst_skip_feats)})
         B = bottleneck_feats.size(0)
         if self.training:
             return self._forward_train(bottleneck_feats, lst_skip_feats, B, device)
@@ -572,44 +609,3 @@ class PassiveSepDecCNN(_PackedModule):
         _lib.check(rc, "m2h_unet_decoder_forward")
         # [BATCH x HEIGHT x WIDTH x CHANNEL] view with the reference's strides (C*16384, 32, 1, 16384)
         return out.permute(0, 2, 3, 1)
-
-
-def smoke_check(obs: torch.Tensor) -> None:
-    """Tiny U-Net forward on ``obs`` ([B,512,32,2] log1p magnitudes) checked against the oracle (used by smoke())."""
-    from oracle import unet as U
-    enc_sd, dec_sd = U.init_state(False, seed=3)
-    enc, dec = PassiveSepEncCNN().cuda().eval(), PassiveSepDecCNN().cuda().eval()
-    enc.load_state_dict(enc_sd)
-    dec.load_state_dict(dec_sd)
-    tc = torch.arange(obs.size(0), device=obs.device).reshape(-1, 1) % 11
-    with torch.no_grad():
-        mask = dec(*enc({"mixed_bin_audio_mag": obs, "target_class": tc}))
-        want = U.separator_forward(enc_sd, dec_sd, obs.cpu(), tc.cpu())
-    err = (mask.cpu() - want).norm() / want.norm()
-    assert float(err) < 2e-2, float(err)
-
-
-def smoke_check_train(obs: torch.Tensor) -> None:
-    """One tiny pretraining forward/backward (train-mode BatchNorm, L1 loss) checked against torch autograd on the oracle."""
-    from oracle import unet as U
-    B = obs.size(0)
-    enc_sd, dec_sd = U.init_state(False, seed=3)
-    enc, dec = PassiveSepEncCNN().cuda().train(), PassiveSepDecCNN().cuda().train()
-    enc.load_state_dict(enc_sd)
-    dec.load_state_dict(dec_sd)
-    tc = torch.arange(B, device=obs.device).reshape(-1, 1) % 11
-    g = torch.Generator().manual_seed(1)
-    gt = torch.rand(B, 512, 32, 2, generator=g) * 2
-    mask = dec(*enc({"mixed_bin_audio_mag": obs, "target_class": tc}))
-    loss = l1_mask_loss(mask, gt.cuda(), mixed_audio=obs)
-    loss.backward()
-    sd_e = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in enc_sd.items()}
-    sd_d = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in dec_sd.items()}
-    want_mask = U.separator_forward(sd_e, sd_d, obs.cpu(), tc.cpu(), training=True, emulate_bf16=True)
-    want, _ = U.supervised_losses(obs.cpu(), want_mask, gt)
-    want.backward()
-    assert abs(float(loss) - float(want)) < 1e-2 * float(want), (float(loss), float(want))
-    gw, ww = dec.cnn[4][0].weight.grad.cpu(), sd_d["cnn.4.0.weight"].grad
-    assert float((gw - ww).norm() / ww.norm()) < 0.2
-    cos = float(torch.dot(gw.reshape(-1), ww.reshape(-1)) / (gw.norm() * ww.norm()))
-    assert cos > 0.97, cos

@@ -171,3 +171,18 @@ def test_row_cache_invariants_random_traffic():
             assert rows_in_batch.setdefault(k, row) == row       # stable inside the batch
         assert len(set(model.values())) == len(model) <= cap
     assert c.hits > 0 and c.misses > cap
+
+
+def test_row_cache_forget_returns_the_row():
+    """Transactional misses (CachedAudioRenderer.render_keys): a key whose row was never filled is unmapped again."""
+    from move2hear_active_av_separation_b200.ingest import RowCache
+    c = RowCache(2)
+    pinned = set()
+    row_a, _ = c.lookup("a", pinned)
+    row_b, _ = c.lookup("b", pinned)
+    c.forget("b")
+    c.forget("never-inserted")
+    assert "b" not in c.rows and c.rows == {"a": row_a} and c.free == [row_b]
+    row_c, hit = c.lookup("c", set())
+    assert not hit and row_c == row_b
+    assert c.lookup("a", set()) == (row_a, True)
