@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define M2H_ABI_VERSION 2
+#define M2H_ABI_VERSION 3
 
 enum m2h_status {
   M2H_OK = 0,
@@ -257,6 +257,46 @@ int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int convert_bin2mono
  * loss_sum (device double) = sum |pred - gt|; dmask (may be NULL) = sign(pred - gt) * mix * grad_scale. */
 int m2h_l1_mask_loss(const float* mask, const float* obs, const float* gt, int B, int C, int use_mix, float grad_scale,
                      double* loss_sum, float* dmask, void* stream);
+
+/*
+ * ---- consumers of the masks on the rollout / evaluation step ----
+ *
+ * STFT_L2_distance(mixed_audio, pred_binSepMasks, gt_bin_comps, pred_mono, gt_mono_comps)
+ *   audio_separation/common/eval_metrics.py:306-366; call sites rl/ppo/ppo_trainer.py:407-420.
+ *   mixed_audio   float [B, 512, T, 2]  log1p magnitudes (contiguous, 8-byte aligned)
+ *   pred_masks    float [B, 512, T, 2]  any strides (element strides in mask_strides[4])
+ *   gt_bin_comps  float [B, 512, T, c_bin]   components 0..3 = mag_l, phase_l, mag_r, phase_r (c_bin >= 4)
+ *   pred_mono     float [B, 512, T, 1]  any strides (mono_strides[4])
+ *   gt_mono_comps float [B, 512, T, c_mono]  components 0..1 = mag, phase (c_mono >= 2)
+ *   bin_dist, mono_dist  float [B]  OUT: the reference's [B, 1] tensors
+ */
+int m2h_stft_l2_distance(const float* mixed_audio, const float* pred_masks, const int64_t* mask_strides,
+                         const float* gt_bin_comps, int c_bin, const float* pred_mono, const int64_t* mono_strides,
+                         const float* gt_mono_comps, int c_mono, int B, int T, float* bin_dist, float* mono_dist,
+                         void* stream);
+
+/*
+ * Raw moments of a (reference, estimate, mixture) waveform triple, from which every scale-invariant BSS metric of
+ * scale_bss_eval_helper / scale_bss_eval / preprocess (audio_separation/common/eval_metrics.py:12-57, 60-122, 167-196)
+ * follows in closed form for the reference's single-source evaluation (compute_waveform_quality, :256-303).
+ *   reference, estimate float [B, L];  mixture float [B, mix_channels, L] (its channel mean is the "mixture" estimate)
+ *   moments double [B, 9] OUT = { L, S r, S e, S m, S rr, S ee, S mm, S re, S rm }
+ */
+int m2h_wave_moments(const float* reference, const float* estimate, const float* mixture, int mix_channels,
+                     int B, int L, double* moments, void* stream);
+
+/*
+ * AcousticMem.forward(pred_mono, prev_pred_monoFromMem_masked)  (audio_separation/rl/models/memory_nets.py:5-69;
+ * call sites rl/ppo/ppo_trainer.py:310-319, rl/ppo/policy.py:195-196), inference statistics:
+ * frequency slicing into 16 chunks, channel concat, Conv2d(32,32,3,p1) [+ BatchNorm2d(32), absent when use_ddppo] + ReLU,
+ * Conv2d(32,16,3,p1), de-slicing - one launch, fp32.
+ *   pred_mono, prev_pred  float [B, 512, 32, 1]  any strides;  conv1_w [32,32,3,3], conv2_w [16,32,3,3]
+ *   bn_*  [32] or all NULL;  out float [B, 512, 32, 1] contiguous
+ */
+int m2h_acoustic_mem_forward(const float* pred_mono, const int64_t* pred_mono_strides, const float* prev_pred,
+                             const int64_t* prev_pred_strides, const float* conv1_w, const float* conv2_w,
+                             const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var, float bn_eps,
+                             int B, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -127,6 +127,9 @@ SIGNATURES = {
     "m2h_unet_decoder_backward": (_i, [_vp, _i, _vp, _i, _vp, _sz, _vp, _vp]),
     "m2h_unet_encoder_backward": (_i, [_vp, _i, _vp, _i, _vp, _sz, _vp, _vp]),
     "m2h_l1_mask_loss": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp]),
+    "m2h_stft_l2_distance": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "m2h_wave_moments": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "m2h_acoustic_mem_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, _i, _vp, _vp]),
 }
 
 

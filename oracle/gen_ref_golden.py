@@ -76,7 +76,8 @@ class _Registry:
 def install_stubs():
     """Put the stub modules into ``sys.modules`` (idempotent).  No arithmetic except the librosa shim."""
     _module("librosa", stft=lambda y, hop_length, n_fft: R.stft_librosa(y, n_fft=n_fft, hop_length=hop_length),
-            magphase=R.magphase_librosa)
+            magphase=R.magphase_librosa,
+            istft=lambda D, hop_length, length: R.istft_librosa(D, hop_length=hop_length, length=length))
     _module("habitat")
     _module("habitat.core")
     _module("habitat.core.registry", registry=_Registry())
@@ -191,11 +192,78 @@ def run_dataset(ds_mod, tmp, K, norm, monos, target_class=3, calls=2):
     return outs
 
 
+def postproc_case_inputs(B=3, seed=71, T=32):
+    """Seeded inputs of the mask consumers (STFT_L2_distance, AcousticMem, compute_waveform_quality)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    d = {"mixed_audio": torch.log1p(torch.rand(B, 512, T, 2, generator=g) * 3.0),
+         "masks": torch.randn(B, 512, T, 2, generator=g) * 0.5 + 0.3,
+         "gt_bin_comps": torch.stack([torch.rand(B, 512, T, generator=g) * 2, (torch.rand(B, 512, T, generator=g) * 2 - 1) * 3.14159,
+                                      torch.rand(B, 512, T, generator=g) * 2, (torch.rand(B, 512, T, generator=g) * 2 - 1) * 3.14159], dim=-1),
+         "pred_mono": torch.rand(B, 512, T, 1, generator=g) * 2,
+         "gt_mono_comps": torch.stack([torch.rand(B, 512, T, generator=g) * 2, (torch.rand(B, 512, T, generator=g) * 2 - 1) * 3.14159], dim=-1),
+         "prev_mem": torch.rand(B, 512, T, 1, generator=g) * 2}
+    return d
+
+
+def waveform_case_inputs(seed=81):
+    """A consistent spectrogram set for compute_waveform_quality: STFTs of seeded waveforms (simulator dtypes widened)."""
+    rng = np.random.default_rng(seed)
+    gt = (rng.standard_normal(16000) * 0.1).astype(np.float32)
+    other = (rng.standard_normal((2, 16000)) * 0.1).astype(np.float32)
+    mixed = np.stack([0.6 * gt + other[0], 0.5 * gt + other[1]]).astype(np.float32)
+    def spec(y):
+        D = R.stft_librosa(y)
+        return np.abs(D).astype(np.float32), np.angle(D).astype(np.float32)
+    ml, pl = spec(mixed[0]); mr, pr = spec(mixed[1]); gm, gp = spec(gt)
+    noise = np.abs(rng.standard_normal(gm.shape)).astype(np.float32)
+    return {"mixed_bin_audio_mag": np.stack([ml, mr], -1)[None], "mixed_bin_audio_phase": np.stack([pl, pr], -1)[None],
+            "gt_mono_mag": gm[None, :, :, None], "gt_mono_phase": gp[None, :, :, None],
+            "pred_mono": (gm * 0.8 + 0.3 * noise)[None, :, :, None], "pred_monoFromMem": (gm * 0.9 + 0.1 * noise)[None, :, :, None]}
+
+
+def gen_postproc():
+    """tests/golden/postproc.npz: outputs of the reference's own STFT_L2_distance, AcousticMem (both variants) and
+    compute_waveform_quality (eval_metrics.py / memory_nets.py imported unmodified)."""
+    import torch
+    install_stubs()
+    em = _load("ref_eval_metrics", "audio_separation/common/eval_metrics.py")
+    mn = _load("ref_memory_nets", "audio_separation/rl/models/memory_nets.py")
+    d = postproc_case_inputs()
+    out = {}
+    b, m = em.STFT_L2_distance(d["mixed_audio"], d["masks"], d["gt_bin_comps"].clone(), d["pred_mono"], d["gt_mono_comps"].clone())
+    out["stft_l2_bin"], out["stft_l2_mono"] = b.numpy(), m.numpy()
+    for ddppo in (False, True):
+        torch.manual_seed(5 + int(ddppo))
+        mod = mn.AcousticMem(use_ddppo=ddppo).eval()
+        if not ddppo:       # non-trivial inference statistics
+            g = torch.Generator().manual_seed(9)
+            mod.cnn[1].weight.data = 0.5 + torch.rand(32, generator=g)
+            mod.cnn[1].bias.data = 0.2 * torch.randn(32, generator=g)
+            mod.cnn[1].running_mean.data = 0.2 * torch.randn(32, generator=g)
+            mod.cnn[1].running_var.data = 0.5 + torch.rand(32, generator=g)
+        with torch.no_grad():
+            y = mod(d["pred_mono"], d["prev_mem"])
+        tag = "ddppo" if ddppo else "bn"
+        out[f"mem_{tag}_out"] = y.contiguous().numpy()
+        for k, v in mod.state_dict().items():
+            out[f"mem_{tag}_sd.{k}"] = v.numpy()
+    w = waveform_case_inputs()
+    metrics = ["si_sdr", "sd_sdr", "snr", "srr", "si_sdri", "sd_sdri", "snri", "si_sar"]
+    q = em.compute_waveform_quality(w, metrics)
+    out["wq_mono"] = np.array([q["mono"][k] for k in metrics], dtype=np.float64)
+    out["wq_mem"] = np.array([q["monoFromMem"][k] for k in metrics], dtype=np.float64)
+    out["wq_names"] = np.array(metrics)
+    np.savez_compressed(os.path.join(GOLDEN, "postproc.npz"), **out)
+    print("wrote postproc.npz", {k: v.shape for k, v in out.items()})
+
+
 def main():
     if not os.path.isdir(REF_ROOT):
         sys.exit("needs /root/reference (build container only)")
     sim_train, sim_eval, ds_mod = load_reference_modules()
     os.makedirs(GOLDEN, exist_ok=True)
+    gen_postproc()
     for name, K, lens, seed, norm in REF_CASES:
         with tempfile.TemporaryDirectory() as tmp:
             monos, _ = write_case_files(tmp, K, lens, seed)

@@ -176,11 +176,26 @@ def test_backward_kernels_layer_by_layer():
     assert not bad, bad
 
 
+# End-to-end gradient bounds per block, ~1.2x the measured rel-L2 (B200, B = 16, round-2 table in DESIGN.md 4.4):
+#   head 0.004 | dec4 0.048 | dec3 0.072 | dec2 0.10 | dec1 0.11 | dec0 0.12 | enc4 0.134 | enc3 0.126 | enc2 0.113 | enc1 0.12 | enc0 0.09
+# Each single backward kernel is within the stated 5e-2 on identical inputs (test_backward_kernels_layer_by_layer: 0.014-0.043);
+# the end-to-end figure compounds one such error per block passed on the way back from the loss (11 blocks to enc0) on
+# top of the ReLU-gate flips of a bf16 forward, which is why it grows with the distance from the output and not with the
+# layer's own arithmetic.
+_E2E_BOUNDS = {"dec.5": 0.01, "dec.4": 0.07, "dec.3": 0.09, "dec.2": 0.12, "dec.1": 0.14, "dec.0": 0.15,
+               "enc.4": 0.16, "enc.3": 0.15, "enc.2": 0.14, "enc.1": 0.145, "enc.0": 0.11}
+
+
+def _e2e_bound(name):
+    tag, _, rest = name.partition(".cnn.")
+    return _E2E_BOUNDS[("enc" if tag.startswith("enc") else "dec") + "." + rest.split(".")[0]]
+
+
 def test_backward_end_to_end_against_fp32_autograd():
     """All parameter gradients of both separators under a linear functional of the outputs against fp32 autograd with the
-    CUDA path's operand roundings emulated in the oracle's forward.  Tolerance: rel-L2 0.2 and cosine 0.98 - the residual
-    is the gate-flip noise described above, which grows with depth (measured 0.05 at the last decoder block, 0.13 at the
-    deepest encoder block) and is unbiased (norm ratios within 1 %)."""
+    CUDA path's operand roundings emulated in the oracle's forward.  Tolerance: the per-block table ``_E2E_BOUNDS`` (the
+    tightest bounds that pass with ~20 % margin) and cosine 0.98 - the residual is the gate-flip noise described above,
+    compounded per block on the way back from the loss, and it is unbiased (norm ratios within 2 %)."""
     B = 16
     enc_sd, dec_sd = U.init_state(False, seed=11)
     enc2_sd, dec2_sd = U.init_state(True, seed=12)
@@ -202,7 +217,8 @@ def test_backward_end_to_end_against_fp32_autograd():
     assert rel_l2(mask.detach().cpu().numpy(), wm.detach().numpy()) < TOL_FWD
     assert rel_l2(mono.detach().cpu().numpy(), wmono.detach().numpy()) < TOL_FWD
     errs = _grad_errors(pol, sds)
-    bad = {k: round(v, 4) for k, v in errs.items() if not v < 0.2}
+    print("E2E_GRAD_TABLE", {k: round(v, 4) for k, v in errs.items()})
+    bad = {k: round(v, 4) for k, v in errs.items() if not v < _e2e_bound(k)}
     assert not bad, bad
     mods = (pol.binSep_enc.passive_sep_encoder, pol.binSep_dec.passive_sep_decoder,
             pol.bin2mono_enc.passive_sep_encoder, pol.bin2mono_dec.passive_sep_decoder)
