@@ -114,17 +114,19 @@ class CpuReference:
 
 
 def cpu_sample_size(cores):
-    """Mixtures per CPU step: a few tasks per worker, bounded so that a step stays around a second."""
+    """Mixtures per CPU step of the in-line `cpu_baseline` leg: a few tasks per worker, bounded so that a step stays around a second."""
     return max(16, min(256, 4 * cores))
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU arithmetic on the box's host cores, on OUR arm's configuration - every step is
+    the full 1024-mixture batch of configs[1] (about 1.4 s per step on 16 cores, so the default 20 + 3 steps take ~35 s)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     monos, rirs, lens, tc = synth_host_inputs()
     ref = CpuReference()
-    sample = cpu_sample_size(ref.cores)
+    sample = B_PER_GPU
     sl = [i % N_DISTINCT for i in range(sample)]
     for _ in range(max(args.warmup, 1)):
         ref.step(monos[sl], rirs[sl], lens[sl], tc[sl])
@@ -134,12 +136,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     ref.close()
     value = sample * args.steps / dt
+    world = args.gpus
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
-            "config": workload_config({"sample_per_step": sample}),
+            "config": workload_config({"global_batch": world * B_PER_GPU, "parallelism": f"shard-by-mixture x{world}, no data-path collective"}),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port",
-                             "sample": f"{sample} mixtures/step of the same seeded workload, scipy.fftconvolve + restated librosa STFT on a {ref.cores}-process pool, then torch-fp32 U-Net on {ref.cores} threads"},
+                             "sample": f"{sample} mixtures/step (one full per-GPU batch of the same seeded workload; the host does not grow with N), "
+                                       f"scipy.fftconvolve + restated librosa STFT on a {ref.cores}-process pool, then torch-fp32 U-Net on {ref.cores} threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -195,6 +199,60 @@ class ClockSampler:
             sm, mx, reasons = self._collect(t0 if t_load0 is None else t_load0, t1 + 0.05)
             window = "timed region + the warm-up steps before it (same load)"
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[3] as written: 14 env PROCESSES per GPU, each calling the B = 1 drop-in shim once per env step
+# (common/env_utils.py:236-269 forkserver workers; task.py:85-86 -> sim.get_current_mixed_bin_audio_mag_spec)
+# ------------------------------------------------------------------------------------------------
+def _rollout_worker(idx, local, n_steps, barrier, out_q):
+    import numpy as np
+    import torch
+    from types import SimpleNamespace
+    torch.cuda.set_device(local)
+    from move2hear_active_av_separation_b200 import render as MR
+    from oracle import render as R
+    monos = R.synth_monos(1, K_SRC, N_SAMPLES, seed=1000 + idx)[0]
+    rp, ln = R.synth_rirs(8, K_SRC, L_TAPS, seed=2000 + idx, ragged=True)
+    rirs = [[R.rir_wav_layout(rp[j, k], int(ln[j, k])) for k in range(K_SRC)] for j in range(8)]
+    sim = SimpleNamespace(_cached_mono_waveforms={}, _cached_mono_specs={}, config=SimpleNamespace(AUDIO=SimpleNamespace(NORM_TYPE="l2")))
+    names = ["a", "b"]
+    for j in range(3):                                   # context, library load, mono-spec cache
+        MR.render_sim_arrays(sim, list(monos), rirs[j % 8], names, 1.2)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for j in range(n_steps):
+        obs = MR.render_sim_arrays(sim, list(monos), rirs[j % 8], names, 1.2)     # returns host fp16 [512,32,2] + the 3 side-effect fields
+    dt = time.perf_counter() - t0
+    barrier.wait()
+    out_q.put((idx, dt, float(np.asarray(obs, dtype=np.float32).sum())))
+
+
+def run_rollout_processes(local, n_procs=14, n_steps=40):
+    """env-steps/s of `n_procs` processes sharing GPU `local` (one CUDA context each), each rendering one mixture per step."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    barrier, q = ctx.Barrier(n_procs), ctx.Queue()
+    procs = [ctx.Process(target=_rollout_worker, args=(i, local, n_steps, barrier, q)) for i in range(n_procs)]
+    t_spawn = time.perf_counter()
+    for p in procs:
+        p.start()
+    res = []
+    try:
+        for _ in range(n_procs):
+            res.append(q.get(timeout=600))
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    dts = [r[1] for r in res]
+    return {"workload": "configs[3] per-process mode: %d processes x 1 mixture (K=2, sim dtypes: fp16 obs + phases + all-source GT) per env step, "
+                        "inputs as host arrays, outputs as host numpy (the sensors' contract)" % n_procs,
+            "processes": n_procs, "steps_per_process": n_steps, "env_steps_per_s": n_procs * n_steps / max(dts),
+            "latency_ms_per_step_mean": 1e3 * sum(dts) / len(dts) / n_steps, "latency_ms_per_step_worst_process": 1e3 * max(dts) / n_steps,
+            "startup_s": time.perf_counter() - t_spawn - max(dts),
+            "reference_cpu_ms_per_step": "15-36 ms per env step and core (SURVEY 8a, measured in the survey container)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -415,37 +473,113 @@ def run_ours(args):
     lat_roll_eager = latency(roll_eager, 50)
     lat_roll_graph = latency(lambda: graphed(rm, rr, rl, rt), 50)
 
-    # ---- BASELINE configs[4] flavour (farTarget / unheard stress): 4 sources, 48000-tap RIRs (3 x the clip: the kernel's
-    # "taps that reach the window" clipping and the un-pruned first radix stage are exercised), B = 1024 mixtures, render only.
-    # Parity of this shape is covered by tests (golden cases k3_long / k4_48000); inputs are generated on the device.
-    K_ST, L_ST = 4, 48000
+    # ---- BASELINE configs[4] (farTarget / unheard stress) as written: K in {3, 4} sources x L in {32000, 48000} taps (2-3 s RIRs:
+    # the "taps that reach the window" clipping and the un-pruned first radix stage are exercised), B = 4096 mixtures per GPU,
+    # render + binSep inference, every rank independent.  Parity of these shapes: golden cases k3_long / k4_48000.
+    # Inputs are generated on the device (6.3 GB of RIRs at the largest point).
+    B_ST = 4096
+    sweep = []
     gen = torch.Generator(device=dev)
     gen.manual_seed(17 + rank)
-    st_mono = (3000.0 * torch.randn((B, K_ST, N_SAMPLES), device=dev, generator=gen)).round().clamp(-32767, 32767).to(torch.int16)
-    decay = torch.exp(-torch.arange(L_ST, device=dev, dtype=torch.float32) / (L_ST / 6.0))
-    st_rir = torch.randn((B, K_ST, 2, L_ST), device=dev, generator=gen) * decay * 0.03
-    st_len = torch.full((B, K_ST), L_ST, dtype=torch.int32, device=dev)
+    d_tc_st = d_tc.repeat(B_ST // B, 1)
+    for K_ST, L_ST in ((3, 32000), (3, 48000), (4, 32000), (4, 48000)):
+        st_mono = (3000.0 * torch.randn((B_ST, K_ST, N_SAMPLES), device=dev, generator=gen)).round().clamp(-32767, 32767).to(torch.int16)
+        decay = torch.exp(-torch.arange(L_ST, device=dev, dtype=torch.float32) / (L_ST / 6.0))
+        st_rir = torch.randn((B_ST, K_ST, 2, L_ST), device=dev, generator=gen)
+        st_rir.mul_(decay).mul_(0.03)
+        st_len = torch.full((B_ST, K_ST), L_ST, dtype=torch.int32, device=dev)
+        st_waves = torch.empty((B_ST, K_ST, 2, N_SAMPLES), dtype=torch.int16, device=dev)
 
-    def step_stress(tm=None):
-        if tm is not None:
-            tm[0].record(stream)
-        w = rend.rir_convolve(st_mono, st_rir, st_len)
-        if tm is not None:
-            tm[1].record(stream)
-        rend.stft_waves(w)
-        if tm is not None:
-            tm[2].record(stream)
+        def step_stress(tm=None):
+            if tm is not None:
+                tm[0].record(stream)
+            w = rend.rir_convolve(st_mono, st_rir, st_len, out=st_waves)
+            if tm is not None:
+                tm[1].record(stream)
+            mix, _, _ = rend.stft_waves(w)
+            if tm is not None:
+                tm[2].record(stream)
+            with torch.no_grad():
+                dec(*enc({"mixed_bin_audio_mag": mix, "target_class": d_tc_st}))
+            if tm is not None:
+                tm[3].record(stream)
 
-    for _ in range(3):
-        step_stress()
-    st_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(5)]
-    barrier()
-    for tm in st_ev:
-        step_stress(tm)
-    barrier()
-    ms_st_conv = sum(t[0].elapsed_time(t[1]) for t in st_ev) / len(st_ev)
-    ms_st_stft = sum(t[1].elapsed_time(t[2]) for t in st_ev) / len(st_ev)
-    del st_mono, st_rir, st_len
+        for _ in range(2):
+            step_stress()
+        st_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(3)]
+        barrier()
+        for tm in st_ev:
+            step_stress(tm)
+        barrier()
+        ms_c = sum(t[0].elapsed_time(t[1]) for t in st_ev) / len(st_ev)
+        ms_s = sum(t[1].elapsed_time(t[2]) for t in st_ev) / len(st_ev)
+        ms_u = sum(t[2].elapsed_time(t[3]) for t in st_ev) / len(st_ev)
+        alg = (2 * K_ST * N_SAMPLES + 8 * K_ST * L_ST + 4 * 512 * 32 * 2) * B_ST           # bytes(K, N, L) per mixture
+        sweep.append({"K": K_ST, "L": L_ST, "batch_per_gpu": B_ST, "ms_conv": ms_c, "ms_stft": ms_s, "ms_unet": ms_u,
+                      "mixtures_per_s": world * B_ST / ((ms_c + ms_s + ms_u) * 1e-3),
+                      "render_algorithmic_gb_per_s": alg / ((ms_c + ms_s) * 1e-3) / 1e9,
+                      "render_frac_of_hbm_peak": alg / ((ms_c + ms_s) * 1e-3) / 1e9 / peaks()["hbm_gbs"]})
+        del st_mono, st_rir, st_len, st_waves
+    torch.cuda.empty_cache()
+
+    # ---- batched observation transport - the 14 environments of a rank send (sound ids, RIR ids) requests,
+    # the trainer renders them in one batch from the device caches straight into rollout-storage tensors (all 4 audio sensors)
+    from move2hear_active_av_separation_b200 import transport as TR
+    n_keys = 64
+    tr_clips = {f"s{i}": monos[i % N_DISTINCT, i % K_SRC] for i in range(16)}
+    tr_rirs = {("scene", 0, r, s_): np.ascontiguousarray(rirs[(r * 2 + s_) % N_DISTINCT, s_ % K_SRC, :, :L_TAPS - 37 * r].T) for r in range(n_keys // 2) for s_ in (0, 1)}
+    bor = TR.BatchedObservationRenderer(tr_clips.__getitem__, tr_rirs.__getitem__, device=dev, gt_mono_mag_norm=1.2, rir_capacity=256, clip_capacity=32)
+    T_FR = 32
+    storage = {"mixed_bin_audio_mag": torch.zeros(21, B_ROLL, 512, T_FR, 2, device=dev), "mixed_bin_audio_phase": torch.zeros(21, B_ROLL, 512, T_FR, 2, device=dev),
+               "gt_bin_comps": torch.zeros(21, B_ROLL, 512, T_FR, 4 * K_SRC, device=dev), "gt_mono_comps": torch.zeros(21, B_ROLL, 512, T_FR, 2 * K_SRC, device=dev)}
+    rng = np.random.default_rng(5 + rank)
+
+    def make_requests():
+        obs = []
+        for e in range(B_ROLL):
+            req = TR.AudioRenderRequest((f"s{int(rng.integers(16))}", f"s{int(rng.integers(16))}"), "scene", 0, int(rng.integers(n_keys // 2)), (0, 1))
+            obs.append({k: TR.DeferredObservation(req, k) for k in TR.AUDIO_SENSORS})
+        return obs
+
+    req_steps = [make_requests() for _ in range(20)]
+    for i in range(20):                                   # first pass fills the caches (misses)
+        bor.insert_into(req_steps[i], storage, 1 + i)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for rep_ in range(3):
+        for i in range(20):                               # one episode of MAX_EPISODE_STEPS = 20
+            bor.insert_into(req_steps[i], storage, 1 + i)
+            torch.cuda.synchronize(dev)                   # the policy needs the observation before the next env step
+    dt_tr = (time.perf_counter() - t0) / 60
+    transport = {"workload": "SURVEY 8f row 3: 14 envs send (sound ids, RIR ids); one batched render (sim dtypes, phases, all-source GT) from the device "
+                             "caches written into RolloutStorage-shaped fp32 tensors, device sync per step",
+                 "batch": B_ROLL, "latency_ms_per_step": 1e3 * dt_tr, "env_steps_per_s": world * B_ROLL / dt_tr,
+                 "bytes_over_pipe_per_env_step": 4 * 100, "bytes_over_pipe_reference": 2 * 512 * 32 * (2 + 2 + 4 * K_SRC + 2 * K_SRC),
+                 "cache": bor.cached.stats()}
+    del storage, bor
+
+    # ---- host <-> device copy bandwidth of this rank with every rank copying at the same time: the ceiling of `e2e`
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    side2 = torch.cuda.Stream(dev)
+
+    def copy_bw(both):
+        barrier()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(4):
+            probe_d.copy_(probe_h, non_blocking=True)
+            if both:
+                with torch.cuda.stream(side2):
+                    h_out.view(-1).view(torch.uint8)[:128 << 20].copy_(probe_d[:128 << 20], non_blocking=True)
+        stream.wait_stream(side2)
+        b2.record(stream)
+        barrier()
+        return 4 * (256 << 20) / (a.elapsed_time(b2) * 1e-3) / 1e9
+
+    copy_bw(False)
+    pcie = {"h2d_gb_per_s_alone": copy_bw(False), "h2d_gb_per_s_with_concurrent_d2h": copy_bw(True), "ranks_copying_concurrently": world}
+    del probe_h, probe_d
 
     # ---- BASELINE configs[2]: separator pretraining step (dataset-path render + both U-Nets fwd/bwd + L1 losses + Adam),
     # B = 256 per GPU, gradients all-reduced (mean) across ranks over NCCL, overlapped with backward
@@ -454,10 +588,11 @@ def run_ours(args):
     if not args.no_train:
         train, ms_train = run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_len, d_tc, barrier, stream)
 
-    times = torch.tensor([ms_total, ms_e2e, ms_train, ms_cached], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, ms_e2e, ms_train, ms_cached, -pcie["h2d_gb_per_s_alone"], -pcie["h2d_gb_per_s_with_concurrent_d2h"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, ms_train, ms_cached = (float(times[i]) for i in range(4))
+    pcie["h2d_gb_per_s_alone"], pcie["h2d_gb_per_s_with_concurrent_d2h"] = -float(times[4]), -float(times[5])      # slowest rank
     if train is not None:
         train["ms_per_step"] = ms_train / train["steps"]
         train["value"] = world * train["batch_per_gpu"] * train["steps"] / (ms_train * 1e-3)
@@ -468,6 +603,11 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank != 0:
         return
+    rollout_procs = None
+    if world == 1 and not args.no_procs:
+        del d_mono, d_rir                   # the children allocate their own contexts next to this one
+        torch.cuda.empty_cache()
+        rollout_procs = run_rollout_processes(local)
 
     pk = peaks()
     ms_step = ms_total / args.steps
@@ -522,9 +662,10 @@ def run_ours(args):
                          "latency_ms_eager": lat_roll_eager, "latency_ms_cuda_graph": lat_roll_graph,
                          "note": "gpu_ms: back-to-back calls timed with CUDA events; latency_ms: wall clock per call with a device synchronise after each (host launch path included)",
                          "mixtures_per_s_cuda_graph": world * B_ROLL / (lat_roll_graph * 1e-3)},
-        "stress_render": {"workload": "configs[4] flavour: render of 1024 mixtures with K = 4 sources and 48000-tap RIRs (per GPU)",
-                          "ms_conv": ms_st_conv, "ms_stft": ms_st_stft, "mixtures_per_s": world * B / ((ms_st_conv + ms_st_stft) * 1e-3),
-                          "algorithmic_gb_per_s": (2 * K_ST * N_SAMPLES + 8 * K_ST * L_ST + 4 * 512 * 32 * 2) * B / ((ms_st_conv + ms_st_stft) * 1e-3) / 1e9},
+        "rollout_processes": rollout_procs,
+        "rollout_transport": transport,
+        "stress_sweep": {"workload": "configs[4]: K x L sweep, B = 4096 mixtures per GPU, render + binSep U-Net inference, ranks independent", "points": sweep},
+        "pcie_probe": pcie,
         "gpu_launches": OUR_LAUNCHES_PER_STEP * args.steps,
         "clocks": clocks,
         "train_step": train,
@@ -583,6 +724,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the pretraining-step measurement (train_step key)")
+    ap.add_argument("--no-procs", action="store_true", help="skip the 14-process rollout measurement (rollout_processes key, N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -26,6 +26,7 @@ N_BINS = 512
 SAMPLE_RATE = 16000
 FLAG_F16_OBS = 1
 FLAG_RAW_MAG = 2
+_NP_DTYPE = {torch.float16: np.float16, torch.float32: np.float32, torch.int16: np.int16, torch.int32: np.int32}
 
 
 def _stream_ptr(device) -> int:
@@ -127,26 +128,77 @@ class AudioRenderer:
         return out
 
     # ---- host-array convenience (what the shims use) -------------------------------------------------
+    # The drop-in path runs once per environment step inside every env worker (14 processes per GPU, SURVEY hard part 6):
+    # inputs are assembled in a pinned staging buffer and uploaded with ONE asynchronous copy, results come back through
+    # ONE pinned buffer and ONE synchronisation (first version: three pageable uploads and four blocking .cpu() calls).
+    def _pinned(self, name: str, nbytes: int) -> torch.Tensor:
+        bufs = self.__dict__.setdefault("_pinned_bufs", {})
+        buf = bufs.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = bufs[name] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+        return buf
+
     def pack_sources(self, monos: Sequence[np.ndarray], rirs: Sequence[np.ndarray]):
         """K int16 ``[N]`` clips + K wav-layout ``[L_k, 2]`` RIRs -> device tensors for a batch of one."""
         K = len(monos)
         N = len(monos[0])
         Lmax = max(1, max(len(r) for r in rirs))
+        Lmax += Lmax & 1                                  # even rows: the packed-load variant of the kernel
         for m in monos:
             if np.asarray(m).dtype != np.int16:
                 # the reference convolves whatever wavfile.read returned; its clips are int16 PCM - a silent cast of a
                 # float clip would truncate it before the convolution
                 raise _lib.M2HError(f"source clips must be int16 PCM (wavfile.read of the reference's sounds), got {np.asarray(m).dtype}")
-        mono = np.stack([np.asarray(m, dtype=np.int16) for m in monos])[None]
-        rir = np.zeros((1, K, 2, Lmax), dtype=np.float32)
-        lens = np.zeros((1, K), dtype=np.int32)
-        for k, r in enumerate(rirs):
+        ev = self.__dict__.pop("_in_flight", None)
+        if ev is not None:
+            ev.synchronize()                              # the previous upload must have left the staging buffer (it long has)
+        n_mono, n_rir, n_len = 2 * K * N, 4 * K * 2 * Lmax, 4 * K
+        o_rir = (n_mono + 15) & ~15
+        o_len = o_rir + n_rir
+        total = o_len + n_len
+        host = self._pinned("in", total)
+        hb = host.numpy()
+        mono_h = hb[:n_mono].view(np.int16).reshape(1, K, N)
+        rir_h = hb[o_rir:o_rir + n_rir].view(np.float32).reshape(1, K, 2, Lmax)
+        len_h = hb[o_len:o_len + n_len].view(np.int32).reshape(1, K)
+        for k, (m, r) in enumerate(zip(monos, rirs)):
+            mono_h[0, k] = m
             r = np.asarray(r)
-            lens[0, k] = len(r)
+            len_h[0, k] = len(r)
             if len(r):
-                rir[0, k, :, :len(r)] = np.asarray(r, dtype=np.float32).T
-        dev = self.device
-        return (torch.from_numpy(mono).to(dev), torch.from_numpy(rir).to(dev), torch.from_numpy(lens).to(dev)), N
+                rir_h[0, k, :, :len(r)] = np.asarray(r, dtype=np.float32).T
+            rir_h[0, k, :, len(r):] = 0
+        dev_buf = torch.empty(total, dtype=torch.uint8, device=self.device)
+        dev_buf.copy_(host[:total], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._in_flight = ev
+        mono_d = dev_buf[:n_mono].view(torch.int16).view(1, K, N)
+        rir_d = dev_buf[o_rir:o_rir + n_rir].view(torch.float32).view(1, K, 2, Lmax)
+        len_d = dev_buf[o_len:o_len + n_len].view(torch.int32).view(1, K)
+        return (mono_d, rir_d, len_d), N
+
+    def fetch(self, tensors: Sequence[Optional[torch.Tensor]]):
+        """Device tensors -> numpy arrays (``None`` passes through) through one pinned buffer and one synchronisation."""
+        live = [t for t in tensors if t is not None]
+        sizes = [t.numel() * t.element_size() for t in live]
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 15) & ~15
+        host = self._pinned("out", total)
+        for t, o, n in zip(live, offs, sizes):
+            host[o:o + n].copy_(t.contiguous().view(-1).view(torch.uint8), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        out, it = [], iter(zip(live, offs, sizes))
+        for t in tensors:
+            if t is None:
+                out.append(None)
+                continue
+            tt, o, n = next(it)
+            a = host[o:o + n].numpy().view(_NP_DTYPE[tt.dtype]).reshape(tuple(tt.shape)).copy()    # fresh array owned by the caller
+            out.append(a)
+        return out
 
     def mono_gt_spec(self, mono: np.ndarray, gt_mono_mag_norm: float, want_phase: bool, dataset_semantics: bool = False):
         """Cached-per-sound monaural GT spectrogram (simulator_train.py:443-459, dataset.py:201-212).
@@ -157,10 +209,11 @@ class AudioRenderer:
         mag, ph = self.stft_f32(wave, want_phase)
         mag = mag[0, :, :, 0]
         rms = torch.sqrt(torch.mean(mag * mag))
-        if (dataset_semantics or gt_mono_mag_norm != 0.0) and float(rms) != 0.0:
-            mag = mag * gt_mono_mag_norm / rms
-        mag = mag.cpu().numpy()
-        return (mag, ph[0, :, :, 0].cpu().numpy()) if want_phase else (mag, None)
+        if dataset_semantics or gt_mono_mag_norm != 0.0:
+            # `if rms != 0` of the reference without a host round trip: an all-zero clip keeps its all-zero magnitude
+            mag = torch.where(rms != 0, mag * gt_mono_mag_norm / rms, mag)
+        mag, ph = self.fetch([mag, ph[0, :, :, 0] if want_phase else None])
+        return mag, ph
 
 
 _renderers = {}
@@ -282,8 +335,8 @@ def render_sim_arrays(self, monos, rirs, names, gt_mono_mag_norm, rend=None):
 def _finish_sim_render(self, out, monos, names, gt_mono_mag_norm, rend):
     """Side-effect fields + return value of the simulator render from the device results of one mixture."""
     K = len(monos)
-    gt = out["gt"][0].cpu().numpy()                       # [K,512,T,4] fp16
-    self._gt_bin_audio_components = [gt[k] for k in range(K)]
+    gt, phase, mix = rend.fetch([out["gt"][0], out["mix_phase"][0], out["mix_mag"][0]])      # one pinned D2H + one sync
+    self._gt_bin_audio_components = [gt[k] for k in range(K)]                                   # [512,T,4] fp16 each
     self._gt_mono_audio_components = []
     for k, name in enumerate(names):
         if name not in self._cached_mono_specs:
@@ -292,8 +345,8 @@ def _finish_sim_render(self, out, monos, names, gt_mono_mag_norm, rend):
             mag, ph = rend.mono_gt_spec(monos[k], gt_mono_mag_norm, want_phase=True)
             self._cached_mono_specs[name] = np.stack([mag, ph], axis=-1)
         self._gt_mono_audio_components.append(self._cached_mono_specs[name].astype(np.float16))
-    self._mixed_bin_audio_phase = out["mix_phase"][0].cpu().numpy()
-    return out["mix_mag"][0].cpu().numpy()
+    self._mixed_bin_audio_phase = phase
+    return mix
 
 
 def compute_audiospects(self, rirs_audio, target_class):
@@ -314,9 +367,10 @@ def compute_audiospects_arrays(self, monos, rirs, names, target_class, gt_mono_m
     rend = rend or get_renderer()
     (mono_d, rir_d, len_d), _ = rend.pack_sources(monos, rirs)
     out = rend.render(mono_d, rir_d, len_d, n_gt=1, sim_dtypes=False, want_phase=False)
-    gt_bin_mag = [out["gt"][0, 0].cpu().numpy()]
+    gt_bin, mix = rend.fetch([out["gt"][0, 0], out["mix_mag"][0]])
+    gt_bin_mag = [gt_bin]
     if names[0] not in self._gt_mono_mag_cache:
         mag, _ = rend.mono_gt_spec(monos[0], gt_mono_mag_norm, want_phase=False, dataset_semantics=True)
         self._gt_mono_mag_cache[names[0]] = mag
     gt_mono_mag = [np.expand_dims(self._gt_mono_mag_cache[names[0]], axis=2).astype("float32")]
-    return out["mix_mag"][0].cpu().numpy(), gt_bin_mag, gt_mono_mag, np.array([target_class]).astype("int64")
+    return mix, gt_bin_mag, gt_mono_mag, np.array([target_class]).astype("int64")

@@ -70,3 +70,54 @@ def test_graphed_rollout_step_with_bin2mono_and_memory_refiner():
     assert torch.equal(g.mask, mask) and torch.equal(g.pred_mono, pred_mono)
     assert g.pred_mono.shape == (B, 512, 32, 1) and g.post_out.shape == (B, 512, 32, 1)
     assert torch.allclose(g.post_out, mem, rtol=1e-4, atol=1e-5)
+
+
+def test_graphed_rollout_step_with_native_acoustic_mem_and_stft_l2_against_oracle():
+    """bin2mono prologue + second U-Net + AcousticMem + STFT_L2_distance replayed from ONE graph, checked
+    against the oracle (render_dataset -> unet -> acoustic_mem_forward -> stft_l2_distance), not against eager CUDA."""
+    from oracle import postproc as OP
+    from move2hear_active_av_separation_b200.graphs import GraphedSeparation
+    from move2hear_active_av_separation_b200.postproc import AcousticMem
+    from move2hear_active_av_separation_b200.separator_cnn import PassiveSepDecCNN, PassiveSepEncCNN
+    dev = torch.device("cuda", 0)
+    sds = [*U.init_state(False, seed=3), *U.init_state(True, seed=4)]
+    mods = [PassiveSepEncCNN().to(dev).eval(), PassiveSepDecCNN().to(dev).eval(), PassiveSepEncCNN(True).to(dev).eval(), PassiveSepDecCNN(True).to(dev).eval()]
+    for m, sd in zip(mods, sds):
+        m.load_state_dict(sd)
+    torch.manual_seed(7)
+    mem = AcousticMem(use_ddppo=True).to(dev).eval()
+    mem_sd = {k: v.detach().cpu() for k, v in mem.state_dict().items()}
+    B, K = 14, 2
+    g = GraphedSeparation(mods[0], mods[1], dev, B, K, bin2mono_enc=mods[2], bin2mono_dec=mods[3], acoustic_mem=mem, with_stft_l2=True)
+    gen = torch.Generator().manual_seed(9)
+    for seed in (0, 1):
+        monos = R.synth_monos(B, K, seed=seed)
+        rirs, lens = R.synth_rirs(B, K, L=16000, seed=20 + seed, ragged=True)
+        tc = np.random.default_rng(seed).integers(0, 11, (B, 1))
+        prev = torch.rand(B, 512, 32, 1, generator=gen)
+        gt_bin = torch.stack([torch.rand(B, 512, 32, generator=gen), torch.rand(B, 512, 32, generator=gen) * 6 - 3,
+                              torch.rand(B, 512, 32, generator=gen), torch.rand(B, 512, 32, generator=gen) * 6 - 3], dim=-1)
+        gt_mono = torch.stack([torch.rand(B, 512, 32, generator=gen), torch.rand(B, 512, 32, generator=gen) * 6 - 3], dim=-1)
+        g.prev_mem.copy_(prev)
+        g.gt_bin_comps.copy_(gt_bin)
+        g.gt_mono_comps.copy_(gt_mono)
+        g(torch.from_numpy(monos), torch.from_numpy(rirs), torch.from_numpy(lens), torch.from_numpy(tc))
+        torch.cuda.synchronize()
+        obs = torch.from_numpy(np.stack([R.render_dataset(list(monos[b]), [R.rir_wav_layout(rirs[b, k], int(lens[b, k])) for k in range(K)], 0)[0]
+                                         for b in range(B)]))
+        with torch.no_grad():
+            mask = U.separator_forward(sds[0], sds[1], obs, torch.from_numpy(tc))
+            mono = U.separator_forward(sds[2], sds[3], mask, convert_bin2mono=True, mixed_audio=obs)
+            want_mem = OP.acoustic_mem_forward(mem_sd, mono, prev, use_ddppo=True)
+            wb, wm = OP.stft_l2_distance(obs, mask, gt_bin, mono, gt_mono)
+            _, wmm = OP.stft_l2_distance(obs, mask, gt_bin, want_mem, gt_mono)
+        rel = lambda a, b: float((a.cpu() - b).norm() / b.norm())
+        assert rel(g.mask, mask) < 2e-2 and rel(g.pred_mono, mono) < 4e-2
+        assert rel(g.pred_monoFromMem, want_mem) < 4e-2            # fp32 refiner on a bf16 U-Net's output
+        # the refiner kernel itself, on the graph's own pred_mono: fp32-exact
+        with torch.no_grad():
+            assert rel(g.pred_monoFromMem, OP.acoustic_mem_forward(mem_sd, g.pred_mono.cpu(), prev, use_ddppo=True)) < 1e-5
+            gb, gm = OP.stft_l2_distance(g.obs.cpu(), g.mask.cpu(), gt_bin, g.pred_mono.cpu(), gt_mono)
+        assert torch.allclose(g.stft_l2["bin"].cpu(), gb, rtol=1e-5) and torch.allclose(g.stft_l2["mono"].cpu(), gm, rtol=1e-5)
+        assert torch.allclose(g.stft_l2["bin"].cpu(), wb, rtol=5e-2) and torch.allclose(g.stft_l2["mono"].cpu(), wm, rtol=5e-2)
+        assert torch.allclose(g.stft_l2["monoFromMem"].cpu(), wmm, rtol=5e-2)
