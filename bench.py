@@ -686,7 +686,7 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
     pol = Move2HearPassiveWoMemoryPolicy().to(dev).train()
     broadcast_module_state(pol)
     opt = torch.optim.Adam(pol.parameters(), lr=5e-4, eps=1e-5, fused=True)       # passive_trainer.py:194-195
-    red = GradientAllReducer(pol.parameters()) if world > 1 else None
+    red = GradientAllReducer(pol.parameters(), modules=pol) if world > 1 else None
     B = B_TRAIN
     mono, rir, ln, tc = d_mono[:B], d_rir[:B], d_len[:B], d_tc[:B]
 
@@ -711,7 +711,7 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
     losses.append((float(b.detach()), float(m.detach())))
     per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
     info = {"workload": "configs[2] pretraining step: render (dataset path) + binSep & bin2mono U-Nets fwd/bwd (train-mode BN) + L1 losses + fused Adam",
-            "batch_per_gpu": B, "steps": steps, "unit": "mixtures/s", "grad_allreduce": "NCCL AVG, 32 MB fp32 buckets, after backward on the compute stream" if world > 1 else "none (1 GPU)",
+            "batch_per_gpu": B, "steps": steps, "unit": "mixtures/s", "grad_allreduce": "NCCL AVG in place on the flat gradient arena the wgrad kernels write (32 MB fp32 buckets, no pack / un-pack), after backward on the compute stream" if world > 1 else "none (1 GPU)",
             "bin_mono_loss_first_last": losses, "ms_per_step_median_this_rank": per_step[len(per_step) // 2], "ms_per_step_max_this_rank": per_step[-1]}
     return info, marks[0].elapsed_time(marks[-1])
 

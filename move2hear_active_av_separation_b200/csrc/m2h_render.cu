@@ -9,6 +9,7 @@
 #include "../../include/m2h.h"
 #include "m2h_internal.h"
 #include "render_conv.cuh"
+#include "render_conv24.cuh"
 #include "render_stft.cuh"
 #include "m2h_tables.h"
 
@@ -30,6 +31,7 @@ extern "C" int m2h_abi_version(void) { return M2H_ABI_VERSION; }
 // ---------------------------------------------------------------------------------------------
 struct DeviceTables {
   M2hConvTables* conv = nullptr;
+  M2hConv24Tables* conv24 = nullptr;
   M2hStftTables* stft = nullptr;
   M2hStftTables* istft = nullptr;       // Bluestein tables of the 1022-point inverse DFT (librosa.istft's inferred n_fft)
   int n_sms = 0;
@@ -75,6 +77,15 @@ m2h_rir_conv_kernel(const ConvParams P, const M2hConvTables* __restrict__ tab) {
   conv_cta_body<VEC>(P, s, tab, blockIdx.x, gridDim.x);
 }
 
+// RIRs of at most 16384 taps: circular length 24576, two CTAs per SM (render_conv24.cuh)
+template <bool VEC>
+__global__ void __launch_bounds__(M2H_C24_THREADS, M2H_C24_CTAS_PER_SM)
+m2h_rir_conv24_kernel(const ConvParams P, const M2hConv24Tables* __restrict__ tab) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Conv24Smem& s = *reinterpret_cast<Conv24Smem*>(smem_raw);
+  conv24_cta_body<VEC>(P, s, tab, blockIdx.x, gridDim.x);
+}
+
 // 64 registers / thread (no spills): two 512-thread CTAs per SM, 2 x 86 KB of shared memory
 __global__ void __launch_bounds__(M2H_STFT_THREADS, M2H_STFT_CTAS_PER_SM)
 m2h_istft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
@@ -101,9 +112,16 @@ extern "C" int m2h_init(int device) {
   M2H_CUDA_CHECK(cudaSetDevice(device));
   M2H_CUDA_CHECK(cudaDeviceGetAttribute(&d.n_sms, cudaDevAttrMultiProcessorCount, device));
   static M2hConvTables hc;
+  static M2hConv24Tables hc24;
   static M2hStftTables hs, hi;
   static bool host_built = false;
-  if (!host_built) { build_conv_tables(hc); build_stft_tables(hs); build_istft_tables(hi); host_built = true; }
+  if (!host_built) { build_conv_tables(hc); build_conv24_tables(hc24); build_stft_tables(hs); build_istft_tables(hi); host_built = true; }
+  M2H_CUDA_CHECK(cudaMalloc(&d.conv24, sizeof(M2hConv24Tables)));
+  M2H_CUDA_CHECK(cudaMemcpy(d.conv24, &hc24, sizeof(hc24), cudaMemcpyHostToDevice));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv24_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Conv24Smem)));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv24_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Conv24Smem)));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv24_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv24_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaMalloc(&d.conv, sizeof(M2hConvTables)));
   M2H_CUDA_CHECK(cudaMalloc(&d.stft, sizeof(M2hStftTables)));
   M2H_CUDA_CHECK(cudaMemcpy(d.conv, &hc, sizeof(hc), cudaMemcpyHostToDevice));
@@ -137,7 +155,10 @@ extern "C" size_t m2h_render_workspace_bytes(int device) {
   int n_sms = 148;
   if (device >= 0 && device < M2H_MAX_DEVICES && g_tables[device].ready) n_sms = g_tables[device].n_sms;
   else if (device >= 0) { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) n_sms = v; }
-  return (size_t)n_sms * M2H_CONV_SCRATCH_F4 * sizeof(float4);
+  // one spectrum-scratch slot per resident CTA of either convolution kernel (F = 32768: 128 KB x 1 per SM; F = 24576: 96 KB x 2 per SM)
+  const size_t a = (size_t)n_sms * M2H_CONV_SCRATCH_F4 * sizeof(float4);
+  const size_t b = (size_t)n_sms * M2H_C24_CTAS_PER_SM * M2H_C24_SCRATCH_F2 * sizeof(float2);
+  return a > b ? a : b;
 }
 
 static int launch_conv(const int16_t* mono, const int32_t* mono_index, const float* rir, const int32_t* rir_len, const int32_t* rir_index,
@@ -149,6 +170,21 @@ static int launch_conv(const int16_t* mono, const int32_t* mono_index, const flo
   int rc = ensure_init(&dev);
   if (rc != M2H_OK) return rc;
   const int n_items = B * K;
+  static int force_f32768 = -1;
+  if (force_f32768 < 0) { const char* e = getenv("M2H_CONV_F32768"); force_f32768 = (e && atoi(e)) ? 1 : 0; }
+  if (Lmax <= M2H_C24_MAX_TAPS && !force_f32768) {       // every RIR fits the F = 24576 kernel (the reference's RIRs are 1 s = 16000 taps)
+    int grid24 = M2H_C24_CTAS_PER_SM * g_tables[dev].n_sms;
+    if (grid24 > n_items) grid24 = n_items;
+    if (workspace_bytes < (size_t)grid24 * M2H_C24_SCRATCH_F2 * sizeof(float2)) { m2h_set_error("%s: workspace %zu B < %zu B", who, workspace_bytes, (size_t)grid24 * M2H_C24_SCRATCH_F2 * sizeof(float2)); return M2H_ERR_WORKSPACE; }
+    ConvParams P;
+    P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.mono_index = mono_index; P.rir_index = rir_index;
+    P.waves = waves; P.scratch = (float4*)workspace;
+    P.n_items = n_items; P.N = N; P.Lmax = Lmax;
+    const M2hConv24Tables* tab24 = g_tables[dev].conv24;
+    if (conv_can_vectorise(P)) M2H_CUDA_CHECK(launch_pdl(m2h_rir_conv24_kernel<true>, grid24, M2H_C24_THREADS, sizeof(Conv24Smem), stream, P, tab24));
+    else M2H_CUDA_CHECK(launch_pdl(m2h_rir_conv24_kernel<false>, grid24, M2H_C24_THREADS, sizeof(Conv24Smem), stream, P, tab24));
+    return M2H_OK;
+  }
   int grid = g_tables[dev].n_sms;
   if (grid > n_items) grid = n_items;
   if (workspace_bytes < (size_t)grid * M2H_CONV_SCRATCH_F4 * sizeof(float4)) { m2h_set_error("%s: workspace %zu B < %zu B", who, workspace_bytes, (size_t)grid * M2H_CONV_SCRATCH_F4 * sizeof(float4)); return M2H_ERR_WORKSPACE; }

@@ -25,6 +25,20 @@ static void build_conv_tables(M2hConvTables& t) {
   for (int u = 0; u < 16; ++u) t.unit_tw[u] = cis((double)(u < 8 ? 1024 * u : 512 + 1024 * (u - 8)) / 32768.0);
 }
 
+#ifdef M2H_C24_M
+static void build_conv24_tables(M2hConv24Tables& t) {
+  for (int r = 0; r < 256; ++r) {
+    t.a1[r] = cis((double)r / 4096.0);
+    t.a4[r] = cis((double)(4 * r) / 4096.0);
+    t.t256[r] = cis((double)((r >> 4) * (r & 15)) / 256.0);
+  }
+  for (int i = 0; i < 384; ++i) t.m1[i] = cis((double)i / 12288.0);
+  for (int k1 = 0; k1 < 3; ++k1)
+    for (int q1 = 0; q1 < 16; ++q1)
+      for (int q2 = 0; q2 < 16; ++q2) t.g[k1 * 256 + q1 * 16 + q2] = cis((double)(k1 + 3 * q1 + 48 * q2) / 24576.0);
+}
+#endif
+
 // Bluestein tables of an N-point DFT evaluated as a 2048-point circular convolution (c[n] = exp(+i pi n^2 / N)):
 //   forward (the STFT, N = 1023):  X[k] = conj(c[k]) sum_n (x[n] w[n] conj(c[n])) c[k-n]
 //        wc = hann_N * conj(c),  bf = FFT_2048(c on the circle),  cc = conj(c) / 4096   (1/2048 inverse-FFT scale, 1/2 ear untangle)

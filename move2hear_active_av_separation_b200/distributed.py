@@ -23,7 +23,12 @@ class GradientAllReducer:
     B200 this is SLOWER (+3.3 ms per step on 4 GPUs against +0.9 ms): the backward kernels are persistent and fill every SM, so
     the NCCL kernels of the side stream are scheduled piecemeal and every rank waits for the slowest one."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None, overlap: bool = False):
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None, overlap: bool = False,
+                 modules: torch.nn.Module = None):
+        """``modules`` (optional): a module tree containing the separator modules of ``separator_cnn``.  Their backward then
+        writes every parameter gradient straight into this reducer's flat per-bucket buffers (the autograd Functions hand
+        out views of the arena, which ``AccumulateGrad`` adopts as ``p.grad`` without a copy), so a bucket is all-reduced
+        IN PLACE: no ``torch.cat`` pack, no un-pack copy (each cost a 134 MB read + write per step)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.overlap = overlap
@@ -40,6 +45,19 @@ class GradientAllReducer:
         if cur:
             self.buckets.append(cur)
         self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._arena = None            # per bucket: flat fp32 buffer; _slot[id(p)] = (bucket, offset)
+        self._slot = {}
+        if modules is not None:
+            self._arena = []
+            for i, b in enumerate(self.buckets):
+                o = 0
+                for p in b:
+                    self._slot[id(p)] = (i, o)
+                    o += (p.numel() + 3) & ~3                       # 16-byte aligned slots
+                self._arena.append(torch.zeros(o, dtype=torch.float32, device=b[0].device))
+            for m in modules.modules():
+                if hasattr(m, "_grad_struct"):
+                    m._grad_arena = self
         self._pending = [0] * len(self.buckets)
         self._flat = [None] * len(self.buckets)
         self._work = [None] * len(self.buckets)
@@ -58,9 +76,24 @@ class GradientAllReducer:
         """NCCL averages inside the collective; other backends (gloo in the CPU tests) sum and :meth:`finish` divides."""
         return dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
 
+    def grad_view(self, p: torch.nn.Parameter) -> torch.Tensor:
+        """A FRESH view (so that autograd may adopt it) of the arena slot that receives ``p``'s gradient."""
+        i, o = self._slot[id(p)]
+        return self._arena[i][o:o + p.numel()].view(p.shape)
+
+    def _in_arena(self, i: int) -> bool:
+        if self._arena is None:
+            return False
+        base = self._arena[i].data_ptr()
+        return all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+                   and p.grad.data_ptr() == base + 4 * self._slot[id(p)][1] for p in self.buckets[i])
+
     def _launch(self, i: int):
         bucket = self.buckets[i]
-        flat = torch.cat([p.grad.reshape(-1).float() for p in bucket])
+        if self._in_arena(i):
+            flat = self._arena[i]                       # the gradients already live in the flat buffer: reduce in place
+        else:
+            flat = torch.cat([p.grad.reshape(-1).float() for p in bucket])
         self._flat[i] = flat
         if not self.overlap:
             self._work[i] = dist.all_reduce(flat, op=self._avg_op(), group=self.group, async_op=True)
@@ -95,6 +128,8 @@ class GradientAllReducer:
                 torch.cuda.current_stream(flat.device).wait_stream(self._stream)
             if self._avg_op() != dist.ReduceOp.AVG:
                 flat.div_(self.world)
+            if self._arena is not None and flat is self._arena[i]:
+                continue                                # reduced in place
             views, o = [], 0
             for p in bucket:
                 n = p.numel()

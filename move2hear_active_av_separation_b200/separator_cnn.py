@@ -364,6 +364,15 @@ class _PackedModule(nn.Module):
             self._tws = ws
         return ws
 
+    def _alloc_grads(self):
+        """Gradient buffers of one backward: fresh tensors, or - under data-parallel training - fresh views of the
+        ``distributed.GradientAllReducer`` arena, so that the all-reduce runs in place on what the kernels wrote."""
+        arena = getattr(self, "_grad_arena", None)
+        ps = self._train_params()
+        if arena is not None and all(q.requires_grad and q.dtype == torch.float32 for q in ps):
+            return [arena.grad_view(q) for q in ps]
+        return [torch.empty_like(q, memory_format=torch.contiguous_format) for q in ps]
+
     def _train_params(self):
         """Parameters in the order the autograd Functions return their gradients: conv weights, BN weights, BN biases (+ head)."""
         ps = [self.cnn[i][0].weight for i in range(5)] + [self.cnn[i][1].weight for i in range(5)] + [self.cnn[i][1].bias for i in range(5)]
@@ -436,7 +445,7 @@ class PassiveSepEncCNN(_PackedModule):
         return p, keep
 
     def _grad_struct(self, device):
-        grads = [torch.empty_like(q, memory_format=torch.contiguous_format) for q in self._train_params()]
+        grads = self._alloc_grads()
         g = _EncGrads()
         for i in range(5):
             g.conv_w[i], g.bn_w[i], g.bn_b[i] = grads[i].data_ptr(), grads[5 + i].data_ptr(), grads[10 + i].data_ptr()
@@ -562,7 +571,7 @@ class PassiveSepDecCNN(_PackedModule):
         return p, keep
 
     def _grad_struct(self, device):
-        grads = [torch.empty_like(q, memory_format=torch.contiguous_format) for q in self._train_params()]
+        grads = self._alloc_grads()
         g = _DecGrads()
         for i in range(5):
             g.deconv_w[i], g.bn_w[i], g.bn_b[i] = grads[i].data_ptr(), grads[5 + i].data_ptr(), grads[10 + i].data_ptr()

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../move2hear_active_av_separation_b200/csrc/render_conv.cuh"
+#include "../../move2hear_active_av_separation_b200/csrc/render_conv24.cuh"
 #include "../../move2hear_active_av_separation_b200/csrc/render_stft.cuh"
 #include "../../move2hear_active_av_separation_b200/csrc/m2h_tables.h"
 
@@ -47,9 +48,10 @@ void m2h_emu_store(void* base, size_t idx, float v, bool f16) {
 }
 
 static M2hConvTables g_ct;
+static M2hConv24Tables g_c24;
 static M2hStftTables g_st;
 static bool g_ready = false;
-static void ensure() { if (!g_ready) { build_conv_tables(g_ct); build_stft_tables(g_st); g_ready = true; } }
+static void ensure() { if (!g_ready) { build_conv_tables(g_ct); build_conv24_tables(g_c24); build_stft_tables(g_st); g_ready = true; } }
 
 extern "C" int emu_rir_convolve(const int16_t* mono, const float* rir, const int32_t* rir_len,
                                 int B, int K, int N, int Lmax, int16_t* waves, int n_ctas) {
@@ -59,7 +61,16 @@ extern "C" int emu_rir_convolve(const int16_t* mono, const float* rir, const int
   ConvParams P;
   P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.waves = waves; P.scratch = scratch.data();
   P.n_items = B * K; P.N = N; P.Lmax = Lmax; P.mono_index = nullptr; P.rir_index = nullptr;
-  const bool vec = conv_can_vectorise(P);      // same dispatch rule as m2h_rir_convolve
+  const bool vec = conv_can_vectorise(P);      // same dispatch rules as m2h_rir_convolve
+  if (Lmax <= M2H_C24_MAX_TAPS) {              // F = 24576 kernel (render_conv24.cuh)
+    Conv24Smem* s24 = new Conv24Smem;
+    for (int cta = 0; cta < n_ctas; ++cta) {
+      if (vec) conv24_cta_body<true>(P, *s24, &g_c24, cta, n_ctas); else conv24_cta_body<false>(P, *s24, &g_c24, cta, n_ctas);
+    }
+    delete s24;
+    delete s;
+    return vec ? 3 : 2;
+  }
   for (int cta = 0; cta < n_ctas; ++cta) {
     if (vec) conv_cta_body<true>(P, *s, &g_ct, cta, n_ctas); else conv_cta_body<false>(P, *s, &g_ct, cta, n_ctas);
   }

@@ -89,8 +89,37 @@ GRAD_WORKER = textwrap.dedent("""
     w0 = [torch.zeros_like(net[0].weight) for _ in range(world)]
     dist.all_gather(w0, net[0].weight.data)
     same_init = bool(torch.equal(w0[0], w0[1]))
+    # arena mode: a module whose backward hands out views of the reducer's flat buffers (what separator_cnn does on CUDA)
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, mod, x, w):
+            ctx.mod, ctx.x = mod, x
+            return x @ w
+        @staticmethod
+        def backward(ctx, dy):
+            g = ctx.mod._grad_arena.grad_view(ctx.mod.w)
+            g.copy_(ctx.x.t() @ dy)
+            return None, None, g
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.randn(8, 4))
+        def _grad_struct(self, device=None):
+            pass
+        def forward(self, x):
+            return Fn.apply(self, x, self.w)
+    toy = Toy()
+    broadcast_module_state(toy)
+    red2 = GradientAllReducer(toy.parameters(), modules=toy)
+    torch.nn.functional.mse_loss(toy(x), y).backward()
+    in_place = toy.w.grad.data_ptr() == red2._arena[0].data_ptr() and red2._in_arena(0)
+    local = toy.w.grad.clone()
+    red2.finish()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    arena_ok = bool(in_place and torch.allclose(toy.w.grad, sum(gathered) / world, atol=1e-6) and toy.w.grad.data_ptr() == red2._arena[0].data_ptr())
     if rank == 0:
-        print(json.dumps({"ok": bool(ok), "same_init": same_init, "n_buckets": len(red.buckets)}))
+        print(json.dumps({"ok": bool(ok), "same_init": same_init, "n_buckets": len(red.buckets), "arena_ok": arena_ok}))
     dist.destroy_process_group()
 """) % ROOT
 
@@ -106,3 +135,4 @@ def test_two_rank_gloo_gradient_allreduce(tmp_path, overlap):
     import json
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert d["ok"] and d["same_init"] and d["n_buckets"] > 1
+    assert d["arena_ok"]            # gradients written into the flat arena are adopted by autograd and reduced in place
