@@ -61,8 +61,8 @@ M2H_DEV void c24_load_radix3(Conv24Smem& s, int tid, const M2hConv24Tables* M2H_
     const int n2 = tid + M2H_C24_THREADS * i;
     if (n2 < M2H_C24_SUB) {
       const float2 x0 = load(n2), x1 = load(n2 + M2H_C24_SUB);
-      const float2 a = make_float2(x0.x - 0.5f * x1.x, x0.y - 0.5f * x1.y);
-      const float2 b = make_float2(hs * x1.y, -hs * x1.x);            // -i (sqrt3/2) x1
+      const float2 a = c_add(x0, c_scale(x1, -0.5f));
+      const float2 b = c_scale(make_float2(x1.y, -x1.x), hs);          // -i (sqrt3/2) x1
       const float2 w1 = mul_tw32<false>(wt, i);                          // W_M^n2 (384 / 12288 = 1 / 32)
       const float2 w2 = c_mul(w1, w1);
       const int p = c24_pos(n2);
@@ -160,18 +160,19 @@ M2H_DEV void c24_inv_pass_c(Conv24Smem& s, int tid, int round, float2 (&u)[16]) 
 }
 
 // 2 X[f] = (Zm + conj Zp) - i w (Zm - conj Zp),  w = W_F^f,  Zp = Z[M - f]   (valid for every 0 < f < M, f = M/2 included)
+// (conjugations and rotations by +-i are operand modifiers of the packed adds: five FADD2 / FMUL2 / FFMA2 in all)
 M2H_DEV float2 c24_untangle(float2 zm, float2 zp, float2 w) {
-  const float2 sm = make_float2(zm.x + zp.x, zm.y - zp.y);
-  const float2 df = make_float2(zm.x - zp.x, zm.y + zp.y);
+  const float2 sm = c_add(zm, make_float2(zp.x, -zp.y));
+  const float2 df = c_add(zm, make_float2(-zp.x, zp.y));
   const float2 q = c_mul(w, df);
-  return make_float2(sm.x + q.y, sm.y - q.x);
+  return c_add(sm, make_float2(q.y, -q.x));
 }
 // 8 Z'[f] = (Ym + conj Yp) + i conj(w) (Ym - conj Yp)      (Y = 4 x the true product spectrum)
 M2H_DEV float2 c24_retangle(float2 ym, float2 yp, float2 w) {
-  const float2 sm = make_float2(ym.x + yp.x, ym.y - yp.y);
-  const float2 df = make_float2(ym.x - yp.x, ym.y + yp.y);
+  const float2 sm = c_add(ym, make_float2(yp.x, -yp.y));
+  const float2 df = c_add(ym, make_float2(-yp.x, yp.y));
   const float2 q = c_mulc(df, w);
-  return make_float2(sm.x - q.y, sm.y + q.x);
+  return c_add(sm, make_float2(-q.y, q.x));
 }
 
 // Spectrum step of a lane's row.  `zp(idx)` / `yp(idx)` fetch register idx of the PARTNER lane's v / y array.
@@ -236,8 +237,8 @@ M2H_DEV void c24_radix3_stage(Conv24Smem& s, int tid, const M2hConv24Tables* M2H
       const float2 b1 = c_mulc(s.buf[M2H_C24_SUBBUF + p], w1);
       const float2 b2 = c_mulc(s.buf[2 * M2H_C24_SUBBUF + p], c_mul(w1, w1));
       const float2 sm = c_add(b1, b2), df = c_sub(b1, b2);
-      const float2 c = make_float2(a0.x - 0.5f * sm.x, a0.y - 0.5f * sm.y);
-      const float2 d = make_float2(-hs * df.y, hs * df.x);           // i (sqrt3/2) (b1 - b2)
+      const float2 c = c_add(a0, c_scale(sm, -0.5f));
+      const float2 d = c_scale(make_float2(-df.y, df.x), hs);         // i (sqrt3/2) (b1 - b2)
       const float2 z0 = c_add(a0, sm), z1 = c_add(c, d), z2 = c_sub(c, d);
       uint32_t* w0 = reinterpret_cast<uint32_t*>(&s.buf[p]);
       uint32_t* wa = reinterpret_cast<uint32_t*>(&s.buf[M2H_C24_SUBBUF + p]);
