@@ -686,7 +686,14 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
     pol = Move2HearPassiveWoMemoryPolicy().to(dev).train()
     broadcast_module_state(pol)
     opt = torch.optim.Adam(pol.parameters(), lr=5e-4, eps=1e-5, fused=True)       # passive_trainer.py:194-195
-    red = GradientAllReducer(pol.parameters(), modules=pol) if world > 1 else None
+    red = None
+    if world > 1:
+        mode = os.environ.get("M2H_DDP_MODE", "after_backward")       # "overlap": hooked, on a side stream, CTA-limited communicator
+        if mode == "overlap":
+            from move2hear_active_av_separation_b200.distributed import make_reduction_group
+            red = GradientAllReducer(pol.parameters(), modules=pol, overlap=True, group=make_reduction_group(int(os.environ.get("M2H_DDP_CTAS", "8"))))
+        else:
+            red = GradientAllReducer(pol.parameters(), modules=pol)
     B = B_TRAIN
     mono, rir, ln, tc = d_mono[:B], d_rir[:B], d_len[:B], d_tc[:B]
 

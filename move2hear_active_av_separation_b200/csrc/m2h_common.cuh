@@ -29,6 +29,7 @@
   M2H_DEV float m2h_rintf(float v) { return nearbyintf(v); }
   M2H_DEV float m2h_ldg(const float* p) { return *p; }
   M2H_DEV float2 m2h_ldg2(const float2* p) { return *p; }
+  M2H_DEV float2 m2h_ldg2_nc(const float2* p) { return *p; }
   M2H_DEV uint32_t m2h_ldg_u32(const uint32_t* p) { return *p; }
   M2H_DEV int m2h_f2i_rn(float v) {           // cvt.rni.s32.f32: round half to even, saturate
     const float r = nearbyintf(v);
@@ -65,6 +66,8 @@
   M2H_DEV float m2h_rintf(float v) { return rintf(v); }
   M2H_DEV float m2h_ldg(const float* p) { return __ldg(p); }
   M2H_DEV float2 m2h_ldg2(const float2* p) { return __ldg(p); }
+  // plain (coherent) load: data written earlier in the SAME kernel by the same thread must not go through the read-only path
+  M2H_DEV float2 m2h_ldg2_nc(const float2* p) { return *p; }
   M2H_DEV uint32_t m2h_ldg_u32(const uint32_t* p) { return __ldg(p); }
   M2H_DEV int m2h_f2i_rn(float v) { return __float2int_rn(v); }
   M2H_DEV uint32_t m2h_funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }

@@ -94,8 +94,10 @@ m2h_istft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
   istft_cta_body(P, s, tab, blockIdx.x, gridDim.x);
 }
 
-template <bool F16>
-__global__ void __launch_bounds__(M2H_STFT_THREADS, M2H_STFT_CTAS_PER_SM)
+// CTAS = resident CTAs per SM the register allocation targets: 3 (80 registers, no spills) or 4 (64 registers, 72 bytes of
+// spills, 32 warps per SM); M2H_STFT_CTAS selects at run time (measured: see DESIGN.md 4.2)
+template <bool F16, int CTAS>
+__global__ void __launch_bounds__(M2H_STFT_THREADS, CTAS)
 m2h_stft_kernel(const StftParams P, const M2hStftTables* __restrict__ tab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
@@ -132,11 +134,13 @@ extern "C" int m2h_init(int device) {
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_istft_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem)));
-  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
-  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem)));
   // the driver's default carve-out (102 KB, ncu r1b) left room for ONE STFT CTA per SM: ask for the maximum
-  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_stft_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#define M2H_STFT_ATTR(K) \
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem))); \
+  M2H_CUDA_CHECK(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  M2H_STFT_ATTR((m2h_stft_kernel<false, 3>)) M2H_STFT_ATTR((m2h_stft_kernel<true, 3>))
+  M2H_STFT_ATTR((m2h_stft_kernel<false, 4>)) M2H_STFT_ATTR((m2h_stft_kernel<true, 4>))
+#undef M2H_STFT_ATTR
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaFuncSetAttribute(m2h_rir_conv_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   M2H_CUDA_CHECK(cudaSetDevice(prev));
@@ -294,15 +298,22 @@ extern "C" int m2h_clip_ingest(const void* raw_frames, int format, int channels,
 static int launch_stft(const StftParams& P, int dev, void* stream) {
   const int n_items = P.B * P.n_signals * ((P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS);      // (mixture, signal, M2H_STFT_GROUPS frames)
   if (n_items == 0) return M2H_OK;
-  int grid = M2H_STFT_CTAS_PER_SM * g_tables[dev].n_sms;
+  static int ctas = -1;
+  if (ctas < 0) { const char* e = getenv("M2H_STFT_CTAS"); ctas = (e && atoi(e) == 4) ? 4 : (e && atoi(e) == 3 ? 3 : M2H_STFT_CTAS_PER_SM); }
+  int grid = ctas * g_tables[dev].n_sms;
   if (grid > n_items) grid = n_items;
   // outputs are written as (left, right) pairs
   const void* outs[5] = {P.mix_mag, P.mix_phase, P.gt_mag, P.f_mag, P.f_phase};
   for (int i = 0; i < 5; ++i)
     if (((uintptr_t)outs[i] & 7) != 0) { m2h_set_error("stft: output buffers must be 8-byte aligned"); return M2H_ERR_ARG; }
   const M2hStftTables* tab = g_tables[dev].stft;
-  if (P.flags & M2H_OUT_F16) M2H_CUDA_CHECK(launch_pdl(m2h_stft_kernel<true>, grid, M2H_STFT_THREADS, sizeof(StftSmem), stream, P, tab));
-  else M2H_CUDA_CHECK(launch_pdl(m2h_stft_kernel<false>, grid, M2H_STFT_THREADS, sizeof(StftSmem), stream, P, tab));
+  if (ctas == 4) {
+    if (P.flags & M2H_OUT_F16) M2H_CUDA_CHECK(launch_pdl(m2h_stft_kernel<true, 4>, grid, M2H_STFT_THREADS, sizeof(StftSmem), stream, P, tab));
+    else M2H_CUDA_CHECK(launch_pdl(m2h_stft_kernel<false, 4>, grid, M2H_STFT_THREADS, sizeof(StftSmem), stream, P, tab));
+  } else {
+    if (P.flags & M2H_OUT_F16) M2H_CUDA_CHECK(launch_pdl(m2h_stft_kernel<true, 3>, grid, M2H_STFT_THREADS, sizeof(StftSmem), stream, P, tab));
+    else M2H_CUDA_CHECK(launch_pdl(m2h_stft_kernel<false, 3>, grid, M2H_STFT_THREADS, sizeof(StftSmem), stream, P, tab));
+  }
   return M2H_OK;
 }
 

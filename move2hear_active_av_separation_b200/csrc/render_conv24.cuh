@@ -46,10 +46,10 @@ struct M2hConv24Tables {
 struct Conv24Smem {
   float2 buf[3 * M2H_C24_SUBBUF];
   float2 t256[256];
+  float2 sp[3][16];            // the one self-paired row (sub 0, slab 0, q2 = 0): Z, Y and Z' parked for 16 helper lanes
 };
 
 M2H_DEV int c24_pos(int n2) { return (n2 >> 8) * M2H_C24_S1 + ((n2 >> 4) & 15) * M2H_C24_S2 + (n2 & 15); }
-M2H_DEV int c24_word_pos(int j) { return (j >> 12) * M2H_C24_SUBBUF + c24_pos(j & 4095); }
 
 // ---- radix-3 step on the loads --------------------------------------------------------------------------------------
 // LOAD(j) -> packed sample j (0 beyond the valid length).  u0 = x0 + x1, u1 = (x0 + w3 x1) W_M^n2, u2 = (x0 + w3^2 x1) W_M^(2 n2)
@@ -57,18 +57,28 @@ template <typename Load>
 M2H_DEV void c24_load_radix3(Conv24Smem& s, int tid, const M2hConv24Tables* M2H_RESTRICT t, Load load) {
   const float2 wt = m2h_ldg2(&t->m1[tid]);
   const float hs = 0.8660254037844386f;
-  M2H_UNROLL for (int i = 0; i < 11; ++i) {
-    const int n2 = tid + M2H_C24_THREADS * i;
-    if (n2 < M2H_C24_SUB) {
-      const float2 x0 = load(n2), x1 = load(n2 + M2H_C24_SUB);
-      const float2 a = c_add(x0, c_scale(x1, -0.5f));
-      const float2 b = c_scale(make_float2(x1.y, -x1.x), hs);          // -i (sqrt3/2) x1
-      const float2 w1 = mul_tw32<false>(wt, i);                          // W_M^n2 (384 / 12288 = 1 / 32)
-      const float2 w2 = c_mul(w1, w1);
-      const int p = c24_pos(n2);
-      s.buf[p] = c_add(x0, x1);
-      s.buf[M2H_C24_SUBBUF + p] = c_mul(c_add(a, b), w1);
-      s.buf[2 * M2H_C24_SUBBUF + p] = c_mul(c_sub(a, b), w2);
+  // every global load of the thread is issued before the first use (22 independent loads in flight: the step was bound by
+  // their latency when each iteration waited for its own pair - ncu r2e: 20 % of the kernel's samples, long scoreboard)
+  M2H_UNROLL for (int half = 0; half < 2; ++half) {          // two batches of 12 / 10 loads: all in flight, no spills at 80 registers
+    const int i0 = half * 6, cnt = half ? 5 : 6;
+    float2 x0[6], x1[6];
+    M2H_UNROLL for (int k = 0; k < 6; ++k) {
+      const int n2 = tid + M2H_C24_THREADS * (i0 + k);
+      x0[k] = make_float2(0.f, 0.f); x1[k] = make_float2(0.f, 0.f);
+      if (k < cnt && n2 < M2H_C24_SUB) { x0[k] = load(n2); x1[k] = load(n2 + M2H_C24_SUB); }
+    }
+    M2H_UNROLL for (int k = 0; k < 6; ++k) {
+      const int i = i0 + k, n2 = tid + M2H_C24_THREADS * i;
+      if (k < cnt && n2 < M2H_C24_SUB) {
+        const float2 a = c_add(x0[k], c_scale(x1[k], -0.5f));
+        const float2 b = c_scale(make_float2(x1[k].y, -x1[k].x), hs);   // -i (sqrt3/2) x1
+        const float2 w1 = mul_tw32<false>(wt, i);                          // W_M^n2 (384 / 12288 = 1 / 32)
+        const float2 w2 = c_mul(w1, w1);
+        const int p = c24_pos(n2);
+        s.buf[p] = c_add(x0[k], x1[k]);
+        s.buf[M2H_C24_SUBBUF + p] = c_mul(c_add(a, b), w1);
+        s.buf[2 * M2H_C24_SUBBUF + p] = c_mul(c_sub(a, b), w2);
+      }
     }
   }
 }
@@ -184,32 +194,44 @@ M2H_DEV void c24_spectrum_a(int tid, int round, const M2hConv24Tables* M2H_RESTR
   const float2 wU = m2h_ldg2(&t->g[R.k1 * 256 + R.q1 * 16 + (tid & 15)]);
   float2* gx = g + (size_t)round * 16 * M2H_C24_THREADS + tid;
   M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) {
-    const float2 zm = v[bitrev<4>(q3)];
     const float2 zo = zp(bitrev<4>(15 - q3));                      // every lane takes part in the exchange
-    const float2 zs = v[bitrev<4>((16 - q3) & 15)];                // the self-paired row's own partner element
-    const float2 zq = R.special ? zs : zo;
-    const float2 w = mul_tw32<false>(wU, q3);                        // W_F^(f0 + 768 q3)
-    float2 x2 = c24_untangle(zm, zq, w);
-    if (q3 == 0 && R.special) x2 = make_float2(2.f * (zm.x + zm.y), 2.f * (zm.x - zm.y));      // f = 0 | f = M: both real
-    if (MONO) gx[q3 * M2H_C24_THREADS] = x2;
-    else {
-      const float2 x = gx[q3 * M2H_C24_THREADS];
-      y[q3] = (q3 == 0 && R.special) ? make_float2(x.x * x2.x, x.y * x2.y) : c_mul(x, x2);
-    }
+    const float2 x2 = c24_untangle(v[bitrev<4>(q3)], zo, mul_tw32<false>(wU, q3));       // w = W_F^(f0 + 768 q3)
+    if (MONO) { if (!R.special) gx[q3 * M2H_C24_THREADS] = x2; }
+    else y[q3] = c_mul(y[q3], x2);                                   // y arrives holding 2 X[f] of the clip (c24_load_x)
   }
+}
+// The clip's spectrum row comes from the L2-resident scratch: issued BEFORE the row's own radix pass so that the ~300-cycle
+// L2 latency runs under the butterflies (ncu r2f: 12.7 % of the kernel's samples waited on these loads at the product)
+M2H_DEV void c24_load_x(int tid, int round, const float2* g, float2 (&y)[16]) {
+  const float2* gx = g + (size_t)round * 16 * M2H_C24_THREADS + tid;
+  M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) y[q3] = m2h_ldg2_nc(gx + q3 * M2H_C24_THREADS);
 }
 template <typename PartnerY>
 M2H_DEV void c24_spectrum_b(int tid, int round, const M2hConv24Tables* M2H_RESTRICT t, const float2 (&y)[16], float2 (&u)[16], PartnerY yp) {
   const C24Row R = c24_row(tid, round);
   const float2 wU = m2h_ldg2(&t->g[R.k1 * 256 + R.q1 * 16 + (tid & 15)]);
-  M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) {
-    const float2 yo = yp(15 - q3);
-    const float2 ys = y[(16 - q3) & 15];
-    const float2 yq = R.special ? ys : yo;
-    const float2 w = mul_tw32<false>(wU, q3);
-    u[q3] = c24_retangle(y[q3], yq, w);
-    if (q3 == 0 && R.special) u[0] = make_float2(y[0].x + y[0].y, y[0].x - y[0].y);
-  }
+  M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) u[q3] = c24_retangle(y[q3], yp(15 - q3), mul_tw32<false>(wU, q3));
+}
+// The self-paired row (held by lane 16 of the warp that owns unit 23) pairs element q3 with 16 - q3 of ITSELF, and its
+// f = 0 slot carries the real DC and Nyquist terms.  Doing that in the owning lane's registers costs every thread of the
+// kernel registers (the compiler keeps both variants live: 700 bytes of spills); instead the lane parks its row in shared
+// memory and lanes 0..15 of the same warp handle one element each (f = 768 q3, w = W_32^q3 = t256[8 * 16 + q3]).
+M2H_DEV bool c24_is_special_warp(int tid, int round) { return (tid >> 5) + 12 * round == 23; }
+M2H_DEV int c24_special_tid(int round) { return (23 - 12 * round) * 32 + 16; }
+template <bool MONO>
+M2H_DEV void c24_special_a(Conv24Smem& s, int tid, int round, float2* g) {      // lanes 0..15 of the special warp
+  const int q3 = tid & 31;
+  const float2 zm = s.sp[0][q3];
+  float2 x2 = c24_untangle(zm, s.sp[0][(16 - q3) & 15], s.t256[8 * 16 + q3]);
+  if (q3 == 0) x2 = make_float2(2.f * (zm.x + zm.y), 2.f * (zm.x - zm.y));             // f = 0 | f = M: both real
+  float2* gx = g + (size_t)round * 16 * M2H_C24_THREADS + q3 * M2H_C24_THREADS + c24_special_tid(round);
+  if (MONO) *gx = x2;
+  else { const float2 x = *gx; s.sp[1][q3] = q3 == 0 ? make_float2(x.x * x2.x, x.y * x2.y) : c_mul(x, x2); }
+}
+M2H_DEV void c24_special_b(Conv24Smem& s, int tid) {                                       // lanes 0..15 of the special warp
+  const int q3 = tid & 31;
+  const float2 y = s.sp[1][q3];
+  s.sp[2][q3] = q3 == 0 ? make_float2(y.x + y.y, y.x - y.y) : c24_retangle(y, s.sp[1][(16 - q3) & 15], s.t256[8 * 16 + q3]);
 }
 
 #ifdef M2H_HOST_EMU
@@ -224,12 +246,16 @@ M2H_DEV void c24_spectrum_b(int tid, int round, const M2hConv24Tables* M2H_RESTR
 M2H_DEV uint32_t c24_quantise_pair(float a, float b) {
   return ((uint32_t)m2h_f2i_rn(a) & 0xffffu) | ((uint32_t)m2h_f2i_rn(b) << 16);
 }
-M2H_DEV void c24_radix3_stage(Conv24Smem& s, int tid, const M2hConv24Tables* M2H_RESTRICT t, int j_lo, int j_hi) {
+// Phase 1 computes the thread's (up to) 33 output words; after a CTA barrier phase 2 stores them CONTIGUOUSLY over the
+// consumed transform buffer (word j of the packed result at stage[j]), so that the copy-out is plain coalesced reads.
+#define M2H_C24_NW 33
+M2H_DEV void c24_radix3_words(const Conv24Smem& s, int tid, const M2hConv24Tables* M2H_RESTRICT t, uint32_t (&w)[M2H_C24_NW]) {
   const float2 wt = m2h_ldg2(&t->m1[tid]);
   const float hs = 0.8660254037844386f;
   const float scale = 1.0f / (8.0f * (float)M2H_C24_M);              // 1/M inverse scale, 2*2*2 from the untangle / re-tangle steps
   M2H_UNROLL for (int i = 0; i < 11; ++i) {
     const int n2 = tid + M2H_C24_THREADS * i;
+    w[3 * i] = w[3 * i + 1] = w[3 * i + 2] = 0u;
     if (n2 < M2H_C24_SUB) {
       const int p = c24_pos(n2);
       const float2 a0 = s.buf[p];
@@ -239,32 +265,31 @@ M2H_DEV void c24_radix3_stage(Conv24Smem& s, int tid, const M2hConv24Tables* M2H
       const float2 sm = c_add(b1, b2), df = c_sub(b1, b2);
       const float2 c = c_add(a0, c_scale(sm, -0.5f));
       const float2 d = c_scale(make_float2(-df.y, df.x), hs);         // i (sqrt3/2) (b1 - b2)
-      const float2 z0 = c_add(a0, sm), z1 = c_add(c, d), z2 = c_sub(c, d);
-      uint32_t* w0 = reinterpret_cast<uint32_t*>(&s.buf[p]);
-      uint32_t* wa = reinterpret_cast<uint32_t*>(&s.buf[M2H_C24_SUBBUF + p]);
-      uint32_t* wb = reinterpret_cast<uint32_t*>(&s.buf[2 * M2H_C24_SUBBUF + p]);
-      if (n2 >= j_lo && n2 <= j_hi) *w0 = c24_quantise_pair(z0.x * scale, z0.y * scale);
-      if (n2 + M2H_C24_SUB >= j_lo && n2 + M2H_C24_SUB <= j_hi) *wa = c24_quantise_pair(z1.x * scale, z1.y * scale);
-      if (n2 + 2 * M2H_C24_SUB >= j_lo && n2 + 2 * M2H_C24_SUB <= j_hi) *wb = c24_quantise_pair(z2.x * scale, z2.y * scale);
+      const float2 z0 = c_scale(c_add(a0, sm), scale), z1 = c_scale(c_add(c, d), scale), z2 = c_scale(c_sub(c, d), scale);
+      w[3 * i] = c24_quantise_pair(z0.x, z0.y);
+      w[3 * i + 1] = c24_quantise_pair(z1.x, z1.y);
+      w[3 * i + 2] = c24_quantise_pair(z2.x, z2.y);
     }
   }
 }
-M2H_DEV uint32_t c24_word(const Conv24Smem& s, int j) { return *reinterpret_cast<const uint32_t*>(&s.buf[c24_word_pos(j)]); }
+M2H_DEV void c24_store_words(Conv24Smem& s, int tid, const uint32_t (&w)[M2H_C24_NW]) {
+  uint32_t* stage = reinterpret_cast<uint32_t*>(s.buf);
+  M2H_UNROLL for (int i = 0; i < 11; ++i) {
+    const int n2 = tid + M2H_C24_THREADS * i;
+    if (n2 < M2H_C24_SUB) { stage[n2] = w[3 * i]; stage[n2 + M2H_C24_SUB] = w[3 * i + 1]; stage[n2 + 2 * M2H_C24_SUB] = w[3 * i + 2]; }
+  }
+}
 template <bool VEC>
 M2H_DEV void c24_copy_out(const Conv24Smem& s, int tid, int16_t* out, int N, int c_off) {
+  const uint32_t* stage = reinterpret_cast<const uint32_t*>(s.buf);
   if (VEC) {
     uint32_t* o = (uint32_t*)out;
-    const int sh = (c_off & 1) * 16;
-    for (int w = tid; w < (N >> 1); w += M2H_C24_THREADS) {
-      const int k = (2 * w + c_off) >> 1;
-      const uint32_t lo = c24_word(s, k);
-      const uint32_t hi = sh ? c24_word(s, k + 1) : 0u;
-      o[w] = m2h_funnel_r(lo, hi, sh);
-    }
+    const int sh = (c_off & 1) * 16, k0 = c_off >> 1;
+    for (int w = tid; w < (N >> 1); w += M2H_C24_THREADS) o[w] = m2h_funnel_r(stage[k0 + w], stage[k0 + w + 1], sh);
   } else {
     for (int m = tid; m < N; m += M2H_C24_THREADS) {
       const int q = m + c_off;
-      const uint32_t w = c24_word(s, q >> 1);
+      const uint32_t w = stage[q >> 1];
       out[m] = (int16_t)(uint16_t)((q & 1) ? (w >> 16) : (w & 0xffffu));
     }
   }
@@ -283,28 +308,51 @@ M2H_DEV void c24_transform(Conv24Smem& s, const M2hConv24Tables* M2H_RESTRICT t,
     M2H_SYNC_WARP();
 #ifdef M2H_HOST_EMU
     M2H_C24_REGS_DECL;
+    const int sp_tid = c24_special_tid(round), sp_w0 = sp_tid - 16;
+    if (!MONO) { M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_load_x(tid, round, g, c24_y[tid]); }
     M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_fwd_pass_c(s, tid, round, c24_v[tid]);
+    if (round == 1) for (int q3 = 0; q3 < 16; ++q3) s.sp[0][q3] = c24_v[sp_tid][bitrev<4>(q3)];
     M2H_FOR_THREADS(tid, M2H_C24_THREADS) {
       const int pt = (tid & ~31) | c24_row(tid, round).partner;
       c24_spectrum_a<MONO>(tid, round, t, g, c24_v[tid], c24_y[tid], [&](int idx) { return c24_v[pt][idx]; });
     }
+    if (round == 1) for (int l = 0; l < 16; ++l) c24_special_a<MONO>(s, sp_w0 + l, round, g);
     if (!MONO) {
+      if (round == 1) for (int q3 = 0; q3 < 16; ++q3) c24_y[sp_tid][q3] = s.sp[1][q3];
       M2H_FOR_THREADS(tid, M2H_C24_THREADS) {
         const int pt = (tid & ~31) | c24_row(tid, round).partner;
         c24_spectrum_b(tid, round, t, c24_y[tid], c24_u[tid], [&](int idx) { return c24_y[pt][idx]; });
+      }
+      if (round == 1) {
+        for (int l = 0; l < 16; ++l) c24_special_b(s, sp_w0 + l);
+        for (int q3 = 0; q3 < 16; ++q3) c24_u[sp_tid][q3] = s.sp[2][q3];
       }
       M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_inv_pass_c(s, tid, round, c24_u[tid]);
       M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_inv_pass_b(s, tid, round);
     }
 #else
     {
-      const int tid = threadIdx.x;
+      const int tid = threadIdx.x, lane = tid & 31;
       const int partner = c24_row(tid, round).partner;
+      const bool spw = c24_is_special_warp(tid, round);              // warp-uniform
       float2 v[16], y[16];
+      if (!MONO) c24_load_x(tid, round, g, y);
       c24_fwd_pass_c(s, tid, round, v);
+      if (spw && lane == 16) { M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) s.sp[0][q3] = v[bitrev<4>(q3)]; }
       c24_spectrum_a<MONO>(tid, round, t, g, v, y, [&](int idx) { return c24_shfl(v[idx], partner); });
+      if (spw) {
+        M2H_SYNC_WARP();
+        if (lane < 16) c24_special_a<MONO>(s, tid, round, g);
+        M2H_SYNC_WARP();
+        if (!MONO && lane == 16) { M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) y[q3] = s.sp[1][q3]; }
+      }
       if (!MONO) {
         c24_spectrum_b(tid, round, t, y, v, [&](int idx) { return c24_shfl(y[idx], partner); });
+        if (spw) {
+          if (lane < 16) c24_special_b(s, tid);
+          M2H_SYNC_WARP();
+          if (lane == 16) { M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) v[q3] = s.sp[2][q3]; }
+        }
         c24_inv_pass_c(s, tid, round, v);
         M2H_SYNC_WARP();
         c24_inv_pass_b(s, tid, round);
@@ -317,6 +365,11 @@ M2H_DEV void c24_transform(Conv24Smem& s, const M2hConv24Tables* M2H_RESTRICT t,
     M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_inv_pass_a(s, tid, t);
   }
   M2H_SYNC();
+}
+
+// L2 prefetch of a row that the NEXT transform will load (one 128-byte line per thread and step)
+M2H_DEV void c24_prefetch_row(int tid, const void* row, int bytes) {
+  for (int o = tid * 128; o < bytes; o += M2H_C24_THREADS * 128) m2h_prefetch_l2((const char*)row + o);
 }
 
 // The whole per-CTA loop (same ConvParams as render_conv.cuh).  Requires P.Lmax <= 16384 and P.N <= 16384.
@@ -345,6 +398,7 @@ M2H_DEV void conv24_cta_body(const ConvParams& P, Conv24Smem& s, const M2hConv24
       continue;
     }
     const int16_t* x = P.mono + (size_t)mi * N;
+    M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_prefetch_row(tid, P.rir + (size_t)ri * 2 * P.Lmax + jmin, Leff * 4);      // ear 0, loaded one transform from now
     c24_transform<true>(s, gtab, g, [&](int tid, int j) {
       float a = 0.f, b = 0.f;
       if (VEC) {
@@ -358,9 +412,13 @@ M2H_DEV void conv24_cta_body(const ConvParams& P, Conv24Smem& s, const M2hConv24
       }
       return make_float2(a, b);
     });
-    const int j_lo = c_off >> 1, j_hi = (c_off + N - 1) >> 1;
     for (int ear = 0; ear < 2; ++ear) {
       const float* h = P.rir + ((size_t)ri * 2 + ear) * P.Lmax + jmin;
+      M2H_FOR_THREADS(tid, M2H_C24_THREADS) {          // rows the next transform will load: the other ear, or the next item's clip
+        if (ear == 0) c24_prefetch_row(tid, h + P.Lmax, Leff * 4);
+        else if (item + n_ctas < P.n_items)
+          c24_prefetch_row(tid, P.mono + (size_t)(P.mono_index ? P.mono_index[item + n_ctas] : item + n_ctas) * N, N * 2);
+      }
       c24_transform<false>(s, gtab, g, [&](int tid, int j) {
         float2 a = make_float2(0.f, 0.f);
         if (VEC) {
@@ -372,7 +430,18 @@ M2H_DEV void conv24_cta_body(const ConvParams& P, Conv24Smem& s, const M2hConv24
         }
         return a;
       });
-      M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_radix3_stage(s, tid, gtab, j_lo, j_hi);
+#ifdef M2H_HOST_EMU
+      static uint32_t c24_w[M2H_C24_THREADS][M2H_C24_NW];
+      M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_radix3_words(s, tid, gtab, c24_w[tid]);
+      M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_store_words(s, tid, c24_w[tid]);
+#else
+      {
+        uint32_t w[M2H_C24_NW];
+        c24_radix3_words(s, threadIdx.x, gtab, w);
+        M2H_SYNC();                       // every thread has read its triples: the buffer may be overwritten
+        c24_store_words(s, threadIdx.x, w);
+      }
+#endif
       M2H_SYNC();
       M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_copy_out<VEC>(s, tid, P.waves + ((size_t)item * 2 + ear) * N, N, c_off);
       M2H_SYNC();

@@ -144,6 +144,20 @@ class GradientAllReducer:
         self._hooks = []
 
 
+def make_reduction_group(max_ctas: int = 8):
+    """A dedicated NCCL communicator for the gradient all-reduce whose kernels use at most ``max_ctas`` CTAs
+    (``ncclConfig_t.maxCTAs``).  The backward kernels of this path are persistent and fill every SM; an all-reduce launched
+    next to them with NCCL's default CTA count is scheduled piecemeal and every rank waits for the slowest (measured in round 1:
+    the hooked overlap was slower than reducing after backward).  A small CTA budget lets the collective run in the gaps:
+    NVLink 5 needs only a few CTAs to saturate (NVLS reduces inside the switch)."""
+    if not dist.is_initialized() or dist.get_backend() != "nccl":
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(max_ctas)
+    opts.config.min_ctas = 1
+    return dist.new_group(backend="nccl", pg_options=opts)
+
+
 def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None):
     """Parameters and buffers (BatchNorm running statistics) follow rank ``src``, as DDP does at construction / each forward."""
     if not dist.is_initialized() or dist.get_world_size(group) <= 1:
