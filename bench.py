@@ -37,7 +37,7 @@ BYTES_CONV = 2 * K_SRC * N_SAMPLES + 8 * K_SRC * L_TAPS + 2 * K_SRC * 2 * N_SAMP
 BYTES_STFT = 2 * K_SRC * 2 * N_SAMPLES + 4 * 512 * 32 * 2                                   # int16 waves in, fp32 log-mag out
 BYTES_RENDER = 2 * K_SRC * N_SAMPLES + 8 * K_SRC * L_TAPS + 4 * 512 * 32 * 2                # 451,072 B
 FLOPS_UNET = 220.7e6                                                                         # binSep fwd, nominal 2*MACs
-# kernels of this library launched per timed step: m2h_rir_conv_kernel, m2h_stft_kernel, pack_input_kernel,
+# kernels of this library launched per timed step: m2h_rir_conv24_kernel, m2h_stft_kernel, pack_input_kernel,
 # 3 x unet_slab_kernel (enc0, dec3, dec4 + head), 7 x unet_gemm_tma_kernel (enc1-4, dec0-2), bf16_to_f32_kernel (bottleneck)
 OUR_LAUNCHES_PER_STEP = 14
 
@@ -620,7 +620,7 @@ def run_ours(args):
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("m2h_rir_conv_kernel", {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get("m2h_rir_conv24_kernel", {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     line = {
@@ -628,10 +628,11 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (render) / bf16 operands + f32 accumulate (U-Net)", "data": "synthetic",
         "config": workload_config({"global_batch": world * B, "parallelism": f"shard-by-mixture x{world}, no data-path collective"}),
-        "roofline": {"kernel": "m2h_rir_conv_kernel", "bound": "hbm", "achieved": conv_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "roofline": {"kernel": "m2h_rir_conv24_kernel", "bound": "hbm", "achieved": conv_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": conv_gbs / pk["hbm_gbs"], "traffic": traffic, "peak_src": pk["src"],
                      "algorithmic_bytes_per_launch": BYTES_CONV * B, "ms_per_launch": t_conv,
-                     "note": "fp32 FFT arithmetic (11.5 MFLOP per mixture, issue-bound on the FP32 pipe), not HBM, bounds this kernel: see DESIGN.md section 4"},
+                     "note": "an fp32-exact FFT convolution is bound on-chip, not by HBM: ncu (profiles/r2) shows the shared-memory / L1 data pipe 62 % "
+                             "and the FP32 pipe 53 % busy, DRAM 15 %; see DESIGN.md section 4.1b"},
         "roofline_other": [
             {"kernel": "m2h_stft_kernel", "bound": "hbm", "achieved": BYTES_STFT * B / (t_stft * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
              "frac": BYTES_STFT * B / (t_stft * 1e-3) / 1e9 / pk["hbm_gbs"], "ms_per_launch": t_stft},
@@ -639,15 +640,15 @@ def run_ours(args):
              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": BYTES_RENDER * B / ((t_conv + t_stft) * 1e-3) / 1e9 / pk["hbm_gbs"], "ms": t_conv + t_stft},
             {"kernel": "U-Net forward: 3 unet_slab_kernel + 7 unet_gemm_tma_kernel + pack_input_kernel", "bound": "tensor", "achieved": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
              "unit": "TFLOP/s", "frac": FLOPS_UNET * B / (t_unet * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], "ms": t_unet},
-            # informational: both render kernels are bound by FP32 instruction issue, not by HBM.  Warp
-            # instructions per launch are the ncu counts of this workload (profiles/r1g/ncu_full_summary.json, B = 1024 per GPU);
-            # peak = 4 schedulers x 148 SMs x the sampled SM clock, one warp instruction per scheduler and cycle.
-            {"kernel": "m2h_rir_conv_kernel (informational)", "bound": "fp32-issue", "achieved": 391.05e6 * B / 1024 / (t_conv * 1e-3) / 1e9,
-             "peak": 4 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G warp-instr/s",
-             "frac": 391.05e6 * B / 1024 / (t_conv * 1e-3) / 1e9 / (4 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3)},
-            {"kernel": "m2h_stft_kernel (informational)", "bound": "fp32-issue", "achieved": 336.09e6 * B / 1024 / (t_stft * 1e-3) / 1e9,
-             "peak": 4 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G warp-instr/s",
-             "frac": 336.09e6 * B / 1024 / (t_stft * 1e-3) / 1e9 / (4 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3)},
+            # informational: what actually bounds the render kernels on the SM: shared-memory wavefronts per
+            # launch are the ncu counts of this workload (profiles/r2/ncu_render_summary.json, B = 1024 per GPU); peak = one
+            # 128-byte wavefront per SM and clock at the sampled SM clock.
+            {"kernel": "m2h_rir_conv24_kernel (informational)", "bound": "shared-memory data pipe", "achieved": 70.01e6 * B / 1024 / (t_conv * 1e-3) / 1e9,
+             "peak": 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G wavefronts/s",
+             "frac": 70.01e6 * B / 1024 / (t_conv * 1e-3) / 1e9 / (148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3)},
+            {"kernel": "m2h_stft_kernel (informational)", "bound": "shared-memory data pipe", "achieved": 50.51e6 * B / 1024 / (t_stft * 1e-3) / 1e9,
+             "peak": 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G wavefronts/s",
+             "frac": 50.51e6 * B / 1024 / (t_stft * 1e-3) / 1e9 / (148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e-3)},
         ],
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -685,7 +686,7 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
     torch.manual_seed(1234)
     pol = Move2HearPassiveWoMemoryPolicy().to(dev).train()
     broadcast_module_state(pol)
-    opt = torch.optim.Adam(pol.parameters(), lr=5e-4, eps=1e-5, fused=True)       # passive_trainer.py:194-195
+    opt = torch.optim.Adam(pol.parameters(), lr=5e-4, eps=1e-5, fused=True, capturable=True)       # passive_trainer.py:194-195
     red = None
     if world > 1:
         mode = os.environ.get("M2H_DDP_MODE", "after_backward")       # "overlap": hooked, on a side stream, CTA-limited communicator
@@ -701,26 +702,47 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
         out = rend.render(mono, rir, ln, n_gt=1)                                   # dataset path: fp32 log-mag mixture + target GT magnitude
         mixed, gt_bin = out["mix_mag"], out["gt"][:, 0]
         gt_mono, _ = rend.stft_f32((mono[:, :1].float() * (1.0 / 32768)).contiguous())      # monaural GT magnitude [B,512,T,1]
-        return train_step(pol, opt, mixed, gt_bin, gt_mono, tc, grad_sync=red.finish if red else None)
+        b_, m_ = train_step(pol, opt, mixed, gt_bin, gt_mono, tc, grad_sync=red.finish if red else None)
+        return b_.detach(), m_.detach()          # keep no autograd graph alive between steps
+
+    def timed(fn, steps):
+        barrier()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        marks[0].record(stream)
+        for i in range(steps):
+            out = fn()
+            marks[i + 1].record(stream)
+        barrier()
+        per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+        return out, marks[0].elapsed_time(marks[-1]), per
 
     losses = []
     for _ in range(3):
         b, m = step()
     losses.append((float(b.detach()), float(m.detach())))
     steps = max(5, args.steps // 2)
-    barrier()
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    marks[0].record(stream)
-    for i in range(steps):
-        b, m = step()
-        marks[i + 1].record(stream)
-    barrier()
+    (b, m), ms_eager, per_eager = timed(step, steps)
+    # the same step replayed from ONE CUDA graph (pretrain.GraphedTrainStep): the eager step is host-bound (tools/train_hostbound.py)
+    mode, ms_total, per_step = "eager", ms_eager, per_eager
+    graph_err = None
+    if not os.environ.get("M2H_TRAIN_EAGER"):
+        try:
+            from move2hear_active_av_separation_b200.pretrain import GraphedTrainStep
+            gstep = GraphedTrainStep(pol, opt, B, dev, renderer=rend, n_sources=K_SRC, n_samples=N_SAMPLES, rir_taps=L_TAPS,
+                                     grad_sync=red.finish if red else None)
+            for _ in range(3):
+                gstep(mono, rir, ln, target_class=tc)
+            (b, m), ms_total, per_step = timed(lambda: gstep(mono, rir, ln, target_class=tc), steps)
+            mode = "cuda_graph"
+        except Exception as e:       # e.g. a collective that cannot be captured on this NCCL: keep the eager number
+            graph_err = repr(e)[:300]
+            torch.cuda.synchronize(dev)
     losses.append((float(b.detach()), float(m.detach())))
-    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
     info = {"workload": "configs[2] pretraining step: render (dataset path) + binSep & bin2mono U-Nets fwd/bwd (train-mode BN) + L1 losses + fused Adam",
             "batch_per_gpu": B, "steps": steps, "unit": "mixtures/s", "grad_allreduce": "NCCL AVG in place on the flat gradient arena the wgrad kernels write (32 MB fp32 buckets, no pack / un-pack), after backward on the compute stream" if world > 1 else "none (1 GPU)",
-            "bin_mono_loss_first_last": losses, "ms_per_step_median_this_rank": per_step[len(per_step) // 2], "ms_per_step_max_this_rank": per_step[-1]}
-    return info, marks[0].elapsed_time(marks[-1])
+            "bin_mono_loss_first_last": losses, "ms_per_step_median_this_rank": per_step[len(per_step) // 2], "ms_per_step_max_this_rank": per_step[-1],
+            "mode": mode, "ms_per_step_eager_this_rank": ms_eager / steps, "graph_capture_error": graph_err}
+    return info, ms_total
 
 
 def main():

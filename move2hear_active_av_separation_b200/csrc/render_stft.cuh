@@ -93,54 +93,28 @@ M2H_DEV float2 stft_sample(const StftParams& P, int b, int sig, int i) {
 }
 
 struct StftI16x8 { uint32_t w[4]; };
-M2H_DEV void stft_acc8v(int (&acc)[8], const StftI16x8& q) {
+M2H_DEV void stft_acc8(int (&acc)[8], const int16_t* p) {
+  const StftI16x8 q = *reinterpret_cast<const StftI16x8*>(p);       // 16-byte aligned by construction
   M2H_UNROLL for (int u = 0; u < 4; ++u) {
     acc[2 * u] += (int)(int16_t)(q.w[u] & 0xffffu);
     acc[2 * u + 1] += (int)(int16_t)(q.w[u] >> 16);
   }
 }
-M2H_DEV void stft_acc8(int (&acc)[8], const int16_t* p) {
-  stft_acc8v(acc, *reinterpret_cast<const StftI16x8*>(p));       // 16-byte aligned by construction
-}
-// The first two sources' vectors of a thread's NEXT window, loaded into registers while the current frame's results are
-// being written out (P6 needs few registers): the staging that follows then finds its data instead of waiting for L2 / HBM
-// (ncu r2e: 11 % of the kernel's samples sat on the staging loads).  `n` = number of sources preloaded (0 = nothing).
-struct StftPre { StftI16x8 q[4]; int n; };
-M2H_DEV bool stft_vector_rows(const StftParams& P) { return P.waves && (P.N & 7) == 0 && ((uintptr_t)P.waves & 15) == 0; }
-M2H_DEV void stft_preload(const StftParams& P, int tid, int b, int sig, int t0, StftPre& pre) {
-  pre.n = 0;
-  const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
-  if (!stft_vector_rows(P) || t >= P.T) return;
-  const int i = M2H_HOP * t - M2H_HOP + 8 * lt;
-  if (i < 0 || i >= P.N) return;
-  const int16_t* w = P.waves + (size_t)b * P.K * 2 * P.N + i;
-  const int k_lo = sig == 0 ? 0 : sig - 1, k_hi = sig == 0 ? P.K : sig;
-  pre.n = k_hi - k_lo < 2 ? k_hi - k_lo : 2;
-  M2H_UNROLL for (int j = 0; j < 2; ++j) {
-    if (j < pre.n) {
-      pre.q[2 * j] = *reinterpret_cast<const StftI16x8*>(w + (size_t)(2 * (k_lo + j)) * P.N);
-      pre.q[2 * j + 1] = *reinterpret_cast<const StftI16x8*>(w + (size_t)(2 * (k_lo + j) + 1) * P.N);
-    }
-  }
-}
 // P0: each 128-thread group stages the 1024-sample window of its own frame (the mixture is formed here, in exactly the
 // reference's fp32 arithmetic).  Rows that allow it are read as 8 x int16 vectors: one vector per thread and row.
-M2H_DEV void stft_stage(const StftParams& P, StftSmem& s, int tid, int b, int sig, int t0, const StftPre& pre) {
+M2H_DEV void stft_stage(const StftParams& P, StftSmem& s, int tid, int b, int sig, int t0) {
   const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
   if (t >= P.T) return;
   const int i0 = M2H_HOP * t - M2H_HOP;
   float2* st = s.buf[grp];
-  if (stft_vector_rows(P)) {
+  if (P.waves && (P.N & 7) == 0 && ((uintptr_t)P.waves & 15) == 0) {
     const int i = i0 + 8 * lt;
     if (i >= 0 && i < P.N) {
       const int16_t* w = P.waves + (size_t)b * P.K * 2 * P.N + i;
       int al[8], ar[8];
       M2H_UNROLL for (int u = 0; u < 8; ++u) { al[u] = 0; ar[u] = 0; }
       const int k_lo = sig == 0 ? 0 : sig - 1, k_hi = sig == 0 ? P.K : sig;
-      M2H_UNROLL for (int j = 0; j < 2; ++j) {
-        if (j < pre.n) { stft_acc8v(al, pre.q[2 * j]); stft_acc8v(ar, pre.q[2 * j + 1]); }
-      }
-      for (int k = k_lo + pre.n; k < k_hi; ++k) {
+      for (int k = k_lo; k < k_hi; ++k) {
         stft_acc8(al, w + (size_t)(2 * k) * P.N);
         stft_acc8(ar, w + (size_t)(2 * k + 1) * P.N);
       }
@@ -308,24 +282,6 @@ template <bool F16>
 M2H_DEV void stft_p6(const StftParams& P, StftSmem& s, int tid, int b, int sig, int t0) {
   const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
   if (t >= P.T) return;
-  if (P.waves && sig == 0 && P.mix_mag && !P.mix_phase) {
-    // the hot case (mixture magnitude only: every training / rollout observation): all mode branches and the 64-bit index
-    // arithmetic of stft_emit hoisted out of the bin loop
-    const bool lg = (P.flags & M2H_OUT_MIX_LOG1P) != 0;
-    const size_t o0 = ((size_t)b * M2H_NBINS * P.T + t) * 2, stride = (size_t)P.T * 2;
-    M2H_UNROLL for (int j = 0; j < M2H_NBINS / 128; ++j) {
-      const int k = lt + 128 * j;
-      const float2 a = s.buf[grp][stft_pos(k)];
-      const float2 c = s.buf[grp][stft_pos(k == 0 ? 0 : M2H_NFFT - k)];
-      float ml = stft_abs<F16>(make_float2(a.x + c.x, a.y - c.y)), mr = stft_abs<F16>(make_float2(a.y + c.y, c.x - a.x));
-      if (lg) {
-        ml = F16 ? stft_log1p_f16(ml) : stft_log1p_fast(ml);
-        mr = F16 ? stft_log1p_f16(mr) : stft_log1p_fast(mr);
-      }
-      stft_store2<F16>(P.mix_mag, o0 + (size_t)k * stride, ml, mr);
-    }
-    return;
-  }
   for (int k = lt; k < M2H_NBINS; k += 128) {
     const float2 a = s.buf[grp][stft_pos(k)];
     const float2 c = s.buf[grp][stft_pos(k == 0 ? 0 : M2H_NFFT - k)];
@@ -345,22 +301,13 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
   // work item = (mixture, signal, M2H_STFT_GROUPS frames): small batches (the 14 environments of a rollout rank) still fill the GPU
   const int n_fgroups = (P.T + M2H_STFT_GROUPS - 1) / M2H_STFT_GROUPS;
   const int n_items = P.B * P.n_signals * n_fgroups;
-#ifdef M2H_HOST_EMU
-  static StftPre pre_all[M2H_STFT_THREADS];
-  for (int i = 0; i < M2H_STFT_THREADS; ++i) pre_all[i].n = 0;
-  #define M2H_STFT_PRE(tid) pre_all[tid]
-#else
-  StftPre pre_reg;
-  pre_reg.n = 0;
-  #define M2H_STFT_PRE(tid) pre_reg
-#endif
   for (int item = cta; item < n_items; item += n_ctas) {
     const int bs = item / n_fgroups, t0 = (item - bs * n_fgroups) * M2H_STFT_GROUPS;
     const int b = bs / P.n_signals, sig = bs - b * P.n_signals;
     {
       // each 128-thread group owns one frame pair and its buffer: only the group meets between the passes, the four
       // groups of a CTA drift apart freely
-      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_stage(P, s, tid, b, sig, t0, M2H_STFT_PRE(tid));
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_stage(P, s, tid, b, sig, t0);
       M2H_SYNC_GROUP128();
 #ifdef M2H_HOST_EMU
       static float2 vs[M2H_STFT_THREADS][16];
@@ -383,15 +330,7 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
       M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p5(P, s, gt, tid, t0);
       M2H_SYNC_GROUP128();
-      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) {
-        const int nxt = item + n_ctas;
-        M2H_STFT_PRE(tid).n = 0;
-        if (nxt < n_items) {      // the next window's loads fly under this frame's epilogue
-          const int nbs = nxt / n_fgroups, nt0 = (nxt - nbs * n_fgroups) * M2H_STFT_GROUPS;
-          stft_preload(P, tid, nbs / P.n_signals, nbs % P.n_signals, nt0, M2H_STFT_PRE(tid));
-        }
-        stft_p6<F16>(P, s, tid, b, sig, t0);
-      }
+      M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p6<F16>(P, s, tid, b, sig, t0);
       M2H_SYNC_GROUP128();      // the next window is staged into the buffer P6 reads
     }
   }

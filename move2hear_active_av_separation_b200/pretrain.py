@@ -41,3 +41,99 @@ def train_step(actor_critic, optimizer, mixed_audio, gt_bin_mag, gt_mono_mag, ta
     bin_loss, mono_loss, _ = optimize_supervised_loss(optimizer, mixed_audio, pred_binSepMasks, gt_bin_mag, pred_mono, gt_mono_mag,
                                                       split="train", grad_sync=grad_sync)
     return bin_loss, mono_loss
+
+
+class GraphedTrainStep:
+    """One pretraining iteration - (optionally the dataset-path render,) both separators forward with batch statistics, the two
+    L1 losses, backward, (the data-parallel gradient all-reduce,) the optimizer update - captured ONCE into a CUDA graph and
+    replayed per step.
+
+    Why: at the reference's batch sizes the step is ~230 short kernels and the Python / launch path that enqueues them takes
+    as long as the GPU needs to run them (B = 256 on a B200: 3.7 ms of host time for ~3 ms of GPU time per step, measured with
+    ``tools/train_hostbound.py``): the step is host-bound.  Replaying a graph removes the host from the loop; the graph holds
+    exactly the kernels of the eager path (CUDA streams and graphs, not a tracing compiler).
+
+    ``optimizer`` must be capturable (``torch.optim.Adam(..., fused=True, capturable=True)``).  Inputs are copied into static
+    buffers; the returned losses are static device tensors overwritten by the next call.  Drop every reference to the autograd
+    graph of earlier EAGER steps first (e.g. loss tensors with a ``grad_fn``): their ``AccumulateGrad`` nodes are bound to the
+    stream they ran on and invalidate the capture.  Capturing needs a few eager warm-up
+    steps (lazy workspaces, optimizer state): parameters, buffers and optimizer state are restored IN PLACE afterwards, so
+    the first replay is the first training step.
+    """
+
+    def __init__(self, actor_critic, optimizer, batch_size: int, device, renderer=None, n_sources: int = 2, n_samples: int = 16000,
+                 rir_taps: int = 16000, grad_sync=None, warmup: int = 3):
+        import torch
+        from . import _lib
+        if not torch.cuda.is_available():
+            raise _lib.M2HError("no CUDA device: the B200 path has no CPU fallback")
+        if not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise _lib.M2HError("GraphedTrainStep needs a capturable optimizer: torch.optim.Adam(..., fused=True, capturable=True)")
+        self.device = torch.device(device)
+        dev, B = self.device, batch_size
+        self.actor_critic, self.optimizer, self.rend, self.grad_sync = actor_critic, optimizer, renderer, grad_sync
+        if renderer is not None:          # render inside the graph: the dataset item's inputs are the static buffers
+            self.mono = torch.zeros((B, n_sources, n_samples), dtype=torch.int16, device=dev)
+            self.rir = torch.zeros((B, n_sources, 2, rir_taps + (rir_taps & 1)), dtype=torch.float32, device=dev)
+            self.rir_len = torch.zeros((B, n_sources), dtype=torch.int32, device=dev)
+            self.static = (self.mono, self.rir, self.rir_len)
+        else:
+            T = 1 + (n_samples - 1) // 512
+            self.mixed_audio = torch.zeros((B, 512, T, 2), dtype=torch.float32, device=dev)
+            self.gt_bin_mag = torch.zeros((B, 512, T, 2), dtype=torch.float32, device=dev)
+            self.gt_mono_mag = torch.zeros((B, 512, T, 1), dtype=torch.float32, device=dev)
+            self.static = (self.mixed_audio, self.gt_bin_mag, self.gt_mono_mag)
+        self.target_class = torch.zeros((B, 1), dtype=torch.int64, device=dev)
+        # ---- snapshot, eager warm-up on a side stream, capture, in-place restore
+        params = list(actor_critic.parameters()) + list(actor_critic.buffers())
+        saved = [t.detach().clone() for t in params]
+        saved_opt = {p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()} for p, st in optimizer.state.items()}
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.bin_loss, self.mono_loss = self._step()
+        with torch.no_grad():
+            for t, s in zip(params, saved):
+                t.copy_(s)
+            for p, st in optimizer.state.items():
+                old = saved_opt.get(p)
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()                 # a fresh optimizer: step 0, zero moments
+        torch.cuda.synchronize(dev)
+
+    def _step(self):
+        if self.rend is not None:
+            mono, rir, ln = self.static
+            out = self.rend.render(mono, rir, ln, n_gt=1)                  # dataset path (dataset.py:162-228): fp32 mixture + target GT
+            mixed, gt_bin = out["mix_mag"], out["gt"][:, 0]
+            gt_mono, _ = self.rend.stft_f32((mono[:, :1].float() * (1.0 / 32768)).contiguous())
+        else:
+            mixed, gt_bin, gt_mono = self.static
+        bin_loss, mono_loss = train_step(self.actor_critic, self.optimizer, mixed, gt_bin, gt_mono, self.target_class, grad_sync=self.grad_sync)
+        return bin_loss.detach(), mono_loss.detach()      # no reference to the autograd graph survives the step
+
+    def __call__(self, *inputs, target_class=None):
+        """``(mono, rir, rir_len)`` with a renderer, else ``(mixed_audio, gt_bin_mag, gt_mono_mag)``; plus ``target_class``."""
+        for dst, src in zip(self.static, inputs):
+            if dst.shape != src.shape:
+                if dst is getattr(self, "rir", None) and src.shape[:3] == dst.shape[:3] and src.shape[3] <= dst.shape[3]:
+                    dst[..., :src.shape[3]].copy_(src, non_blocking=True)       # taps beyond rir_len are never read
+                    continue
+                from . import _lib
+                raise _lib.M2HError(f"GraphedTrainStep was captured for {tuple(dst.shape)}, got {tuple(src.shape)}")
+            dst.copy_(src, non_blocking=True)
+        if target_class is not None:
+            self.target_class.copy_(target_class.reshape(self.target_class.shape), non_blocking=True)
+        self.graph.replay()
+        return self.bin_loss, self.mono_loss
