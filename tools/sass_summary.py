@@ -20,7 +20,7 @@ for line in sass.splitlines():
         cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
         counts[cur] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
     if m and cur:
         op = m.group(1)
         counts[cur]["total"] += 1
