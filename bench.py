@@ -733,7 +733,7 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
         try:
             from move2hear_active_av_separation_b200.pretrain import GraphedTrainStep
             gstep = GraphedTrainStep(pol, opt, B, dev, renderer=rend, n_sources=K_SRC, n_samples=N_SAMPLES, rir_taps=L_TAPS,
-                                     grad_sync=red.finish if red else None)
+                                     grad_sync=red.finish if red else None, two_streams=bool(int(os.environ.get("M2H_TRAIN_TWO_STREAMS", "1"))))
             for _ in range(3):
                 gstep(mono, rir, ln, target_class=tc)
             (b, m), ms_total, per_step = timed(lambda: gstep(mono, rir, ln, target_class=tc), steps)
@@ -745,7 +745,8 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
     info = {"workload": "configs[2] pretraining step: render (dataset path) + binSep & bin2mono U-Nets fwd/bwd (train-mode BN) + L1 losses + fused Adam",
             "batch_per_gpu": B, "steps": steps, "unit": "mixtures/s", "grad_allreduce": "NCCL AVG in place on the flat gradient arena the wgrad kernels write (32 MB fp32 buckets, no pack / un-pack), after backward on the compute stream" if world > 1 else "none (1 GPU)",
             "bin_mono_loss_first_last": losses, "ms_per_step_median_this_rank": per_step[len(per_step) // 2], "ms_per_step_max_this_rank": per_step[-1],
-            "mode": mode, "ms_per_step_eager_this_rank": ms_eager / steps, "graph_capture_error": graph_err}
+            "mode": mode, "ms_per_step_eager_this_rank": ms_eager / steps, "graph_capture_error": graph_err,
+            "graph_note": "one CUDA graph per step; the converter branch and the weight gradients are parallel branches of it (pretrain.train_step side_stream, csrc wgrad fork)"}
     return info, ms_total
 
 

@@ -1,6 +1,7 @@
 // C-ABI entry points of the passive-separator U-Net (include/m2h.h): weight packing, input packing, layer launches.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <mutex>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>

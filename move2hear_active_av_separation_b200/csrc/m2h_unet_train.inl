@@ -326,6 +326,56 @@ extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int6
 }
 
 // ------------------------------------------------------------------------------------------------
+// weight gradients on a forked stream
+// ------------------------------------------------------------------------------------------------
+// A layer's weight gradient is a leaf of the backward pass: it needs dz of its own layer and the layer's (read-only) input
+// activation, and nothing downstream needs it before the optimizer.  The backward functions therefore fork: after the
+// BatchNorm backward of layer i the weight-gradient kernel goes to a side stream (event fork), the data gradient and the
+// next layers continue on the caller's stream, and the function joins the side stream before it returns.  The step is a
+// chain of short, latency-bound kernels (B = 256: ~10 us each), so the two chains fill each other's gaps; the same
+// fork / join is captured as parallel branches by pretrain.GraphedTrainStep.  M2H_NO_WGRAD_FORK=1 keeps one stream.
+struct WgradFork {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool used = false;
+};
+static WgradFork g_forks[M2H_MAX_DEVICES][8];
+static std::mutex g_fork_mutex;
+
+static WgradFork* wgrad_fork_get(cudaStream_t st) {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("M2H_NO_WGRAD_FORK"); disabled = (e && atoi(e)) ? 1 : 0; }
+  if (disabled) return nullptr;
+  int dev;
+  if (m2h_current_device_checked(&dev) != M2H_OK) return nullptr;
+  std::lock_guard<std::mutex> lock(g_fork_mutex);
+  WgradFork* slot = nullptr;
+  for (int i = 0; i < 8; ++i) {
+    WgradFork& f = g_forks[dev][i];
+    if (f.used && f.main == st) return &f;
+    if (!f.used && !slot) slot = &f;
+  }
+  if (!slot) return nullptr;                       // more than 8 distinct caller streams: stay on the caller's stream
+  if (cudaStreamCreateWithFlags(&slot->side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&slot->fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&slot->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  slot->main = st; slot->used = true;
+  return slot;
+}
+// stream for the weight gradient of the layer whose dz has just been produced on `st`
+static cudaStream_t wgrad_stream(WgradFork* f, cudaStream_t st) {
+  if (!f) return st;
+  if (cudaEventRecord(f->fork, st) != cudaSuccess || cudaStreamWaitEvent(f->side, f->fork, 0) != cudaSuccess) return st;
+  return f->side;
+}
+static int wgrad_join(WgradFork* f, cudaStream_t st) {
+  if (!f) return M2H_OK;
+  M2H_CUDA_CHECK(cudaEventRecord(f->join, f->side));
+  M2H_CUDA_CHECK(cudaStreamWaitEvent(st, f->join, 0));
+  return M2H_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
 extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int convert_bin2mono, const float* dmask, int B, void* workspace,
@@ -352,6 +402,7 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
   M2H_CUDA_CHECK(launch_pdl(head_bwd_kernel, dim3(hb_chunks < 592 ? hb_chunks : 592), dim3(128), (size_t)(0), st, W.bf(TW_A4), p->head_w, dmask, W.bf(TW_DA4), grads->head_w, grads->head_b, B, c_last));
   M2H_CUDA_CHECK(cudaGetLastError());
   const FMap none = fmap(nullptr, 0, 0, 0, 0);
+  WgradFork* fk = wgrad_fork_get(st);
   for (int i = 4; i >= 0; --i) {
     const int lvl_out = 4 - i, lvl_in = 5 - i;          // lvl_in == 5: the bottleneck
     const int C = kDecCoutBase[i], Creal = i == 4 ? c_last : C;
@@ -363,8 +414,9 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
     if (rc != M2H_OK) return rc;
     // weight gradient: dense = layer input (cat_{lvl_in} or the bottleneck), sampled = dz (now in z)
     const int hq_in = i == 0 ? 1 : hp[lvl_in] - 2;
-    if (i == 0) rc = launch_wgrad(W.bf(TW_BOTT), 512, 0, 512, false, z.p, z.ld, 0, Creal, Creal, 1, B, grads->deconv_w[0], st);
-    else rc = launch_wgrad(W.bf(cat_slot[lvl_in]), cat_ld[lvl_in], 0, kDecCin[i], true, z.p, z.ld, 0, Creal, Creal, hq_in, B, grads->deconv_w[i], st);
+    const cudaStream_t wst = wgrad_stream(fk, st);
+    if (i == 0) rc = launch_wgrad(W.bf(TW_BOTT), 512, 0, 512, false, z.p, z.ld, 0, Creal, Creal, 1, B, grads->deconv_w[0], wst);
+    else rc = launch_wgrad(W.bf(cat_slot[lvl_in]), cat_ld[lvl_in], 0, kDecCin[i], true, z.p, z.ld, 0, Creal, Creal, hq_in, B, grads->deconv_w[i], wst);
     if (rc != M2H_OK) return rc;
     // data gradient: Conv2d(k4, s2, p1) over dz -> d(cat_{lvl_in}) (all its channels: previous decoder output | skip) or d(bottleneck)
     UGLayer g;
@@ -382,7 +434,7 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
     rc = launch_layer_auto(g, 128, B, st);
     if (rc != M2H_OK) return rc;
   }
-  return M2H_OK;
+  return wgrad_join(fk, st);
 }
 
 extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int convert_bin2mono, const float* target_class_plus1, int B,
@@ -406,6 +458,7 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
     M2H_CUDA_CHECK(cudaMemsetAsync(grads->conv_w[i], 0, (size_t)kEncCout[i] * cin_full * 16 * 4, st));
   }
   const FMap none = fmap(nullptr, 0, 0, 0, 0);
+  WgradFork* fk = wgrad_fork_get(st);
   for (int i = 4; i >= 0; --i) {
     const int C = kEncCout[i];
     const int lvl = i + 1;                          // output level of layer i (5 = bottleneck)
@@ -418,15 +471,16 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
     rc = bn_backward(W, i, da1, da2, a, z, C, C, (double)B * hq * hq, 0.2f, grads->bn_w[i], grads->bn_b[i], st);
     if (rc != M2H_OK) return rc;
     // weight gradient: dense = dz (output resolution), sampled = layer input
+    const cudaStream_t wst = wgrad_stream(fk, st);
     if (i == 0) {
-      rc = launch_wgrad(z.p, z.ld, z.coff, 64, true, W.bf(TW_X0P), 32, 0, 32, convert_bin2mono ? 32 : 33, 16, B, grads->conv_w[0], st);
+      rc = launch_wgrad(z.p, z.ld, z.coff, 64, true, W.bf(TW_X0P), 32, 0, 32, convert_bin2mono ? 32 : 33, 16, B, grads->conv_w[0], wst);
       if (rc != M2H_OK) return rc;
       if (!convert_bin2mono) {
-        M2H_CUDA_CHECK(launch_pdl(wgrad_cls_kernel, dim3(dim3(64, 16)), dim3(256), (size_t)(0), st, z.p, z.ld, z.coff, target_class_plus1, B, grads->conv_w[0], 33));
+        M2H_CUDA_CHECK(launch_pdl(wgrad_cls_kernel, dim3(dim3(64, 16)), dim3(256), (size_t)(0), wst, z.p, z.ld, z.coff, target_class_plus1, B, grads->conv_w[0], 33));
         M2H_CUDA_CHECK(cudaGetLastError());
       }
     } else {
-      rc = launch_wgrad(z.p, z.ld, z.coff, C, i < 4, W.bf(cat_slot[i]), cat_ld[i], cat_ld[i] / 2, kEncCin[i], kEncCin[i], hq, B, grads->conv_w[i], st);
+      rc = launch_wgrad(z.p, z.ld, z.coff, C, i < 4, W.bf(cat_slot[i]), cat_ld[i], cat_ld[i] / 2, kEncCin[i], kEncCin[i], hq, B, grads->conv_w[i], wst);
       if (rc != M2H_OK) return rc;
       // data gradient: ConvTranspose2d(k4, s2, p1) over dz -> denc_i (gradient of the skip feature at level i)
       UGLayer g;
@@ -447,7 +501,7 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
       if (rc != M2H_OK) return rc;
     }
   }
-  return M2H_OK;
+  return wgrad_join(fk, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -33,13 +33,36 @@ def optimize_supervised_loss(optimizer, mixed_audio, pred_binSepMasks, gt_bin_ma
     return bin_loss, mono_loss, optimizer
 
 
-def train_step(actor_critic, optimizer, mixed_audio, gt_bin_mag, gt_mono_mag, target_class, grad_sync=None):
-    """One train-split iteration of ``PassiveTrainer.train`` (passive_trainer.py:218-245) -> ``(bin_loss, mono_loss)``."""
+def train_step(actor_critic, optimizer, mixed_audio, gt_bin_mag, gt_mono_mag, target_class, grad_sync=None, side_stream=None):
+    """One train-split iteration of ``PassiveTrainer.train`` (passive_trainer.py:218-245) -> ``(bin_loss, mono_loss)``.
+
+    ``side_stream`` (optional ``torch.cuda.Stream``): the binaural-to-monaural converter consumes the DETACHED masks
+    (passive_trainer.py:229-230), so its forward, its loss and its whole backward are independent of the binaural separator's
+    loss and backward.  With a side stream the converter branch runs there (autograd replays a node on its forward's stream),
+    next to the separator's backward on the calling stream: the step is ~230 short, latency-bound kernels, and the two chains
+    fill each other's gaps.  Same arithmetic, same results."""
+    import torch
     obs_batch = {"mixed_bin_audio_mag": mixed_audio, "target_class": target_class}
     pred_binSepMasks = actor_critic.get_binSepMasks(obs_batch)
-    pred_mono = actor_critic.convert_bin2mono(pred_binSepMasks.detach(), mixed_audio=mixed_audio)
-    bin_loss, mono_loss, _ = optimize_supervised_loss(optimizer, mixed_audio, pred_binSepMasks, gt_bin_mag, pred_mono, gt_mono_mag,
-                                                      split="train", grad_sync=grad_sync)
+    if side_stream is None:
+        pred_mono = actor_critic.convert_bin2mono(pred_binSepMasks.detach(), mixed_audio=mixed_audio)
+        bin_loss, mono_loss, _ = optimize_supervised_loss(optimizer, mixed_audio, pred_binSepMasks, gt_bin_mag, pred_mono, gt_mono_mag,
+                                                          split="train", grad_sync=grad_sync)
+        return bin_loss, mono_loss
+    main = torch.cuda.current_stream(mixed_audio.device)
+    side_stream.wait_stream(main)                       # the masks (and everything before them) are ready
+    with torch.cuda.stream(side_stream):
+        pred_mono = actor_critic.convert_bin2mono(pred_binSepMasks.detach(), mixed_audio=mixed_audio)
+        mono_loss = l1_mask_loss(pred_mono, gt_mono_mag)
+    bin_loss = l1_mask_loss(pred_binSepMasks, gt_bin_mag, mixed_audio=mixed_audio)
+    optimizer.zero_grad()
+    main.wait_stream(side_stream)                       # the sum below reads the converter's loss
+    loss = bin_loss + mono_loss
+    loss.backward()                                     # converter nodes run on the side stream, separator nodes here
+    main.wait_stream(side_stream)
+    if grad_sync is not None:
+        grad_sync()
+    optimizer.step()
     return bin_loss, mono_loss
 
 
@@ -62,7 +85,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, actor_critic, optimizer, batch_size: int, device, renderer=None, n_sources: int = 2, n_samples: int = 16000,
-                 rir_taps: int = 16000, grad_sync=None, warmup: int = 3):
+                 rir_taps: int = 16000, grad_sync=None, warmup: int = 3, two_streams: bool = False):
         import torch
         from . import _lib
         if not torch.cuda.is_available():
@@ -72,6 +95,8 @@ class GraphedTrainStep:
         self.device = torch.device(device)
         dev, B = self.device, batch_size
         self.actor_critic, self.optimizer, self.rend, self.grad_sync = actor_critic, optimizer, renderer, grad_sync
+        # two_streams: the converter branch of the step on a second stream (see train_step): two parallel chains in the graph
+        self.side = torch.cuda.Stream(self.device) if two_streams else None
         if renderer is not None:          # render inside the graph: the dataset item's inputs are the static buffers
             self.mono = torch.zeros((B, n_sources, n_samples), dtype=torch.int16, device=dev)
             self.rir = torch.zeros((B, n_sources, 2, rir_taps + (rir_taps & 1)), dtype=torch.float32, device=dev)
@@ -120,7 +145,8 @@ class GraphedTrainStep:
             gt_mono, _ = self.rend.stft_f32((mono[:, :1].float() * (1.0 / 32768)).contiguous())
         else:
             mixed, gt_bin, gt_mono = self.static
-        bin_loss, mono_loss = train_step(self.actor_critic, self.optimizer, mixed, gt_bin, gt_mono, self.target_class, grad_sync=self.grad_sync)
+        bin_loss, mono_loss = train_step(self.actor_critic, self.optimizer, mixed, gt_bin, gt_mono, self.target_class, grad_sync=self.grad_sync,
+                                         side_stream=self.side)
         return bin_loss.detach(), mono_loss.detach()      # no reference to the autograd graph survives the step
 
     def __call__(self, *inputs, target_class=None):
