@@ -653,10 +653,10 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps,
-                # what the host link allows: every rank uploading its 328 MB per step at the bandwidth the slowest rank reached in
-                # `pcie_probe` with all ranks copying at once (and the masks going back on the other direction)
-                "pcie_ceiling": world * B / (h2d / (pcie["h2d_gb_per_s_with_concurrent_d2h"] * 1e9)),
-                "frac_of_pcie_ceiling": e2e_value / (world * B / (h2d / (pcie["h2d_gb_per_s_with_concurrent_d2h"] * 1e9)))},
+                # what the host link allows at best: every rank uploading its 328 MB per step at the bandwidth the slowest rank
+                # reached in `pcie_probe` with all ranks uploading at once (an upper bound: the masks going back cost some of it)
+                "pcie_ceiling": world * B / (h2d / (pcie["h2d_gb_per_s_alone"] * 1e9)),
+                "frac_of_pcie_ceiling": e2e_value / (world * B / (h2d / (pcie["h2d_gb_per_s_alone"] * 1e9)))},
         "e2e_device_cache": {"value": world * B * e2e_steps / (ms_cached * 1e-3), "unit": UNIT, "ms_per_step": ms_cached / e2e_steps,
                              "h2d_bytes_per_step": 2 * 4 * B * K_SRC, "d2h_bytes_per_step": d2h,
                              "rir_hit_rate": cache_stats["rir_hits"] / max(1, cache_stats["rir_hits"] + cache_stats["rir_misses"]),

@@ -313,6 +313,7 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   } else {
     // ------------------------------ epilogue: two groups of 4 warps alternate tiles / TMEM buffers ------------------------------
     const int grp = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
+    const bool relu = L.slope == 0.f;   // warp-uniform: the decoder's ReLU needs no slope multiply
     for (int j = 0;; ++j) {             // the group's j-th tile: iter = 2j + grp, accumulator buffer grp + 2*(j % bufs_per_q)
       const int iter = 2 * j + grp;
       if (iter >= n_my) break;
@@ -353,8 +354,11 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
                 a0 = fmaf(clsv, c4.x, a0); a1 = fmaf(clsv, c4.y, a1); a2 = fmaf(clsv, c4.z, a2); a3 = fmaf(clsv, c4.w, a3);
               }
               a0 = fmaf(a0, s01.x, s01.y); a1 = fmaf(a1, s01.z, s01.w); a2 = fmaf(a2, s23.x, s23.y); a3 = fmaf(a3, s23.z, s23.w);
-              yv[i] = fmaxf(a0, a0 * L.slope); yv[i + 1] = fmaxf(a1, a1 * L.slope);
-              yv[i + 2] = fmaxf(a2, a2 * L.slope); yv[i + 3] = fmaxf(a3, a3 * L.slope);
+              if (relu) { yv[i] = fmaxf(a0, 0.f); yv[i + 1] = fmaxf(a1, 0.f); yv[i + 2] = fmaxf(a2, 0.f); yv[i + 3] = fmaxf(a3, 0.f); }
+              else {
+                yv[i] = fmaxf(a0, a0 * L.slope); yv[i + 1] = fmaxf(a1, a1 * L.slope);
+                yv[i + 2] = fmaxf(a2, a2 * L.slope); yv[i + 3] = fmaxf(a3, a3 * L.slope);
+              }
             }
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
@@ -395,8 +399,8 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
               const float4 s01 = *reinterpret_cast<const float4*>(sb_smem + 2 * i);
               float a0 = fmaf(__uint_as_float(v[i]), s01.x, s01.y);
               float a1 = fmaf(__uint_as_float(v[i + 1]), s01.z, s01.w);
-              a0 = fmaxf(a0, a0 * L.slope);
-              a1 = fmaxf(a1, a1 * L.slope);
+              if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }       // ReLU: no slope multiply (every decoder layer)
+              else { a0 = fmaxf(a0, a0 * L.slope); a1 = fmaxf(a1, a1 * L.slope); }
               __nv_bfloat162 t2 = __floats2bfloat162_rn(a0, a1);
               pk[pl][i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
             }
