@@ -373,7 +373,7 @@ def run_ours(args):
     # package's host-buffer entry (pipeline.SeparationPipeline: chunks in flight on 3 streams so copies overlap kernels)
     from move2hear_active_av_separation_b200.pipeline import SeparationPipeline
     h_out = torch.empty((B, 2, 512, 32), dtype=torch.float32).pin_memory()
-    pipe = SeparationPipeline(enc, dec, dev, K_SRC, N_SAMPLES, L_TAPS)
+    pipe = SeparationPipeline(enc, dec, dev, K_SRC, N_SAMPLES, L_TAPS, stream_calls=True)      # steps stream through the lanes back to back
 
     def step_e2e():
         pipe(h_mono, h_rir, h_len, h_tc, h_out)

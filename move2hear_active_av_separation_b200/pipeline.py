@@ -38,12 +38,17 @@ class SeparationPipeline:
 
     Args:
         enc, dec: ``PassiveSepEncCNN`` / ``PassiveSepDecCNN`` (binaural separator, ``.eval()``) on ``device``.
-        chunk: mixtures per chunk (a multiple of 74 keeps the persistent conv grid of 148 CTAs evenly loaded for K = 2; small
+        chunk: mixtures per chunk (148 mixtures x K = 2 sources = one item per CTA of the convolution's 296-CTA grid; small
             chunks shorten the un-overlapped first copy-in and last copy-out).
         lanes: number of chunks in flight (3 = one copying in, one computing, one copying out).
     """
 
-    def __init__(self, enc, dec, device, K: int, N: int, Lmax: int, chunk: int = 148, lanes: int = 3):
+    def __init__(self, enc, dec, device, K: int, N: int, Lmax: int, chunk: int = 148, lanes: int = 3, stream_calls: bool = False):
+        """``stream_calls``: successive calls overlap - a lane starts the next call's chunk as soon as its own previous chunk is
+        done instead of waiting for the caller's stream (which waits for the whole previous call): the first copy-in of call
+        i + 1 then runs under the last kernels and copy-out of call i.  Safe when the inputs are host buffers that are ready
+        when the call is made (they are: pinned host memory) and the caller reads ``out`` only after synchronising its stream."""
+        self.stream_calls = stream_calls
         if not torch.cuda.is_available():
             raise _lib.M2HError("no CUDA device: the B200 hot path has no CPU fallback")
         self.device = torch.device(device)
@@ -88,7 +93,8 @@ class SeparationPipeline:
             n = e - s
             lane = self.lanes[i % len(self.lanes)]
             with torch.cuda.stream(lane.stream):
-                lane.stream.wait_event(start)
+                if not self.stream_calls:
+                    lane.stream.wait_event(start)
                 lane.mono[:n].copy_(mono[s:e], non_blocking=True)
                 lane.rir[:n].copy_(rir[s:e], non_blocking=True)
                 lane.len[:n].copy_(rir_len[s:e], non_blocking=True)
