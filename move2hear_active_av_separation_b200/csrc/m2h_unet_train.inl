@@ -336,7 +336,7 @@ extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int6
 // fork / join is captured as parallel branches by pretrain.GraphedTrainStep.  M2H_NO_WGRAD_FORK=1 keeps one stream.
 struct WgradFork {
   cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, ready = nullptr;
   bool used = false;
 };
 static WgradFork g_forks[M2H_MAX_DEVICES][8];
@@ -358,7 +358,8 @@ static WgradFork* wgrad_fork_get(cudaStream_t st) {
   if (!slot) return nullptr;                       // more than 8 distinct caller streams: stay on the caller's stream
   if (cudaStreamCreateWithFlags(&slot->side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
   if (cudaEventCreateWithFlags(&slot->fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&slot->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      cudaEventCreateWithFlags(&slot->join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&slot->ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   slot->main = st; slot->used = true;
   return slot;
 }
@@ -367,6 +368,18 @@ static cudaStream_t wgrad_stream(WgradFork* f, cudaStream_t st) {
   if (!f) return st;
   if (cudaEventRecord(f->fork, st) != cudaSuccess || cudaStreamWaitEvent(f->side, f->fork, 0) != cudaSuccess) return st;
   return f->side;
+}
+// The data-gradient weight operands only depend on the weights: they are packed on the side stream while the caller's
+// stream zeroes the gradients and runs the first BatchNorm backward; the first data-gradient GEMM waits for `ready`.
+static int fork_mark_ready(WgradFork* f) {                   // right after the packing launches on the side stream
+  if (!f) return M2H_OK;
+  M2H_CUDA_CHECK(cudaEventRecord(f->ready, f->side));
+  return M2H_OK;
+}
+static int fork_wait_ready(WgradFork* f, cudaStream_t st) {   // before the first consumer on the caller's stream
+  if (!f) return M2H_OK;
+  M2H_CUDA_CHECK(cudaStreamWaitEvent(st, f->ready, 0));
+  return M2H_OK;
 }
 static int wgrad_join(WgradFork* f, cudaStream_t st) {
   if (!f) return M2H_OK;
@@ -391,9 +404,17 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
   const int dcat_slot[5] = {0, TW_DCAT1, TW_DCAT2, TW_DCAT3, TW_DCAT4};
   const int cat_ld[5] = {0, 128, 256, 512, 1024}, hp[5] = {0, 18, 10, 6, 4};
   // data-gradient operands: ConvTranspose2d weight [Cin][Cout][4][4] read as a Conv2d weight [out = Cin][in = Cout]
+  WgradFork* fk = wgrad_fork_get(st);
+  const cudaStream_t pst = wgrad_stream(fk, st);            // packed next to the memsets / head backward / first BatchNorm backward
+  for (int i = 4; i >= 0; --i) {                            // in the order the data gradients need them
+    const int cout_real = i == 4 ? c_last : kDecCoutBase[i];
+    M2H_CUDA_CHECK(launch_pdl(pack_conv_w_kernel, dim3(256), dim3(256), (size_t)(0), pst, p->deconv_w[i], (__nv_bfloat16*)(pk + dec_dg_off(i)), kDecCin[i], cout_real, kDecCoutBase[i], i == 0 ? 4 : 16));
+  }
+  rc = fork_mark_ready(fk);
+  if (rc != M2H_OK) return rc;
+  bool packs_joined = false;
   for (int i = 0; i < 5; ++i) {
     const int cout_real = i == 4 ? c_last : kDecCoutBase[i];
-    M2H_CUDA_CHECK(launch_pdl(pack_conv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[i], (__nv_bfloat16*)(pk + dec_dg_off(i)), kDecCin[i], cout_real, kDecCoutBase[i], i == 0 ? 4 : 16));
     M2H_CUDA_CHECK(cudaMemsetAsync(grads->deconv_w[i], 0, (size_t)kDecCin[i] * cout_real * 16 * 4, st));
   }
   M2H_CUDA_CHECK(cudaMemsetAsync(grads->head_w, 0, (size_t)c_last * c_last * 4, st));
@@ -402,7 +423,6 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
   M2H_CUDA_CHECK(launch_pdl(head_bwd_kernel, dim3(hb_chunks < 592 ? hb_chunks : 592), dim3(128), (size_t)(0), st, W.bf(TW_A4), p->head_w, dmask, W.bf(TW_DA4), grads->head_w, grads->head_b, B, c_last));
   M2H_CUDA_CHECK(cudaGetLastError());
   const FMap none = fmap(nullptr, 0, 0, 0, 0);
-  WgradFork* fk = wgrad_fork_get(st);
   for (int i = 4; i >= 0; --i) {
     const int lvl_out = 4 - i, lvl_in = 5 - i;          // lvl_in == 5: the bottleneck
     const int C = kDecCoutBase[i], Creal = i == 4 ? c_last : C;
@@ -419,6 +439,7 @@ extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int conve
     else rc = launch_wgrad(W.bf(cat_slot[lvl_in]), cat_ld[lvl_in], 0, kDecCin[i], true, z.p, z.ld, 0, Creal, Creal, hq_in, B, grads->deconv_w[i], wst);
     if (rc != M2H_OK) return rc;
     // data gradient: Conv2d(k4, s2, p1) over dz -> d(cat_{lvl_in}) (all its channels: previous decoder output | skip) or d(bottleneck)
+    if (!packs_joined) { rc = fork_wait_ready(fk, st); if (rc != M2H_OK) return rc; packs_joined = true; }
     UGLayer g;
     layer_defaults(g);
     g.in = z.p; g.Hin = g.Win = hq_out; g.Cin = C; g.cin_shift = ilog2(C); g.in_ld = z.ld; g.in_pad = 1;
@@ -449,16 +470,20 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
   const int dcat_slot[5] = {0, TW_DCAT1, TW_DCAT2, TW_DCAT3, TW_DCAT4}, denc_slot[5] = {0, TW_DENC1, TW_DENC2, TW_DENC3, TW_DENC4};
   const int cat_ld[5] = {0, 128, 256, 512, 1024}, hp[5] = {0, 18, 10, 6, 4};
   // data-gradient operands: Conv2d weight [Cout][Cin][4][4] read as a ConvTranspose2d weight [in = Cout][out = Cin]
-  for (int i = 1; i < 5; ++i) {
-    if (i == 4) M2H_CUDA_CHECK(launch_pdl(pack_deconv0_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->conv_w[4], (__nv_bfloat16*)(pk + enc_dg_off(4)), 512, 512));
-    else M2H_CUDA_CHECK(launch_pdl(pack_deconv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->conv_w[i], (__nv_bfloat16*)(pk + enc_dg_off(i)), kEncCout[i], kEncCin[i], kEncCin[i]));
+  WgradFork* fk = wgrad_fork_get(st);
+  const cudaStream_t pst = wgrad_stream(fk, st);
+  for (int i = 4; i >= 1; --i) {                            // in the order the data gradients need them
+    if (i == 4) M2H_CUDA_CHECK(launch_pdl(pack_deconv0_w_kernel, dim3(256), dim3(256), (size_t)(0), pst, p->conv_w[4], (__nv_bfloat16*)(pk + enc_dg_off(4)), 512, 512));
+    else M2H_CUDA_CHECK(launch_pdl(pack_deconv_w_kernel, dim3(256), dim3(256), (size_t)(0), pst, p->conv_w[i], (__nv_bfloat16*)(pk + enc_dg_off(i)), kEncCout[i], kEncCin[i], kEncCin[i]));
   }
+  rc = fork_mark_ready(fk);
+  if (rc != M2H_OK) return rc;
+  bool packs_joined = false;
   for (int i = 0; i < 5; ++i) {
     const int cin_full = i == 0 ? (convert_bin2mono ? 32 : 33) : kEncCin[i];
     M2H_CUDA_CHECK(cudaMemsetAsync(grads->conv_w[i], 0, (size_t)kEncCout[i] * cin_full * 16 * 4, st));
   }
   const FMap none = fmap(nullptr, 0, 0, 0, 0);
-  WgradFork* fk = wgrad_fork_get(st);
   for (int i = 4; i >= 0; --i) {
     const int C = kEncCout[i];
     const int lvl = i + 1;                          // output level of layer i (5 = bottleneck)
@@ -483,6 +508,7 @@ extern "C" int m2h_unet_encoder_backward(const m2h_unet_enc_params* p, int conve
       rc = launch_wgrad(z.p, z.ld, z.coff, C, i < 4, W.bf(cat_slot[i]), cat_ld[i], cat_ld[i] / 2, kEncCin[i], kEncCin[i], hq, B, grads->conv_w[i], wst);
       if (rc != M2H_OK) return rc;
       // data gradient: ConvTranspose2d(k4, s2, p1) over dz -> denc_i (gradient of the skip feature at level i)
+      if (!packs_joined) { rc = fork_wait_ready(fk, st); if (rc != M2H_OK) return rc; packs_joined = true; }
       UGLayer g;
       layer_defaults(g);
       g.w = (const __nv_bfloat16*)(pk + enc_dg_off(i)); g.slope = 1.f;
