@@ -77,11 +77,18 @@ static int grid_for(long long work, int per_block) {
   return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
 }
 // BatchNorm forward of one layer: stats over z, running-stat update, a = act(BN(z)).  layer = BN slot (0-4 encoder, 5-9 decoder)
+// The fp64 reduction slots (forward sums | backward sums) of layers [first, first + count) are zeroed by ONE memset at the
+// start of a forward function (they were one memset per layer and pass: 40 graph nodes per step)
+static int bn_zero_slots(const TW& W, int first, int count, cudaStream_t st) {
+  M2H_CUDA_CHECK(cudaMemsetAsync(W.stats(first), 0, (size_t)count * 4 * 512 * 8, st));
+  return M2H_OK;
+}
 static int bn_forward(const TW& W, int layer, const FMap& z, const FMap& a, int C, int Creal, double n, const float* gamma, const float* beta,
                       float* run_mean, float* run_var, long long* nbt, float eps, float momentum, float slope, cudaStream_t st) {
   double* stats = W.stats(layer);
-  M2H_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)4 * 512 * 8, st));
   M2H_CUDA_CHECK(launch_pdl(bn_stats_kernel, dim3(grid_for(z.P, 4 * (256 / (C / 8)))), dim3(256), (size_t)(2 * 256 * 8 * sizeof(float)), st, z, C, stats));
+  // (a fused finalize + apply kernel was measured and dropped: every thread of the wide apply grid re-derives eight channels'
+  // scale / shift in fp64, which costs more than the 20 tiny finalize launches it saves: 3.33 vs 3.18 ms per step)
   M2H_CUDA_CHECK(launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, stats, n, gamma, beta, eps, momentum, run_mean, run_var, nbt, W.aux(layer), Creal, C));
   M2H_CUDA_CHECK(launch_pdl(bn_apply_kernel, dim3(grid_for(z.P * (C / 8), 256)), dim3(256), (size_t)(0), st, z, a, C, W.aux(layer), slope));
   M2H_CUDA_CHECK(cudaGetLastError());
@@ -90,8 +97,7 @@ static int bn_forward(const TW& W, int layer, const FMap& z, const FMap& a, int 
 // BatchNorm backward of one layer: dz written over z; fp32 dgamma / dbeta out
 static int bn_backward(const TW& W, int layer, const FMap& da1, const FMap& da2, const FMap& a, const FMap& z, int C, int Creal, double n,
                        float slope, float* dgamma, float* dbeta, cudaStream_t st) {
-  double* red = W.stats(layer) + 2 * 512;
-  M2H_CUDA_CHECK(cudaMemsetAsync(red, 0, (size_t)2 * 512 * 8, st));
+  double* red = W.stats(layer) + 2 * 512;          // zeroed by the forward pass of the same step (bn_zero_slots)
   // reductions use [C] strides inside the 512-wide slots: kernels index red[c] and red[C + c]
   M2H_CUDA_CHECK(launch_pdl(bn_bwd_reduce_kernel, dim3(grid_for(z.P, 4 * (256 / (C / 8)))), dim3(256), (size_t)(2 * 256 * 8 * sizeof(float)), st, da1, da2, a, z, C, W.aux(layer), slope, red));
   M2H_CUDA_CHECK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(z.P * (C / 8), 256)), dim3(256), (size_t)(0), st, da1, da2, a, z, C, Creal, W.aux(layer), slope, red, n, dgamma, dbeta));
@@ -185,6 +191,8 @@ extern "C" int m2h_unet_encoder_forward_train(const m2h_unet_enc_params* p, int6
   const TW W = tw_make(workspace, B);
   char* pk = W.base + W.off[TW_PACK_ENC];
   const EncLayout PL = enc_layout();
+  rc = bn_zero_slots(W, 0, 5, st);
+  if (rc != M2H_OK) return rc;
   // bf16 GEMM operands of the current weights (BatchNorm is NOT folded in train mode)
   for (int i = 0; i < 5; ++i) {
     const int cin_full = i == 0 ? (convert_bin2mono ? 32 : 33) : kEncCin[i];
@@ -266,6 +274,8 @@ extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int6
   cudaStream_t st = (cudaStream_t)stream;
   const TW W = tw_make(workspace, B);
   char* pk = W.base + W.off[TW_PACK_DEC];
+  rc = bn_zero_slots(W, 5, 5, st);
+  if (rc != M2H_OK) return rc;
   const DecLayout PL = dec_layout();
   const int c_last = convert_bin2mono ? 16 : 32;
   for (int i = 0; i < 5; ++i) {
