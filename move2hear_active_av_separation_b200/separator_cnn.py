@@ -370,7 +370,10 @@ class _PackedModule(nn.Module):
         arena = getattr(self, "_grad_arena", None)
         ps = self._train_params()
         if arena is not None and all(q.requires_grad and q.dtype == torch.float32 for q in ps):
-            return [arena.grad_view(q) for q in ps]
+            # a parameter that still holds a gradient (accumulation over several backward passes without zero_grad) keeps it:
+            # the kernels must not overwrite the arena slot p.grad lives in - that backward gets a separate buffer and autograd
+            # adds it into the slot
+            return [arena.grad_view(q) if q.grad is None else torch.empty_like(q, memory_format=torch.contiguous_format) for q in ps]
         return [torch.empty_like(q, memory_format=torch.contiguous_format) for q in ps]
 
     def _train_params(self):
