@@ -239,8 +239,14 @@ def run_rollout_processes(local, n_procs=14, n_steps=40):
         p.start()
     res = []
     try:
-        for _ in range(n_procs):
-            res.append(q.get(timeout=600))
+        import queue as _queue
+        deadline = time.perf_counter() + 180.0
+        while len(res) < n_procs:
+            try:
+                res.append(q.get(timeout=2.0))
+            except _queue.Empty:
+                if time.perf_counter() > deadline or any(p.exitcode not in (None, 0) for p in procs):
+                    raise RuntimeError("a rollout worker process died or timed out (exit codes %s)" % [p.exitcode for p in procs])
     finally:
         for p in procs:
             p.join(timeout=60)
@@ -607,7 +613,10 @@ def run_ours(args):
     if world == 1 and not args.no_procs:
         del d_mono, d_rir                   # the children allocate their own contexts next to this one
         torch.cuda.empty_cache()
-        rollout_procs = run_rollout_processes(local)
+        try:
+            rollout_procs = run_rollout_processes(local)
+        except Exception as e:           # never lose the line to the process-mode leg
+            rollout_procs = {"error": repr(e)[:300]}
 
     pk = peaks()
     ms_step = ms_total / args.steps
