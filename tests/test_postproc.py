@@ -118,3 +118,27 @@ def test_waveform_quality_on_gpu(gold):
         want = OP.evaluate([ref[i:i + 1].astype(np.float64)], [est[i:i + 1].astype(np.float64)], [mix[i].astype(np.float64)])
         for k in ("si_sdr", "sd_sdr", "snr", "srr", "si_sdri", "sd_sdri", "snri", "si_sar"):
             assert abs(got[i][k] - want[k]) < 1e-6, (i, k, got[i][k], want[k])
+
+
+@pytest.mark.gpu
+def test_postproc_other_shapes():
+    """B = 1, odd frame counts, permuted views: STFT_L2_distance against the oracle; AcousticMem at B = 1."""
+    from move2hear_active_av_separation_b200.postproc import AcousticMem, STFT_L2_distance
+    g = torch.Generator().manual_seed(17)
+    for B, T in ((1, 32), (2, 7), (5, 13)):
+        mixed = torch.log1p(torch.rand(B, 512, T, 2, generator=g) * 3)
+        masks = torch.randn(B, 2, 512, T, generator=g).permute(0, 2, 3, 1)                   # the decoder's permuted view
+        gt_bin = torch.stack([torch.rand(B, 512, T, generator=g), torch.rand(B, 512, T, generator=g) * 6 - 3,
+                              torch.rand(B, 512, T, generator=g), torch.rand(B, 512, T, generator=g) * 6 - 3], dim=-1)
+        mono = torch.rand(B, 1, 512, T, generator=g).permute(0, 2, 3, 1)
+        gt_mono = torch.stack([torch.rand(B, 512, T, generator=g), torch.rand(B, 512, T, generator=g) * 6 - 3], dim=-1)
+        wb, wm = OP.stft_l2_distance(mixed, masks, gt_bin, mono, gt_mono)
+        b, m = STFT_L2_distance(mixed.cuda(), masks.cuda(), gt_bin.cuda(), mono.cuda(), gt_mono.cuda())
+        assert tuple(b.shape) == (B, 1) and torch.allclose(b, wb, rtol=5e-6) and torch.allclose(m, wm, rtol=5e-6)
+    torch.manual_seed(3)
+    mem = AcousticMem(use_ddppo=False).cuda().eval()
+    sd = {k: v.detach().cpu() for k, v in mem.state_dict().items()}
+    a, p = torch.rand(1, 512, 32, 1, generator=g), torch.rand(1, 512, 32, 1, generator=g)
+    with torch.no_grad():
+        got, want = mem(a.cuda(), p.cuda()).cpu(), OP.acoustic_mem_forward(sd, a, p)
+    assert float((got - want).norm() / want.norm()) < 1e-5

@@ -224,7 +224,9 @@ def test_conv_and_stft_random_shapes(rend):
     lengths inside a batch, even / odd row lengths (packed and scalar kernel variants, odd first taps)."""
     rng = np.random.default_rng(2024)
     shapes = [(16000, 16000, 2, 3), (16000, 15999, 2, 2), (16000, 48002, 3, 2), (16000, 32001, 1, 2), (8192, 8192, 2, 2),
-              (5000, 12002, 2, 3), (5001, 777, 2, 2), (16384, 32768, 1, 2), (12000, 1, 2, 2), (16000, 40000, 4, 1)]
+              (5000, 12002, 2, 3), (5001, 777, 2, 2), (16384, 32768, 1, 2), (12000, 1, 2, 2), (16000, 40000, 4, 1),
+              # both sides of the dispatch between the F = 24576 kernel (Lmax <= 16384) and the F = 32768 kernel, largest clip
+              (16384, 16384, 2, 2), (16384, 16386, 2, 2), (16000, 16383, 1, 3), (1536, 16384, 2, 2), (513, 2, 3, 2)]
     for N, Lmax, K, B in shapes:
         mono = np.round(2500 * rng.standard_normal((B, K, N))).astype(np.int16)
         lens = rng.integers(max(1, Lmax // 3), Lmax + 1, size=(B, K)).astype(np.int32)

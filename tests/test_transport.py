@@ -90,3 +90,29 @@ def test_batched_render_into_rollout_storage_matches_reference_path():
     st = bor.cached.stats()
     assert st["rir_hits"] > 0 and st["clip_hits"] > st["clip_misses"]
     assert not storage["mixed_bin_audio_mag"][0].any()                      # untouched step
+
+
+@pytest.mark.gpu
+def test_batched_render_three_sources_and_mixed_source_counts_rejected():
+    from move2hear_active_av_separation_b200 import _lib
+    from move2hear_active_av_separation_b200 import transport as TR
+    dev = torch.device("cuda", 0)
+    clips = {f"s{i}": R.synth_monos(1, 1, seed=500 + i)[0, 0] for i in range(3)}
+    rirs = {}
+    for src, L in ((1, 12000), (2, 3000), (3, 16000)):
+        rp, _ = R.synth_rirs(1, 1, L=L, seed=600 + src)
+        rirs[("sc", 0, 0, src)] = R.rir_wav_layout(rp[0, 0], L)
+    bor = TR.BatchedObservationRenderer(clips.__getitem__, rirs.__getitem__, device=dev, gt_mono_mag_norm=0.0, rir_capacity=8, clip_capacity=4)
+    req3 = TR.AudioRenderRequest(("s0", "s1", "s2"), "sc", 0, 0, (1, 2, 3))
+    out = bor.render([req3, req3])
+    want = R.render_sim([clips["s0"], clips["s1"], clips["s2"]], [rirs[("sc", 0, 0, s)] for s in (1, 2, 3)], gt_mono_mag_norm=0.0)
+    assert tuple(out["gt_bin_comps"].shape) == (2, 512, 32, 12) and tuple(out["gt_mono_comps"].shape) == (2, 512, 32, 6)
+    ok, nbad, maxulp = f16_close(out["mixed_bin_audio_mag"][1].cpu().numpy().astype(np.float16), want["mixed_bin_audio_mag"])
+    assert ok, (nbad, maxulp)
+    gm = np.concatenate(want["gt_mono_audio_components"], axis=2).astype(np.float32)
+    got = out["gt_mono_comps"][0].cpu().numpy()
+    for c in range(0, 6, 2):                                           # GT_MONO_MAG_NORM == 0: the simulator keeps raw magnitudes
+        assert np.linalg.norm(got[..., c] - gm[..., c]) <= 1e-3 * np.linalg.norm(gm[..., c])
+    req2 = TR.AudioRenderRequest(("s0", "s1"), "sc", 0, 0, (1, 2))
+    with pytest.raises(_lib.M2HError):
+        bor.render([req3, req2])
