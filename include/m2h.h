@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define M2H_ABI_VERSION 3
+#define M2H_ABI_VERSION 4
 
 enum m2h_status {
   M2H_OK = 0,
@@ -35,7 +35,9 @@ enum m2h_render_flags {
   M2H_RENDER_F16_OBS = 1,      /* simulator dtypes: magnitude -> fp16 -> log1p -> fp16, phases / GT in fp16
                                   (habitat_audio/simulator_train.py:437-441, 483-486).  Otherwise the dataset's
                                   fp32 outputs (audio_separation/pretrain/datasets/dataset.py:198, 226-228). */
-  M2H_RENDER_RAW_MAG = 2       /* write |STFT| of the mixture instead of log1p(|STFT|) */
+  M2H_RENDER_RAW_MAG = 2,      /* write |STFT| of the mixture instead of log1p(|STFT|) */
+  M2H_RENDER_GT_ONLY = 4       /* m2h_stft_waves: only the n_gt per-source spectrograms (mix_mag / mix_phase ignored): the
+                                  mixture's transform comes from another launch, e.g. on another stream */
 };
 
 int m2h_abi_version(void);
@@ -110,6 +112,15 @@ int m2h_clip_ingest(const void* raw_frames, int format, int channels, int frames
  */
 int m2h_stft_waves(const int16_t* waves, int B, int K, int N, int n_gt, int gt_with_phase, int flags,
                    void* mix_mag, void* mix_phase, void* gt, void* stream);
+
+/*
+ * STFT of the mixture written as the binaural separator's first-layer operand: x0 = bf16 [B][18][18][128], the haloed
+ * space-to-depth NHWC form of log1p(|STFT(mix)|) [B,512,32,2] (cell (h/2+1, t/2+1), channel ((h&1)*2 + (t&1))*32 + ear*16 +
+ * slice, h = bin % 32, slice = bin / 32: audio_separation/rl/models/separator_cnn.py:84-90).  Only interior cells are
+ * written: the caller zeroes the buffer once.  N must give 32 frames.  mix_mag (fp32 [B,512,32,2]) is optional.
+ * Feeds m2h_unet_encoder_forward_x0: the fp32 observation never travels through HBM and no repacking kernel runs.
+ */
+int m2h_stft_waves_x0(const int16_t* waves, int B, int K, int N, void* x0, float* mix_mag, void* stream);
 
 /*
  * The whole per-step render: m2h_rir_convolve followed by m2h_stft_waves on the same stream.
@@ -199,6 +210,9 @@ int m2h_unet_workspace_clear_halos(int B, void* workspace, size_t workspace_byte
 int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2mono, const float* obs,
                              const float* target_class_plus1, const float* masks, const int64_t* mask_strides,
                              int B, void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream);
+/* Same, for the binaural separator, with the first-layer operand x0 (see m2h_stft_waves_x0) instead of the fp32 observation. */
+int m2h_unet_encoder_forward_x0(const void* packed_enc, const void* x0, const float* target_class_plus1, int B,
+                                void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream);
 /* Decoder.  mask_out: fp32 [B, C, 512, 32] (C = 2 or 1) - the memory layout behind the reference's permuted
  * [B, 512, 32, C] return value (separator_cnn.py:163-170). */
 int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2mono, int B, void* workspace,
@@ -235,6 +249,13 @@ int m2h_unet_train_workspace_layout(int B, size_t offsets[32]);
 /* Zero a fresh workspace once (feature-map borders must be zero; the kernels only write interiors). */
 int m2h_unet_train_workspace_init(int B, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Train-mode weight packing ahead of time: the bf16 GEMM operands of `enc` and / or `dec` (either may be NULL) are written
+ * into the train workspace - the work m2h_unet_*_forward_train does first.  A training loop issues it on a side stream while
+ * the step's audio is still being rendered, then passes `convert_bin2mono | M2H_UNET_WEIGHTS_PACKED` to the forward
+ * calls (the weights must not change in between; the caller orders the streams). */
+#define M2H_UNET_WEIGHTS_PACKED 2
+int m2h_unet_pack_train_weights(const m2h_unet_enc_params* enc, const m2h_unet_dec_params* dec, int convert_bin2mono, int B,
+                                void* workspace, size_t workspace_bytes, void* stream);
 /* Train-mode forward.  The running_mean / running_var tensors behind p->bn_mean / p->bn_var are UPDATED in place
  * (momentum, unbiased variance) and num_batches_tracked[i] (int64 device scalars, may be NULL) incremented,
  * as nn.BatchNorm2d does.  Other arguments as m2h_unet_encoder_forward / m2h_unet_decoder_forward. */

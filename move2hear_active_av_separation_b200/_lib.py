@@ -122,6 +122,9 @@ SIGNATURES = {
     "m2h_unet_train_workspace_bytes": (_sz, [_i]),
     "m2h_unet_train_workspace_layout": (_i, [_i, _vp]),
     "m2h_unet_train_workspace_init": (_i, [_i, _vp, _sz, _vp]),
+    "m2h_stft_waves_x0": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "m2h_unet_encoder_forward_x0": (_i, [_vp, _vp, _vp, _i, _vp, _sz, _vp, _vp]),
+    "m2h_unet_pack_train_weights": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
     "m2h_unet_encoder_forward_train": (_i, [_vp, _vp, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp, _vp]),
     "m2h_unet_decoder_forward_train": (_i, [_vp, _vp, _i, ctypes.c_float, ctypes.c_float, _i, _vp, _sz, _vp, _vp]),
     "m2h_unet_decoder_backward": (_i, [_vp, _i, _vp, _i, _vp, _sz, _vp, _vp]),

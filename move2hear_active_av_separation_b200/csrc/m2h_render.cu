@@ -322,15 +322,32 @@ extern "C" int m2h_stft_waves(const int16_t* waves, int B, int K, int N, int n_g
   if (B < 0 || K <= 0 || K > 256 || N < M2H_HOP || N > M2H_MAX_SAMPLES || n_gt < 0 || n_gt > K) { m2h_set_error("m2h_stft_waves: bad sizes B=%d K=%d N=%d n_gt=%d", B, K, N, n_gt); return M2H_ERR_ARG; }
   if (B == 0) return M2H_OK;
   if (!waves || (n_gt > 0 && !gt)) { m2h_set_error("m2h_stft_waves: null pointer"); return M2H_ERR_ARG; }
+  const bool gt_only = (flags & M2H_RENDER_GT_ONLY) != 0;
+  if (gt_only && n_gt == 0) return M2H_OK;
   int dev;
   int rc = ensure_init(&dev);
   if (rc != M2H_OK) return rc;
   StftParams P;
   memset(&P, 0, sizeof(P));
   P.waves = waves; P.B = B; P.K = K; P.N = N; P.T = 1 + (N - 1) / M2H_HOP;
-  P.n_gt = n_gt; P.n_signals = 1 + n_gt;
+  P.n_gt = n_gt; P.n_signals = gt_only ? n_gt : 1 + n_gt; P.sig0 = gt_only ? 1 : 0;
   P.flags = ((flags & M2H_RENDER_RAW_MAG) ? 0 : M2H_OUT_MIX_LOG1P) | ((flags & M2H_RENDER_F16_OBS) ? M2H_OUT_F16 : 0);
   P.mix_mag = mix_mag; P.mix_phase = mix_phase; P.gt_mag = gt; P.gt_interleaved_phase = gt_with_phase ? 1 : 0;
+  return launch_stft(P, dev, stream);
+}
+
+extern "C" int m2h_stft_waves_x0(const int16_t* waves, int B, int K, int N, void* x0, float* mix_mag, void* stream) {
+  if (B < 0 || K <= 0 || K > 256 || N < M2H_HOP || N > M2H_MAX_SAMPLES) { m2h_set_error("m2h_stft_waves_x0: bad sizes B=%d K=%d N=%d", B, K, N); return M2H_ERR_ARG; }
+  if (1 + (N - 1) / M2H_HOP != 32) { m2h_set_error("m2h_stft_waves_x0: the separator's input has 32 frames, N=%d gives %d", N, 1 + (N - 1) / M2H_HOP); return M2H_ERR_ARG; }
+  if (B == 0) return M2H_OK;
+  if (!waves || !x0 || ((uintptr_t)x0 & 15) != 0) { m2h_set_error("m2h_stft_waves_x0: null or misaligned pointer"); return M2H_ERR_ARG; }
+  int dev;
+  int rc = ensure_init(&dev);
+  if (rc != M2H_OK) return rc;
+  StftParams P;
+  memset(&P, 0, sizeof(P));
+  P.waves = waves; P.B = B; P.K = K; P.N = N; P.T = 32; P.n_signals = 1; P.flags = M2H_OUT_MIX_LOG1P;
+  P.x0 = x0; P.mix_mag = mix_mag;
   return launch_stft(P, dev, stream);
 }
 

@@ -573,7 +573,10 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
   // weights stay resident in shared memory when they fit next to >= 2 tiles' worth of slab chunks, else they stream through a ring
   L.head_bytes = L.out_mode == UG_OUT_HEAD_NCHW_F32 ? US_HEAD_BYTES : 0;
   const int budget = kSlabMaxSmem - 1024 - 512 - US_AUX_BYTES - L.head_bytes;
-  const int min_stages = L.n_chunks > 2 ? L.n_chunks : 2;         // at least one tile's worth of chunks in flight
+  // at least one PAIR of tiles' worth of chunks in flight (the two issuers work on two tiles at once; with fewer stages every
+  // chunk's load latency is exposed - the last decoder layer ran with 2 stages for 4 boxes per pair)
+  static const bool old_rule = getenv("M2H_SLAB_OLD_RESIDENT_RULE") != nullptr;
+  const int min_stages = old_rule ? (L.n_chunks > 2 ? L.n_chunks : 2) : 2 * L.n_chunks;
   if (w_rows * 128 + min_stages * L.slab_bytes <= budget) {
     L.n_b_stages = 0;
     L.n_slab_stages = (budget - w_rows * 128) / L.slab_bytes;
@@ -705,12 +708,14 @@ extern "C" int m2h_unet_workspace_clear_halos(int B, void* workspace, size_t wor
   return M2H_OK;
 }
 
-extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2mono, const float* obs,
-                                        const float* target_class_plus1, const float* masks, const int64_t* mask_strides,
-                                        int B, void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream) {
+// x0_ext != null: the first layer's operand (bf16 [B][18][18][128], zero border) was written by the STFT kernel
+// (m2h_stft_waves_x0): no fp32 observation, no pack_input_kernel
+static int encoder_forward_impl(const void* packed_enc, int convert_bin2mono, const float* obs, const __nv_bfloat16* x0_ext,
+                                const float* target_class_plus1, const float* masks, const int64_t* mask_strides,
+                                int B, void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream) {
   if (B < 0) { m2h_set_error("m2h_unet_encoder_forward: B < 0"); return M2H_ERR_ARG; }
   if (B == 0) return M2H_OK;
-  if (!packed_enc || !obs || !workspace) { m2h_set_error("m2h_unet_encoder_forward: null pointer"); return M2H_ERR_ARG; }
+  if (!packed_enc || (!obs && !x0_ext) || !workspace) { m2h_set_error("m2h_unet_encoder_forward: null pointer"); return M2H_ERR_ARG; }
   if (convert_bin2mono ? (!masks || !mask_strides) : !target_class_plus1) { m2h_set_error("m2h_unet_encoder_forward: %s", convert_bin2mono ? "bin2mono needs masks + strides" : "binaural separator needs target_class"); return M2H_ERR_ARG; }
   if (workspace_bytes < m2h_unet_workspace_bytes(B)) { m2h_set_error("m2h_unet_encoder_forward: workspace too small"); return M2H_ERR_WORKSPACE; }
   int rc = unet_prepare_device();
@@ -722,11 +727,13 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
 
   // the workspace's zero borders are the caller's contract (m2h_unet_workspace_clear_halos once per allocation): every
   // kernel below writes interiors only
-  PackInParams pp;
-  pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.x0; pp.B = B; pp.x0_plain = nullptr;
-  for (int i = 0; i < 4; ++i) pp.ms[i] = convert_bin2mono ? (long long)mask_strides[i] : 0;
-  M2H_CUDA_CHECK(launch_pdl(pack_input_kernel, dim3((B * 1024 + 255) / 256), dim3(256), (size_t)0, st, pp));
-  M2H_CUDA_CHECK(cudaGetLastError());
+  if (!x0_ext) {
+    PackInParams pp;
+    pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.x0; pp.B = B; pp.x0_plain = nullptr;
+    for (int i = 0; i < 4; ++i) pp.ms[i] = convert_bin2mono ? (long long)mask_strides[i] : 0;
+    M2H_CUDA_CHECK(launch_pdl(pack_input_kernel, dim3((B * 1024 + 255) / 256), dim3(256), (size_t)0, st, pp));
+    M2H_CUDA_CHECK(cudaGetLastError());
+  }
 
   {  // layer 0 on the slab kernel: x0 (space-to-depth, 18x18 cells x 128 ch) -> cat1[..., 64:128]
     USLayer sl; SlabPackDesc pd;
@@ -736,7 +743,7 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
     sl.scale = (const float*)(pk + PL.scale[0]); sl.bias = (const float*)(pk + PL.bias[0]); sl.slope = 0.2f;
     if (!convert_bin2mono) { sl.cls = target_class_plus1; sl.cls_w = (const float*)(pk + PL.cls_w); }
     sl.out = W.cat[1]; sl.out_mode = UG_OUT_NHWC_BF16; sl.out_stride = 1; sl.Hop = sl.Wop = 18; sl.out_ld = 128; sl.out_coff = 64;
-    rc = launch_slab(sl, W.x0, 128, 18, B, (const __nv_bfloat16*)(pk + PL.w[0]), st);
+    rc = launch_slab(sl, x0_ext ? x0_ext : W.x0, 128, 18, B, (const __nv_bfloat16*)(pk + PL.w[0]), st);
     if (rc != M2H_OK) return rc;
   }
   // layers 1-4 (implicit-GEMM gather kernel); skips are written into the upper channel half of the concat buffers
@@ -765,6 +772,19 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
     M2H_CUDA_CHECK(cudaGetLastError());
   }
   return M2H_OK;
+}
+
+extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2mono, const float* obs,
+                                        const float* target_class_plus1, const float* masks, const int64_t* mask_strides,
+                                        int B, void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream) {
+  if (B > 0 && !obs) { m2h_set_error("m2h_unet_encoder_forward: null pointer"); return M2H_ERR_ARG; }
+  return encoder_forward_impl(packed_enc, convert_bin2mono, obs, nullptr, target_class_plus1, masks, mask_strides, B, workspace, workspace_bytes, bottleneck_f32, stream);
+}
+
+extern "C" int m2h_unet_encoder_forward_x0(const void* packed_enc, const void* x0, const float* target_class_plus1, int B,
+                                           void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream) {
+  if (B > 0 && (!x0 || ((uintptr_t)x0 & 127) != 0)) { m2h_set_error("m2h_unet_encoder_forward_x0: x0 must be a 128-byte aligned device pointer"); return M2H_ERR_ARG; }
+  return encoder_forward_impl(packed_enc, 0, nullptr, (const __nv_bfloat16*)x0, target_class_plus1, nullptr, nullptr, B, workspace, workspace_bytes, bottleneck_f32, stream);
 }
 
 extern "C" int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2mono, int B, void* workspace,

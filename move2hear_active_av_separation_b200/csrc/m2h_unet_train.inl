@@ -180,20 +180,9 @@ static int check_train_args(const char* who, int B, const void* ws, size_t ws_by
   return unet_prepare_device();
 }
 
-extern "C" int m2h_unet_encoder_forward_train(const m2h_unet_enc_params* p, int64_t* const* num_batches_tracked, int convert_bin2mono,
-                                              float bn_eps, float bn_momentum, const float* obs, const float* target_class_plus1,
-                                              const float* masks, const int64_t* mask_strides, int B, void* workspace, size_t workspace_bytes,
-                                              float* bottleneck_f32, void* stream) {
-  int rc = check_train_args("m2h_unet_encoder_forward_train", B, workspace, workspace_bytes);
-  if (rc != M2H_OK) return rc;
-  if (!p || !obs || (convert_bin2mono ? (!masks || !mask_strides) : !target_class_plus1)) { m2h_set_error("m2h_unet_encoder_forward_train: null pointer"); return M2H_ERR_ARG; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const TW W = tw_make(workspace, B);
-  char* pk = W.base + W.off[TW_PACK_ENC];
+// bf16 GEMM operands of the current weights (BatchNorm is NOT folded in train mode)
+static int enc_pack_train(const m2h_unet_enc_params* p, int convert_bin2mono, char* pk, cudaStream_t st) {
   const EncLayout PL = enc_layout();
-  rc = bn_zero_slots(W, 0, 5, st);
-  if (rc != M2H_OK) return rc;
-  // bf16 GEMM operands of the current weights (BatchNorm is NOT folded in train mode)
   for (int i = 0; i < 5; ++i) {
     const int cin_full = i == 0 ? (convert_bin2mono ? 32 : 33) : kEncCin[i];
     if (i == 0) {
@@ -205,6 +194,26 @@ extern "C" int m2h_unet_encoder_forward_train(const m2h_unet_enc_params* p, int6
     }
   }
   if (!convert_bin2mono) M2H_CUDA_CHECK(launch_pdl(pack_cls_w_kernel, dim3((9 * 64 + 127) / 128), dim3(128), (size_t)(0), st, p->conv_w[0], (float*)(pk + PL.cls_w), 64, 33));
+  M2H_CUDA_CHECK(cudaGetLastError());
+  return M2H_OK;
+}
+
+extern "C" int m2h_unet_encoder_forward_train(const m2h_unet_enc_params* p, int64_t* const* num_batches_tracked, int convert_bin2mono,
+                                              float bn_eps, float bn_momentum, const float* obs, const float* target_class_plus1,
+                                              const float* masks, const int64_t* mask_strides, int B, void* workspace, size_t workspace_bytes,
+                                              float* bottleneck_f32, void* stream) {
+  const int weights_packed = convert_bin2mono & M2H_UNET_WEIGHTS_PACKED;
+  convert_bin2mono &= 1;
+  int rc = check_train_args("m2h_unet_encoder_forward_train", B, workspace, workspace_bytes);
+  if (rc != M2H_OK) return rc;
+  if (!p || !obs || (convert_bin2mono ? (!masks || !mask_strides) : !target_class_plus1)) { m2h_set_error("m2h_unet_encoder_forward_train: null pointer"); return M2H_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const TW W = tw_make(workspace, B);
+  char* pk = W.base + W.off[TW_PACK_ENC];
+  const EncLayout PL = enc_layout();
+  rc = bn_zero_slots(W, 0, 5, st);
+  if (rc != M2H_OK) return rc;
+  if (!weights_packed) { rc = enc_pack_train(p, convert_bin2mono, pk, st); if (rc != M2H_OK) return rc; }
   PackInParams pp;
   pp.obs = obs; pp.masks = convert_bin2mono ? masks : nullptr; pp.x0 = W.bf(TW_X0S); pp.B = B; pp.x0_plain = W.bf(TW_X0P);
   for (int i = 0; i < 4; ++i) pp.ms[i] = convert_bin2mono ? (long long)mask_strides[i] : 0;
@@ -265,17 +274,7 @@ static void deconv_phases(UGLayer& g, int hin, int B) {
   g.Hout = g.Wout = 2 * hin; g.out_stride = 2; g.out_pad = 1;
 }
 
-extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int64_t* const* num_batches_tracked, int convert_bin2mono,
-                                              float bn_eps, float bn_momentum, int B, void* workspace, size_t workspace_bytes,
-                                              float* mask_out, void* stream) {
-  int rc = check_train_args("m2h_unet_decoder_forward_train", B, workspace, workspace_bytes);
-  if (rc != M2H_OK) return rc;
-  if (!p || !mask_out) { m2h_set_error("m2h_unet_decoder_forward_train: null pointer"); return M2H_ERR_ARG; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const TW W = tw_make(workspace, B);
-  char* pk = W.base + W.off[TW_PACK_DEC];
-  rc = bn_zero_slots(W, 5, 5, st);
-  if (rc != M2H_OK) return rc;
+static int dec_pack_train(const m2h_unet_dec_params* p, int convert_bin2mono, char* pk, cudaStream_t st) {
   const DecLayout PL = dec_layout();
   const int c_last = convert_bin2mono ? 16 : 32;
   for (int i = 0; i < 5; ++i) {
@@ -288,6 +287,25 @@ extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int6
     } else M2H_CUDA_CHECK(launch_pdl(pack_deconv_w_kernel, dim3(256), dim3(256), (size_t)(0), st, p->deconv_w[i], (__nv_bfloat16*)(pk + PL.w[i]), kDecCin[i], cout_real, kDecCoutBase[i]));
   }
   M2H_CUDA_CHECK(cudaGetLastError());
+  return M2H_OK;
+}
+
+extern "C" int m2h_unet_decoder_forward_train(const m2h_unet_dec_params* p, int64_t* const* num_batches_tracked, int convert_bin2mono,
+                                              float bn_eps, float bn_momentum, int B, void* workspace, size_t workspace_bytes,
+                                              float* mask_out, void* stream) {
+  const int weights_packed = convert_bin2mono & M2H_UNET_WEIGHTS_PACKED;
+  convert_bin2mono &= 1;
+  int rc = check_train_args("m2h_unet_decoder_forward_train", B, workspace, workspace_bytes);
+  if (rc != M2H_OK) return rc;
+  if (!p || !mask_out) { m2h_set_error("m2h_unet_decoder_forward_train: null pointer"); return M2H_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const TW W = tw_make(workspace, B);
+  char* pk = W.base + W.off[TW_PACK_DEC];
+  rc = bn_zero_slots(W, 5, 5, st);
+  if (rc != M2H_OK) return rc;
+  const DecLayout PL = dec_layout();
+  const int c_last = convert_bin2mono ? 16 : 32;
+  if (!weights_packed) { rc = dec_pack_train(p, convert_bin2mono, pk, st); if (rc != M2H_OK) return rc; }
   const int cat_slot[5] = {0, TW_CAT1, TW_CAT2, TW_CAT3, TW_CAT4}, zcat_slot[5] = {0, TW_ZCAT1, TW_ZCAT2, TW_ZCAT3, TW_ZCAT4};
   const int cat_ld[5] = {0, 128, 256, 512, 1024}, hp[5] = {0, 18, 10, 6, 4};
   // decoder layer i reads cat_{4-i+1}.. : in level = 5 - i (i >= 1), out level = 4 - i
@@ -401,6 +419,17 @@ static int wgrad_join(WgradFork* f, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+extern "C" int m2h_unet_pack_train_weights(const m2h_unet_enc_params* enc, const m2h_unet_dec_params* dec, int convert_bin2mono, int B,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_train_args("m2h_unet_pack_train_weights", B, workspace, workspace_bytes);
+  if (rc != M2H_OK) return rc;
+  if (!enc && !dec) { m2h_set_error("m2h_unet_pack_train_weights: null pointer"); return M2H_ERR_ARG; }
+  const TW W = tw_make(workspace, B);
+  if (enc) { rc = enc_pack_train(enc, convert_bin2mono & 1, W.base + W.off[TW_PACK_ENC], (cudaStream_t)stream); if (rc != M2H_OK) return rc; }
+  if (dec) { rc = dec_pack_train(dec, convert_bin2mono & 1, W.base + W.off[TW_PACK_DEC], (cudaStream_t)stream); if (rc != M2H_OK) return rc; }
+  return M2H_OK;
+}
+
 extern "C" int m2h_unet_decoder_backward(const m2h_unet_dec_params* p, int convert_bin2mono, const float* dmask, int B, void* workspace,
                                          size_t workspace_bytes, const m2h_unet_dec_grads* grads, void* stream) {
   int rc = check_train_args("m2h_unet_decoder_backward", B, workspace, workspace_bytes);

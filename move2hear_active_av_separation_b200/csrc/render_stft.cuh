@@ -15,6 +15,9 @@
 // cached monaural GT spectrograms (simulator_train.py:443-449, dataset.py:201-207).
 #pragma once
 #include "fft_radix.cuh"
+#ifndef M2H_HOST_EMU
+#include <cuda_bf16.h>
+#endif
 
 #define M2H_STFT_GROUPS 2
 #define M2H_STFT_THREADS (128 * M2H_STFT_GROUPS)
@@ -24,6 +27,7 @@
 #define M2H_STFT_S1 136
 #define M2H_STFT_BUF (16 * M2H_STFT_S1)
 #define M2H_STFT_POS2(i2) ((i2) * 8 + ((i2) >> 1))
+#define M2H_STFT_X0_LD 34             // halfwords per row of the x0 staging tile: 17 words, so a warp's 32 rows hit 32 banks
 
 enum {
   M2H_OUT_MIX_LOG1P = 1,   // mixture magnitude is written as log1p(mag)
@@ -38,6 +42,7 @@ struct StftParams {
   int fwave_channels;
   int B, K, N, T;          // T = 1 + (N - 1) / 512 frames (librosa centre framing with the odd n_fft)
   int n_signals;           // waves mode: 1 (mixture only) .. 1 + n_gt ; fwave mode: 1
+  int sig0;                // first signal of the launch: 0, or 1 = the GT spectrograms alone (the mixture comes from another launch)
   int n_gt;                // number of leading sources that get their own GT spectrogram (0, 1 or K)
   int flags;
   // outputs (null = not wanted).  All [.., 512, T, C] with C innermost like the reference's np.stack(axis=-1).
@@ -45,6 +50,11 @@ struct StftParams {
   void* mix_phase;         // [B, 512, T, 2]
   void* gt_mag;            // dataset layout: [B, n_gt, 512, T, 2] fp32 ; simulator layout: [B, n_gt, 512, T, 4] fp16
   int gt_interleaved_phase;// 1: simulator layout (mag_l, phase_l, mag_r, phase_r)
+  // the mixture's log1p magnitude as the separator's first-layer operand: bf16 [B][18][18][128], the space-to-depth, haloed
+  // NHWC form of the [B,512,32,2] observation that pack_input_kernel (m2h_unet.cu) otherwise builds from mix_mag - cell
+  // (h/2 + 1, t/2 + 1), channel ((h&1)*2 + (t&1))*32 + ear*16 + slice with h = bin % 32, slice = bin / 32
+  // (separator_cnn.py:84-90).  Needs T == 32; interior cells only (the zero border is the buffer owner's).
+  void* x0;
   void* f_mag;             // fwave mode: [B, 512, T, C] fp32
   void* f_phase;           // fwave mode: [B, 512, T, C] fp32 or null
   // inverse transform (m2h_istft_kernel): magnitude / phase [B, 512, T, C] fp32 -> waveforms [B, C, i_length] (pre-zeroed)
@@ -57,6 +67,7 @@ struct StftParams {
 struct StftSmem {
   float2 buf[M2H_STFT_GROUPS][M2H_STFT_BUF];
   float2 bf[2048];          // chirp spectrum, [k3][k1*16+k2] so that consecutive threads read consecutive entries
+  uint16_t x0st[M2H_STFT_GROUPS][32 * M2H_STFT_X0_LD];     // one frame's bf16 cells [h][ear*16 + slice] on their way to P.x0
 };
 // The samples [512*t - 512, 512*t + 512) of a frame (reflection at either end of the signal maps back inside this window) are
 // staged in the group's own FFT buffer before the first pass: sample j of the window lives at STFT_STAGE_POS(j); the
@@ -287,9 +298,29 @@ M2H_DEV void stft_p6(const StftParams& P, StftSmem& s, int tid, int b, int sig, 
     const float2 c = s.buf[grp][stft_pos(k == 0 ? 0 : M2H_NFFT - k)];
     const float2 xl = make_float2(a.x + c.x, a.y - c.y);
     const float2 xr = make_float2(a.y + c.y, c.x - a.x);
+#ifndef M2H_HOST_EMU
+    if (!F16 && P.x0 != nullptr && sig == 0) {       // bf16(log1p |X|): exactly what pack_input_kernel makes of the fp32 observation
+      uint16_t* st = s.x0st[grp] + (k & 31) * M2H_STFT_X0_LD + (k >> 5);
+      st[0] = __bfloat16_as_ushort(__float2bfloat16_rn(stft_log1p_fast(stft_abs<false>(xl))));
+      st[16] = __bfloat16_as_ushort(__float2bfloat16_rn(stft_log1p_fast(stft_abs<false>(xr))));
+      if (P.mix_mag == nullptr && P.mix_phase == nullptr) continue;
+    }
+#endif
     stft_emit<F16>(P, b, sig, k, t, xl, xr);
   }
 }
+#ifndef M2H_HOST_EMU
+// after the group barrier that follows P6: 128 threads move the frame's 32 x 64-byte cells, one 16-byte store each
+M2H_DEV void stft_x0_copy_out(const StftParams& P, StftSmem& s, int tid, int b, int t0) {
+  const int grp = tid >> 7, lt = tid & 127, t = t0 + grp;
+  if (t >= P.T) return;
+  const int h = lt >> 2, part = lt & 3;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(s.x0st[grp]) + h * (M2H_STFT_X0_LD / 2) + part * 4;
+  const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+  uint16_t* dst = reinterpret_cast<uint16_t*>(P.x0) + ((((size_t)b * 18 + (h >> 1) + 1) * 18 + (t >> 1) + 1) * 128 + ((h & 1) * 2 + (t & 1)) * 32 + part * 8);
+  *reinterpret_cast<uint4*>(dst) = v;
+}
+#endif
 
 template <bool F16>     // F16 = simulator dtype (P.flags & M2H_OUT_F16)
 M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables* M2H_RESTRICT gt, int cta, int n_ctas) {
@@ -303,7 +334,7 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
   const int n_items = P.B * P.n_signals * n_fgroups;
   for (int item = cta; item < n_items; item += n_ctas) {
     const int bs = item / n_fgroups, t0 = (item - bs * n_fgroups) * M2H_STFT_GROUPS;
-    const int b = bs / P.n_signals, sig = bs - b * P.n_signals;
+    const int b = bs / P.n_signals, sig = P.sig0 + bs - b * P.n_signals;
     {
       // each 128-thread group owns one frame pair and its buffer: only the group meets between the passes, the four
       // groups of a CTA drift apart freely
@@ -332,6 +363,9 @@ M2H_DEV void stft_cta_body(const StftParams& P, StftSmem& s, const M2hStftTables
       M2H_SYNC_GROUP128();
       M2H_FOR_THREADS(tid, M2H_STFT_THREADS) stft_p6<F16>(P, s, tid, b, sig, t0);
       M2H_SYNC_GROUP128();      // the next window is staged into the buffer P6 reads
+#ifndef M2H_HOST_EMU
+      if (!F16 && P.x0 != nullptr && sig == 0) stft_x0_copy_out(P, s, threadIdx.x, b, t0);    // the tile is rewritten five group barriers later
+#endif
     }
   }
 }

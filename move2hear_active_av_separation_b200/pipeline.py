@@ -30,6 +30,8 @@ class _Lane:
         self.len = torch.empty((chunk, K), dtype=torch.int32, device=device)
         self.tc = torch.empty((chunk, 1), dtype=torch.int64, device=device)
         self.waves = torch.empty((chunk, K, 2, N), dtype=torch.int16, device=device)
+        # the separator's first-layer operand, written by the STFT kernel (zero border established here, once)
+        self.x0 = torch.zeros((chunk, 18, 18, 128), dtype=torch.bfloat16, device=device) if 1 + (N - 1) // 512 == 32 else None
         self.done = torch.cuda.Event()
 
 
@@ -100,7 +102,10 @@ class SeparationPipeline:
                 lane.len[:n].copy_(rir_len[s:e], non_blocking=True)
                 lane.tc[:n].copy_(target_class[s:e], non_blocking=True)
                 waves = lane.rend.rir_convolve(lane.mono[:n], lane.rir[:n], lane.len[:n], out=lane.waves[:n])
-                mix, _, _ = lane.rend.stft_waves(waves)
+                if lane.x0 is not None:       # STFT -> bf16 space-to-depth operand: no fp32 observation, no repacking kernel
+                    mix = lane.rend.stft_waves_x0(waves, out=lane.x0[:n])
+                else:
+                    mix, _, _ = lane.rend.stft_waves(waves)
                 mask = self.dec(*self.enc({"mixed_bin_audio_mag": mix, "target_class": lane.tc[:n]}))
                 out[s:e].copy_(mask.permute(0, 3, 1, 2), non_blocking=True)
                 lane.done.record(lane.stream)

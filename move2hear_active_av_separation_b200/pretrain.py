@@ -33,14 +33,27 @@ def optimize_supervised_loss(optimizer, mixed_audio, pred_binSepMasks, gt_bin_ma
     return bin_loss, mono_loss, optimizer
 
 
-def train_step(actor_critic, optimizer, mixed_audio, gt_bin_mag, gt_mono_mag, target_class, grad_sync=None, side_stream=None):
+def prepack_weights(actor_critic, batch_size: int, device) -> None:
+    """Pack the bf16 GEMM operands of both separators for their next train-mode forward, on the current stream
+    (``separator_cnn.prepack_train_weights``): issued on a side stream, this takes ~20 short launches off the head of the step."""
+    from .separator_cnn import prepack_train_weights
+    ac = actor_critic
+    prepack_train_weights(ac.binSep_enc.passive_sep_encoder, ac.binSep_dec.passive_sep_decoder, batch_size, device)
+    prepack_train_weights(ac.bin2mono_enc.passive_sep_encoder, ac.bin2mono_dec.passive_sep_decoder, batch_size, device)
+
+
+def train_step(actor_critic, optimizer, mixed_audio, gt_bin_mag, gt_mono_mag, target_class, grad_sync=None, side_stream=None,
+               gt_ready=None):
     """One train-split iteration of ``PassiveTrainer.train`` (passive_trainer.py:218-245) -> ``(bin_loss, mono_loss)``.
 
     ``side_stream`` (optional ``torch.cuda.Stream``): the binaural-to-monaural converter consumes the DETACHED masks
     (passive_trainer.py:229-230), so its forward, its loss and its whole backward are independent of the binaural separator's
     loss and backward.  With a side stream the converter branch runs there (autograd replays a node on its forward's stream),
     next to the separator's backward on the calling stream: the step is ~230 short, latency-bound kernels, and the two chains
-    fill each other's gaps.  Same arithmetic, same results."""
+    fill each other's gaps.  Same arithmetic, same results.
+
+    ``gt_ready`` (optional ``torch.cuda.Event``, with ``side_stream``): the ground-truth spectrograms were produced on the side
+    stream and are complete at this event - only the losses read them, so the separator's forward does not wait for them."""
     import torch
     obs_batch = {"mixed_bin_audio_mag": mixed_audio, "target_class": target_class}
     pred_binSepMasks = actor_critic.get_binSepMasks(obs_batch)
@@ -54,6 +67,8 @@ def train_step(actor_critic, optimizer, mixed_audio, gt_bin_mag, gt_mono_mag, ta
     with torch.cuda.stream(side_stream):
         pred_mono = actor_critic.convert_bin2mono(pred_binSepMasks.detach(), mixed_audio=mixed_audio)
         mono_loss = l1_mask_loss(pred_mono, gt_mono_mag)
+    if gt_ready is not None:
+        main.wait_event(gt_ready)
     bin_loss = l1_mask_loss(pred_binSepMasks, gt_bin_mag, mixed_audio=mixed_audio)
     optimizer.zero_grad()
     main.wait_stream(side_stream)                       # the sum below reads the converter's loss
@@ -138,15 +153,40 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
 
     def _step(self):
+        import torch
+        gt_ready = None
+        if self.side is not None:
+            # prologue on the side stream, next to the render / the separator's forward on the main stream: the weight packing
+            # of both separators (depends on the parameters only) and the ground-truth spectrograms (read by the losses only)
+            main = torch.cuda.current_stream(self.device)
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                prepack_weights(self.actor_critic, self.target_class.shape[0], self.device)
+                packs_ready = torch.cuda.Event()
+                packs_ready.record(self.side)
         if self.rend is not None:
-            mono, rir, ln = self.static
-            out = self.rend.render(mono, rir, ln, n_gt=1)                  # dataset path (dataset.py:162-228): fp32 mixture + target GT
-            mixed, gt_bin = out["mix_mag"], out["gt"][:, 0]
-            gt_mono, _ = self.rend.stft_f32((mono[:, :1].float() * (1.0 / 32768)).contiguous())
+            mono, rir, ln = self.static                                     # dataset path (dataset.py:162-228): fp32 mixture + target GT
+            if self.side is None:
+                out = self.rend.render(mono, rir, ln, n_gt=1)
+                mixed, gt_bin = out["mix_mag"], out["gt"][:, 0]
+                gt_mono, _ = self.rend.stft_f32((mono[:, :1].float() * (1.0 / 32768)).contiguous())
+            else:
+                with torch.cuda.stream(self.side):                          # the clean clip's spectrogram does not need the convolution
+                    gt_mono, _ = self.rend.stft_f32((mono[:, :1].float() * (1.0 / 32768)).contiguous())
+                waves = self.rend.rir_convolve(mono, rir, ln)
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    _, _, gt = self.rend.stft_waves(waves, 1, gt_only=True)
+                    gt_bin = gt[:, 0]
+                    gt_ready = torch.cuda.Event()
+                    gt_ready.record(self.side)
+                mixed, _, _ = self.rend.stft_waves(waves, 0)
         else:
             mixed, gt_bin, gt_mono = self.static
+        if self.side is not None:
+            main.wait_event(packs_ready)
         bin_loss, mono_loss = train_step(self.actor_critic, self.optimizer, mixed, gt_bin, gt_mono, self.target_class, grad_sync=self.grad_sync,
-                                         side_stream=self.side)
+                                         side_stream=self.side, gt_ready=gt_ready)
         return bin_loss.detach(), mono_loss.detach()      # no reference to the autograd graph survives the step
 
     def __call__(self, *inputs, target_class=None):

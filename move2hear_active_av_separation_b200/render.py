@@ -26,6 +26,7 @@ N_BINS = 512
 SAMPLE_RATE = 16000
 FLAG_F16_OBS = 1
 FLAG_RAW_MAG = 2
+FLAG_GT_ONLY = 4
 _NP_DTYPE = {torch.float16: np.float16, torch.float32: np.float32, torch.int16: np.int16, torch.int32: np.int32}
 
 
@@ -74,24 +75,43 @@ class AudioRenderer:
         return waves
 
     def stft_waves(self, waves: torch.Tensor, n_gt: int = 0, sim_dtypes: bool = False, want_phase: bool = False,
-                   raw_mag: bool = False):
-        """STFT of the mixture (and of the first ``n_gt`` sources).  Returns ``(mix_mag, mix_phase|None, gt|None)``."""
+                   raw_mag: bool = False, gt_only: bool = False):
+        """STFT of the mixture (and of the first ``n_gt`` sources).  Returns ``(mix_mag, mix_phase|None, gt|None)``.
+        ``gt_only``: only the per-source spectrograms (``mix_mag`` is None) - the mixture comes from another launch."""
         waves = _need_cuda(waves, "waves", torch.int16)
         B, K, _, N = waves.shape
         T = 1 + (N - 1) // HOP_LENGTH
         dt = torch.float16 if sim_dtypes else torch.float32
-        mix = torch.empty((B, N_BINS, T, 2), dtype=dt, device=self.device)
-        phase = torch.empty((B, N_BINS, T, 2), dtype=dt, device=self.device) if want_phase else None
+        mix = None if gt_only else torch.empty((B, N_BINS, T, 2), dtype=dt, device=self.device)
+        phase = torch.empty((B, N_BINS, T, 2), dtype=dt, device=self.device) if want_phase and not gt_only else None
         gt = None
         if n_gt > 0:
             gt = torch.empty((B, n_gt, N_BINS, T, 4 if want_phase else 2), dtype=dt, device=self.device)
-        flags = (FLAG_F16_OBS if sim_dtypes else 0) | (FLAG_RAW_MAG if raw_mag else 0)
+        flags = (FLAG_F16_OBS if sim_dtypes else 0) | (FLAG_RAW_MAG if raw_mag else 0) | (FLAG_GT_ONLY if gt_only else 0)
         with torch.cuda.device(self.device):
             rc = self.lib.m2h_stft_waves(waves.data_ptr(), B, K, N, n_gt, 1 if want_phase else 0, flags,
-                                         mix.data_ptr(), phase.data_ptr() if phase is not None else None,
+                                         mix.data_ptr() if mix is not None else None, phase.data_ptr() if phase is not None else None,
                                          gt.data_ptr() if gt is not None else None, _stream_ptr(self.device))
         _lib.check(rc, "m2h_stft_waves")
         return mix, phase, gt
+
+    def stft_waves_x0(self, waves: torch.Tensor, out: Optional[torch.Tensor] = None, want_mag: bool = False):
+        """STFT of the mixture written straight into the binaural separator's first-layer layout (``m2h_stft_waves_x0``) ->
+        ``separator_cnn.PackedMixture``.  ``out``: a ZERO-INITIALISED bf16 ``[B,18,18,128]`` buffer to reuse (only interior
+        cells are written; a fresh zeroed one is allocated otherwise).  ``want_mag``: also write the fp32 observation."""
+        from .separator_cnn import PackedMixture
+        waves = _need_cuda(waves, "waves", torch.int16)
+        B, K, _, N = waves.shape
+        if out is None:
+            out = torch.zeros((B, 18, 18, 128), dtype=torch.bfloat16, device=self.device)
+        pm = PackedMixture(out, torch.empty((B, N_BINS, 32, 2), dtype=torch.float32, device=self.device) if want_mag else None)
+        if out.shape[0] != B or out.device != waves.device:
+            raise _lib.M2HError(f"stft_waves_x0: out is {tuple(out.shape)} on {out.device} for a batch of {B} on {waves.device}")
+        with torch.cuda.device(self.device):
+            rc = self.lib.m2h_stft_waves_x0(waves.data_ptr(), B, K, N, out.data_ptr(), pm.mag.data_ptr() if want_mag else None,
+                                            _stream_ptr(self.device))
+        _lib.check(rc, "m2h_stft_waves_x0")
+        return pm
 
     def render(self, mono, rir, rir_len, n_gt: int = 0, sim_dtypes: bool = False, want_phase: bool = False,
                raw_mag: bool = False):

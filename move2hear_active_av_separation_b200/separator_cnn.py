@@ -73,6 +73,31 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
+class PackedMixture:
+    """The mixture spectrogram in the layout the binaural separator's first layer reads: ``x0`` = bf16 ``[B,18,18,128]``
+    (space-to-depth, haloed NHWC of ``log1p |STFT|``), written directly by the STFT kernel (``AudioRenderer.stft_waves_x0``).
+    Passed as ``observations["mixed_bin_audio_mag"]`` to ``PassiveSepEncCNN`` (eval mode) instead of the fp32
+    ``[B,512,32,2]`` tensor: the observation skips its fp32 round trip through HBM and the repacking kernel.  ``mag`` holds the
+    fp32 observation when the caller also asked for it."""
+    __slots__ = ("x0", "mag")
+
+    def __init__(self, x0: torch.Tensor, mag: Optional[torch.Tensor] = None):
+        if x0.dtype != torch.bfloat16 or x0.dim() != 4 or tuple(x0.shape[1:]) != (18, 18, 128) or not x0.is_contiguous() or not x0.is_cuda:
+            raise _lib.M2HError(f"PackedMixture: expected a contiguous CUDA bf16 [B,18,18,128] tensor, got {x0.dtype} {tuple(x0.shape)}")
+        self.x0, self.mag = x0, mag
+
+    @property
+    def device(self):
+        return self.x0.device
+
+    @property
+    def shape(self):
+        return torch.Size((self.x0.shape[0], 512, 32, 2))
+
+    def size(self, dim: int):
+        return self.shape[dim]
+
+
 class _Lease:
     """Held by the tensors a forward pass returns; its death tells the pool that their workspace may be reused."""
     __slots__ = ("__weakref__",)
@@ -164,6 +189,8 @@ class _TrainWorkspace:
         self.offsets = list(offs)
         # bumped by every train-mode forward that writes this workspace; backward refuses to run on overwritten activations
         self.generation = 0
+        # set by prepack_train_weights, consumed (and cleared) by the next train-mode forward of the encoder / the decoder
+        self.prepacked_enc = self.prepacked_dec = False
         with torch.cuda.device(device):
             rc = lib.m2h_unet_train_workspace_init(B, self.buf.data_ptr(), self.nbytes, torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "m2h_unet_train_workspace_init")
@@ -186,6 +213,29 @@ class _TrainWorkspace:
             hw, c2 = self.CAT[lvl]
             out.append(self._map(base + lvl, hw, c2)[..., c2 // 2:].permute(0, 3, 1, 2))
         return out
+
+
+_WEIGHTS_PACKED = 2       # M2H_UNET_WEIGHTS_PACKED (include/m2h.h)
+
+
+def prepack_train_weights(enc, dec, B: int, device) -> None:
+    """Write the bf16 GEMM operands of an encoder / decoder pair into their train workspace on the CURRENT stream, ahead of the
+    pair's next train-mode forward (which then skips its own packing launches).  A training loop calls this on a side stream
+    while the step's audio is still being rendered and makes the forward's stream wait for it (``pretrain.GraphedTrainStep``).
+    Valid for exactly one forward of each module; the parameters must not change in between."""
+    lib = _lib.load()
+    device = torch.device(device)
+    for m in (enc, dec):
+        m._check_params_on(device)
+        m._check_train_dtypes()
+    ws = enc._train_workspace(B, device)
+    pe, keep_e = enc._param_struct()
+    pd, keep_d = dec._param_struct()
+    with torch.cuda.device(device):
+        rc = lib.m2h_unet_pack_train_weights(ctypes.byref(pe), ctypes.byref(pd), int(enc._convert_bin2mono), B, ws.buf.data_ptr(), ws.nbytes,
+                                             torch.cuda.current_stream(device).cuda_stream)
+    _lib.check(rc, "m2h_unet_pack_train_weights")
+    ws.prepacked_enc = ws.prepacked_dec = True
 
 
 def _check_generation(ctx, ws):
@@ -228,9 +278,11 @@ class _EncTrainFn(torch.autograd.Function):
         bott = torch.empty((B, 512), dtype=torch.float32, device=device)
         strides = (ctypes.c_int64 * 4)(*masks.stride()) if masks is not None else None
         bn = module.cnn[0][1]
+        mode = int(module._convert_bin2mono) | (_WEIGHTS_PACKED if ws.prepacked_enc else 0)
+        ws.prepacked_enc = False
         with torch.cuda.device(device):
             rc = lib.m2h_unet_encoder_forward_train(
-                ctypes.byref(p), nbt, int(module._convert_bin2mono), float(bn.eps), float(bn.momentum), obs.data_ptr(),
+                ctypes.byref(p), nbt, mode, float(bn.eps), float(bn.momentum), obs.data_ptr(),
                 cls.data_ptr() if cls is not None else None, masks.data_ptr() if masks is not None else None, strides, B,
                 ws.buf.data_ptr(), ws.nbytes, bott.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "m2h_unet_encoder_forward_train")
@@ -280,8 +332,10 @@ class _DecTrainFn(torch.autograd.Function):
         C = module._n_out_audio // SLICE_FACTOR
         out = torch.empty((B, C, 512, 32), dtype=torch.float32, device=device)
         bn = module.cnn[0][1]
+        mode = int(module._convert_bin2mono) | (_WEIGHTS_PACKED if ws.prepacked_dec else 0)
+        ws.prepacked_dec = False
         with torch.cuda.device(device):
-            rc = lib.m2h_unet_decoder_forward_train(ctypes.byref(p), nbt, int(module._convert_bin2mono), float(bn.eps), float(bn.momentum),
+            rc = lib.m2h_unet_decoder_forward_train(ctypes.byref(p), nbt, mode, float(bn.eps), float(bn.momentum),
                                                     B, ws.buf.data_ptr(), ws.nbytes, out.data_ptr(),
                                                     torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "m2h_unet_decoder_forward_train")
@@ -480,7 +534,14 @@ class PassiveSepEncCNN(_PackedModule):
         self._require_cuda(device)
         self._check_params_on(device)
         _check_device(device, masks=masks, target_class=None if self._convert_bin2mono else observations["target_class"])
-        obs = _f32(obs)
+        packed_obs = obs if isinstance(obs, PackedMixture) else None
+        if packed_obs is not None:
+            if self._convert_bin2mono or self.training:
+                if obs.mag is None:
+                    raise _lib.M2HError("a PackedMixture without .mag feeds the binaural separator in eval mode only")
+                obs, packed_obs = obs.mag, None
+        if packed_obs is None:
+            obs = _f32(obs)
         B = obs.size(0)
         if tuple(obs.shape[1:]) != (512, 32, 2):
             raise _lib.M2HError(f"expected a [B,512,32,2] spectrogram, got {tuple(obs.shape)}")
@@ -505,9 +566,13 @@ class PassiveSepEncCNN(_PackedModule):
             keep.append(cls)
             cls_ptr = cls.data_ptr()
         with torch.cuda.device(device):
-            rc = lib.m2h_unet_encoder_forward(packed.data_ptr(), int(self._convert_bin2mono), obs.data_ptr(), cls_ptr,
-                                              mask_ptr, strides, B, ws.buf.data_ptr(), ws.nbytes, bott.data_ptr(),
-                                              torch.cuda.current_stream(device).cuda_stream)
+            if packed_obs is not None:
+                rc = lib.m2h_unet_encoder_forward_x0(packed.data_ptr(), packed_obs.x0.data_ptr(), cls_ptr, B, ws.buf.data_ptr(), ws.nbytes,
+                                                     bott.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+            else:
+                rc = lib.m2h_unet_encoder_forward(packed.data_ptr(), int(self._convert_bin2mono), obs.data_ptr(), cls_ptr,
+                                                  mask_ptr, strides, B, ws.buf.data_ptr(), ws.nbytes, bott.data_ptr(),
+                                                  torch.cuda.current_stream(device).cuda_stream)
         _lib.check(rc, "m2h_unet_encoder_forward")
         skips = ws.skips()
         bott._m2h_ws = ws                              # lets the partner decoder reuse the activations in place

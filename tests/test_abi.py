@@ -23,7 +23,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, n), n
         assert n in _lib.SIGNATURES, "ctypes signature missing for " + n
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.m2h_abi_version() == 3
+    assert lib.m2h_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_gpu():

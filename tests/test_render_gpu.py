@@ -250,3 +250,18 @@ def test_conv_and_stft_random_shapes(rend):
                     want = np.abs(R.stft_librosa(mixed[ear]))
                     got = out["mix_mag"][b, :, :, ear].cpu().numpy()
                     assert got.shape == want.shape and rel_l2(got, want) < 1e-4, (N, Lmax, K, b, ear)
+
+
+def test_stft_gt_only_launch_equals_combined_launch(rend):
+    """M2H_RENDER_GT_ONLY: the per-source spectrograms from their own launch (a training step runs it on a side stream) are
+    bit-identical to those of the combined mixture + GT launch."""
+    mono = R.synth_monos(5, 3, seed=77)
+    rir, ln = R.synth_rirs(5, 3, L=9000, seed=78, ragged=True)
+    waves = rend.rir_convolve(torch.from_numpy(mono).cuda(), torch.from_numpy(rir).cuda(), torch.from_numpy(ln).cuda())
+    for sim in (False, True):
+        mix, _, gt = rend.stft_waves(waves, 2, sim_dtypes=sim, want_phase=sim)
+        none, _, gt2 = rend.stft_waves(waves, 2, sim_dtypes=sim, want_phase=sim, gt_only=True)
+        assert none is None and torch.equal(gt, gt2)
+        mix0, _, _ = rend.stft_waves(waves, 0, sim_dtypes=sim)
+        assert torch.equal(mix, mix0)
+    assert rend.stft_waves(waves, 0, gt_only=True) == (None, None, None)
