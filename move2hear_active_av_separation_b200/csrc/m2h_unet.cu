@@ -586,6 +586,11 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
   }
   if (L.n_slab_stages > US_MAX_STAGES) L.n_slab_stages = US_MAX_STAGES;
   // issue records (unet_slab.cuh::USIssue): what the MMA-issuing warp reads, one item ahead of its use
+  if (L.n_b_stages) {                 // the ring depth divides the item count: an item's stage and parity bit are launch constants
+    while (L.n_b_stages > 2 && L.n_items % L.n_b_stages != 0) --L.n_b_stages;
+    if (L.n_items % L.n_b_stages != 0) { m2h_set_error("slab layer: %d items do not fill a weight ring", L.n_items); return M2H_ERR_ARG; }
+  }
+  const uint32_t desc_lo0 = 1u << 16;         // low word of ug::smem_desc_sw128(0): LBO field = 1
   for (int i = 0; i < L.n_items; ++i) {
     const USItem& it = L.items[i];
     USIssue& r = L.rec[i];
@@ -593,13 +598,15 @@ static int launch_slab(USLayer& L, const __nv_bfloat16* in, int in_ld, int Hp, i
     if (it.n_k16 != 2 && it.n_k16 != 4) { m2h_set_error("slab layer: unsupported K16 count %d", (int)it.n_k16); return M2H_ERR_ARG; }
     const bool first_of_chunk = i == 0 || L.items[i - 1].chunk != it.chunk;
     const bool last_of_chunk = i + 1 == L.n_items || L.items[i + 1].chunk != it.chunk;
-    r.a_off16 = (uint32_t)(it.a_shift * 128 + it.a_k16 * 32) >> 4;
-    r.b_off16 = L.n_b_stages ? 0u : (uint32_t)(it.w_row * 128) >> 4;
-    r.ctl = (uint32_t)it.n_k16 | ((uint32_t)it.n_parts << 8) | (first_of_chunk ? 1u << 16 : 0u) | (last_of_chunk ? 1u << 17 : 0u);
+    const int stage = L.n_b_stages ? i % L.n_b_stages : 0, turn = L.n_b_stages ? i / L.n_b_stages : 0;
+    r.a_off16 = ((uint32_t)(it.a_shift * 128 + it.a_k16 * 32) >> 4) + desc_lo0;
+    r.b_off16 = L.n_b_stages ? (uint32_t)stage * (US_B_STAGE_BYTES >> 4) : (uint32_t)(it.w_row * 128) >> 4;
+    r.ctl = (uint32_t)it.n_k16 | ((uint32_t)it.n_parts << 8) | (first_of_chunk ? 1u << 16 : 0u) | (last_of_chunk ? 1u << 17 : 0u) | ((uint32_t)(turn & 1) << 18);
+    r.b_bar = 8u * (uint32_t)stage;
     for (int p = 0; p < it.n_parts; ++p) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(it.part[p].n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t pw = (uint32_t)it.part[p].tmem_col | ((uint32_t)(it.part[p].b_row * 8) << 16) | (it.part[p].init ? 0u : 1u << 31);
-      if (p == 0) { r.idesc0 = idesc; r.p0 = pw; } else { r.idesc1 = idesc; r.p1 = pw; }
+      const uint32_t col = (uint32_t)it.part[p].tmem_col, brow = (uint32_t)(it.part[p].b_row * 8) + desc_lo0, acc = it.part[p].init ? 0u : 1u;
+      if (p == 0) { r.idesc0 = idesc; r.col0 = col; r.brow0 = brow; r.acc0 = acc; } else { r.idesc1 = idesc; r.col1 = col; r.brow1 = brow; r.acc1 = acc; }
     }
   }
   if (L.n_items > US_MAX_ITEMS || L.slab_rows > 256 || L.n_slab_stages < 2 || L.tmem_cols > 512 || w_rows > 32767) { m2h_set_error("slab layer: unsupported geometry"); return M2H_ERR_ARG; }

@@ -126,7 +126,8 @@ static int launch_wgrad(const __nv_bfloat16* dense, int d_ld, int d_coff, int Cd
   L.nb = 128 / (Hq * L.rows_y);
   L.n_kchunks = ((B + L.nb - 1) / L.nb) * (Hq / L.rows_y);
   L.s_sw64 = Cs <= 32 ? 1 : 0;
-  L.BN = Cs <= 32 ? 32 : (Cs <= 64 ? 64 : 128);
+  L.BN = Cs <= 32 ? 32 : 64;
+  L.TC = 256 / L.BN;
   L.tap_mask = 0;
   for (int kh = 0; kh < 4; ++kh)
     for (int kw = 0; kw < 4; ++kw) {
@@ -136,12 +137,20 @@ static int launch_wgrad(const __nv_bfloat16* dense, int d_ld, int d_coff, int Cd
     }
   L.dw = dw;
   const int m_tiles = (Cd + 127) / 128, n_tiles = (Cs + L.BN - 1) / L.BN;
-  int live_taps = 0;
-  for (int t = 0; t < 16; ++t) live_taps += (L.tap_mask >> t) & 1;
+  int live_taps = 0;                  // tap groups (CTAs along grid.x) with at least one live tap
+  for (int t = 0; t < 16; t += L.TC) live_taps += ((L.tap_mask >> t) & ((1 << L.TC) - 1)) != 0;
   // split the positions so that ~2 waves of CTAs are in flight
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int ksplit = (2 * sms + live_taps * m_tiles * n_tiles - 1) / (live_taps * m_tiles * n_tiles);
+  // Position split: every slice adds a full copy of the gradient tile to L2 with atomics, and the launch runs next to the
+  // data-gradient chain on another stream - measured at B = 256 (one B200): 2 waves of CTAs 3.09 ms per step, 1 wave 2.94,
+  // half a wave 2.88, a third 2.85 (tap groups: 2.73), a ninth 3.14.  M2H_WGRAD_TARGET_CTAS overrides.
+  static int target = -1, target32 = -1;
+  if (target < 0) { const char* e = getenv("M2H_WGRAD_TARGET_CTAS"); target = e && atoi(e) > 0 ? atoi(e) : sms / 3; }
+  if (target32 < 0) { const char* e = getenv("M2H_WGRAD_TARGET_CTAS_32"); target32 = e && atoi(e) > 0 ? atoi(e) : sms; }
+  // the 32-channel layers (first encoder / last decoder layer: 65536 positions at B = 256, a 128 x 32 x 16 gradient) are all
+  // main loop and almost no epilogue: they take a full wave
+  int ksplit = ((Cs <= 32 ? target32 : target) + live_taps * m_tiles * n_tiles - 1) / (live_taps * m_tiles * n_tiles);
   if (ksplit < 1) ksplit = 1;
   if (ksplit > L.n_kchunks) ksplit = L.n_kchunks;
   L.kchunks_per_cta = (L.n_kchunks + ksplit - 1) / ksplit;
@@ -164,7 +173,7 @@ static int launch_wgrad(const __nv_bfloat16* dense, int d_ld, int d_coff, int Cd
     rc = make_tmap_nd(&tm_s, sampled, 5, dims, strides, box, L.s_sw64 != 0);
     if (rc != M2H_OK) return rc;
   }
-  dim3 grid(16, m_tiles * n_tiles, ksplit);
+  dim3 grid(16 / L.TC, m_tiles * n_tiles, ksplit);
   M2H_CUDA_CHECK(launch_pdl(unet_wgrad_kernel, dim3(grid), dim3(WG_THREADS), (size_t)(wg::kSmemBytes), st, tm_d, tm_s, L));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;

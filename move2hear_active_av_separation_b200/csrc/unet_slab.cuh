@@ -43,15 +43,17 @@ struct USItem {                       // one weight tile and the MMAs that consu
   USPart part[2];
 };
 
-// Issue record of an item: everything the MMA-issuing warp needs, pre-combined on the host into eight 32-bit words so that
-// one record is two 16-byte constant-bank loads into uniform registers (fetched one item ahead of its use).
-struct alignas(32) USIssue {
-  uint32_t a_off16;                   // (a_shift*128 + a_k16*32) >> 4, relative to the slab stage
-  uint32_t b_off16;                   // resident weights: (w_row*128) >> 4; streamed: 0 (relative to the ring stage)
-  uint32_t ctl;                       // n_k16 | n_parts << 8 | first_of_chunk << 16 | last_of_chunk << 17
-  uint32_t pad;
-  uint32_t idesc0, p0;                // part 0: instruction descriptor; tmem_col | (b_row*8) << 16 | accumulate-from-start << 31
-  uint32_t idesc1, p1;                // part 1
+// Issue record of an item: everything the MMA-issuing warp needs, pre-combined on the host into twelve 32-bit words so that
+// one record is three 16-byte constant-bank loads into uniform registers (fetched one item ahead of its use) and the issue
+// path holds no shifts, masks or ring arithmetic (ncu r2: the issuing warps, not the tensor pipe, bound the slab layers -
+// ~100 uniform-datapath instructions and ~830 cycles per item).
+struct alignas(16) USIssue {
+  uint32_t a_off16;                   // ((a_shift*128 + a_k16*32) >> 4) + low descriptor word constant; + slab stage address >> 4 = A descriptor low word
+  uint32_t b_off16;                   // resident weights: (w_row*128) >> 4; streamed: ring stage (item % n_b_stages) * stage bytes >> 4
+  uint32_t ctl;                       // n_k16 | n_parts << 8 | first_of_chunk << 16 | last_of_chunk << 17 | ring parity of the item << 18
+  uint32_t b_bar;                     // streamed: 8 * ring stage (byte offset of the stage's full / empty barriers)
+  uint32_t idesc0, col0, brow0, acc0; // part 0: instruction descriptor, accumulator column, (b_row*128) >> 4 + low descriptor word constant, accumulate-from-start
+  uint32_t idesc1, col1, brow1, acc1; // part 1
 };
 struct USLayer {
   int n_items, n_chunks, n_tiles;
@@ -241,73 +243,80 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     // registers: ~45 instructions and several R2UR round trips per MMA, ~300 cycles - the tensor pipe idled).
     const int q = warp == 8 ? 0 : 1;
     if (resident) { ug::mbar_wait(b_full(0), 0); ug::tc_fence_after(); }
-    int bs = 0;                                   // weight ring position of the NEXT item (both issuers walk every pair)
-    uint32_t b_par = 0;
     const uint64_t desc_hi32 = ug::smem_desc_sw128(0) & 0xFFFFFFFF00000000ull;
-    const uint32_t desc_lo0 = (uint32_t)(ug::smem_desc_sw128(0) & 0xFFFFFFFFull);
+    const uint32_t slab0_16 = slab0 >> 4, slab_bytes16 = (uint32_t)L.slab_bytes >> 4, b0_16 = b0 >> 4;
+    const uint32_t b_full0 = b_full(0), b_empty0 = b_empty(0);
+    // weight ring: n_items is a multiple of the ring depth (host), so an item's stage is fixed and its parity is the pair's
+    // base parity xor a per-item bit; slab ring: this issuer's boxes are NS-periodic with step 2 (1 in a ragged last pair)
+    const uint32_t turns_odd = NB ? (uint32_t)(L.n_items / NB) & 1u : 0u;
+    uint32_t pair_par = 0;
+    int cs_next = q;                               // ring position of this issuer's next slab box (NS >= 2 > q)
+    uint32_t s_par = 0;
+    const uint4* recs = reinterpret_cast<const uint4*>(&L.rec[0]);
     for (int p = 0; p < n_pairs; ++p) {
       const bool active = 2 * p + q < n_my;        // the last pair may hold a single tile: issuer 1 then only recycles weight stages
       const bool full = 2 * p + 1 < n_my;
       const int buf = q + 2 * (p % bufs_per_q), use = p / bufs_per_q;
       if (active && use >= 1) { ug::mbar_wait(t_empty(buf), (uint32_t)((use - 1) & 1)); ug::tc_fence_after(); }
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * L.tile_cols);
-      const int cnt0 = p * 2 * L.n_chunks;          // slab boxes issued before this pair (every earlier pair is full)
-      int cs = 0, chunk = -1;
+      const int s_step = full ? 2 : 1;
+      int cs = 0;
       uint32_t a_base16 = 0;
-      uint4 ra = *reinterpret_cast<const uint4*>(&L.rec[0]), rb = *(reinterpret_cast<const uint4*>(&L.rec[0]) + 1);
-      for (int item = 0; item < L.n_items; ++item) {
-        const uint4 ca = ra, cbw = rb;
-        if (item + 1 < L.n_items) {       // next record: its constant-bank latency hides behind this item's MMAs
-          ra = *reinterpret_cast<const uint4*>(&L.rec[item + 1]);
-          rb = *(reinterpret_cast<const uint4*>(&L.rec[item + 1]) + 1);
+      auto do_item = [&](const uint4 r0, const uint4 r1, const uint4 r2) {
+        const uint32_t ctl = r0.z;
+        if (active && (ctl & (1u << 16))) {       // first item of a chunk: its slab must have landed
+          cs = cs_next;
+          ug::mbar_wait(s_full(cs), s_par);
+          a_base16 = slab0_16 + (uint32_t)cs * slab_bytes16;
+          cs_next += s_step;
+          if (cs_next >= NS) { cs_next -= NS; s_par ^= 1u; }       // the wait above used the parity of the box it waited for
+          ug::tc_fence_after();
         }
-        const uint32_t ctl = ca.z;
-        if (ctl & (1u << 16)) {           // first item of a chunk: its slab must have landed
-          ++chunk;
-          if (active) {
-            const int cnt = cnt0 + (full ? 2 * chunk + q : chunk);
-            cs = cnt % NS;
-            ug::mbar_wait(s_full(cs), (uint32_t)((cnt / NS) & 1));
-            a_base16 = (slab0 + (uint32_t)cs * (uint32_t)L.slab_bytes) >> 4;
-            ug::tc_fence_after();
-          }
-        }
-        int cb = 0;
-        uint32_t b_base16 = (b0 >> 4) + ca.y;
         if (!resident) {
-          ug::mbar_wait(b_full(bs), b_par);
-          cb = bs;
-          b_base16 = (b0 + (uint32_t)bs * US_B_STAGE_BYTES) >> 4;
-          if (++bs == NB) { bs = 0; b_par ^= 1u; }
+          ug::mbar_wait(b_full0 + r0.w, pair_par ^ ((ctl >> 18) & 1u));
           ug::tc_fence_after();
         }
         if (active) {
-          // descriptor = (hi word, constant) : (lo word = LBO bit | start address >> 4); shared-memory addresses are < 2^18, so a
-          // K16 step is one 32-bit add of 2 to the lo word
-          const uint32_t a_lo = (a_base16 + ca.x) | desc_lo0;
-          const uint32_t nk = ctl & 0xffu, np = (ctl >> 8) & 0xffu;
-#pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            if (pp < (int)np) {
-              const uint32_t idesc = pp ? cbw.z : cbw.x, pw = pp ? cbw.w : cbw.y;
-              const uint32_t d = tmem_d + (pw & 0xffffu);
-              const uint32_t b_lo = (b_base16 + ((pw >> 16) & 0x7fffu)) | desc_lo0;
-              const uint32_t acc0 = pw >> 31;
-              if (nk == 4) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u * k), desc_hi32 | (uint64_t)(b_lo + 2u * k), idesc, k ? 1u : acc0);
-              } else {
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                  us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u * k), desc_hi32 | (uint64_t)(b_lo + 2u * k), idesc, k ? 1u : acc0);
-              }
+          // descriptor = (hi word, constant) : (lo word = LBO bit | start address >> 4); shared-memory addresses are < 2^18, so the
+          // constant bits never meet a carry and a K16 step is one 32-bit add of 2 to the lo word
+          const uint32_t a_lo = a_base16 + r0.x;
+          const uint32_t b_base16 = b0_16 + r0.y;
+          const bool nk4 = (ctl & 0xffu) == 4u;
+          {
+            const uint32_t d = tmem_d + r1.y, b_lo = b_base16 + r1.z;
+            us::umma_bf16_elect(d, desc_hi32 | (uint64_t)a_lo, desc_hi32 | (uint64_t)b_lo, r1.x, r1.w);
+            us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u), desc_hi32 | (uint64_t)(b_lo + 2u), r1.x, 1u);
+            if (nk4) {
+              us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 4u), desc_hi32 | (uint64_t)(b_lo + 4u), r1.x, 1u);
+              us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 6u), desc_hi32 | (uint64_t)(b_lo + 6u), r1.x, 1u);
+            }
+          }
+          if (ctl & (2u << 8)) {
+            const uint32_t d = tmem_d + r2.y, b_lo = b_base16 + r2.z;
+            us::umma_bf16_elect(d, desc_hi32 | (uint64_t)a_lo, desc_hi32 | (uint64_t)b_lo, r2.x, r2.w);
+            us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 2u), desc_hi32 | (uint64_t)(b_lo + 2u), r2.x, 1u);
+            if (nk4) {
+              us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 4u), desc_hi32 | (uint64_t)(b_lo + 4u), r2.x, 1u);
+              us::umma_bf16_elect(d, desc_hi32 | (uint64_t)(a_lo + 6u), desc_hi32 | (uint64_t)(b_lo + 6u), r2.x, 1u);
             }
           }
         }
-        if (!resident) us::umma_commit_elect(b_empty(cb));      // arrives at once when this warp issued nothing
+        if (!resident) us::umma_commit_elect(b_empty0 + r0.w);      // arrives at once when this warp issued nothing
         if (active && (ctl & (1u << 17))) us::umma_commit_elect(s_empty(cs));
+      };
+      // two items per trip, records fetched one item ahead: their constant-bank latency hides behind the previous item's MMAs and
+      // no register rotation is needed
+      uint4 a0 = recs[0], a1 = recs[1], a2 = recs[2];
+      const int last = L.n_items - 1;
+      for (int item = 0; item < L.n_items; item += 2) {
+        const int i1 = item + 1 < last ? item + 1 : last;       // clamped: an odd item count re-reads the last record and skips it
+        const uint4 c0 = recs[3 * i1], c1 = recs[3 * i1 + 1], c2 = recs[3 * i1 + 2];
+        do_item(a0, a1, a2);
+        const int i2 = item + 2 < last ? item + 2 : last;
+        a0 = recs[3 * i2]; a1 = recs[3 * i2 + 1]; a2 = recs[3 * i2 + 2];
+        if (item + 1 < L.n_items) do_item(c0, c1, c2);
       }
+      pair_par ^= turns_odd;
       if (active) us::umma_commit_elect(t_full(buf));
     }
   } else {

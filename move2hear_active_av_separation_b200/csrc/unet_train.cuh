@@ -356,10 +356,14 @@ __global__ void wgrad_cls_kernel(const __nv_bfloat16* __restrict__ dz, int ld, i
 // The reduction runs over positions, which are the slow axis of both NHWC operands: both tcgen05 operands are MN-major
 // (channels contiguous), read straight from TMA boxes [128 positions][64 channels] (128B swizzle; 32-channel tensors use
 // [128][32] boxes with the 64B swizzle).  The sampled operand's stride-2 window is a dense box of the 5-D view
-// [B][Hp/2][2][Wp/2][2*ld] of its haloed map (pixel parity = tap parity).  One CTA = (tap, 128 dense channels, BN sampled
-// channels, a slice of the positions); partial sums are added to the fp32 gradient with red.global.add.
+// [B][Hp/2][2][Wp/2][2*ld] of its haloed map (pixel parity = tap parity).
+// One CTA = (group of TC consecutive taps, 128 dense channels, BN <= 64 sampled channels, a slice of the positions): the dense
+// box of a position chunk is loaded once and multiplied with the TC shifted sampled boxes into TC accumulators (TC * BN = 256
+// TMEM columns).  The taps of a group are adjacent in the [..][4][4] weight tensor, so partial sums leave as 16-byte vector
+// reductions (red.global.add.v4.f32) - the first version ran one tap per CTA and paid one 4-byte atomic, each on its own
+// 32-byte sector, per gradient element and position slice: the L2 atomic rate, not the tensor pipe, set its time.
 #define WG_THREADS 192
-#define WG_STAGES 3
+#define WG_STAGES 2
 struct WGLayer {
   int Cd, Cs;               // dense / sampled channel counts (gradient is [Cd][Cs_full][16])
   int Cs_full;              // second dimension of the weight tensor (33 for encoder layer 0)
@@ -370,7 +374,8 @@ struct WGLayer {
   int nb, rows_y;           // box = [nb images][rows_y rows][Hq columns] = 128 positions (zero-filled past the batch)
   int n_kchunks;            // position chunks in total: ceil(B / nb) * (Hq / rows_y)
   int kchunks_per_cta;
-  int BN;                   // sampled channels per CTA (32 | 64 | 128)
+  int BN;                   // sampled channels per CTA (32 | 64)
+  int TC;                   // taps per CTA (256 / BN: 8 | 4), taps blockIdx.x * TC ..
   int s_sw64;               // sampled operand uses 32-channel boxes / 64B swizzle
   int tap_mask;             // bit (kh*4+kw): tap can touch the image (1x1 / 2x2 maps only see the centre taps)
   float* dw;
@@ -388,6 +393,9 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // MN-major operand: 64-channel groups (128B swizzle) lbo bytes apart, 8-position groups 1024 B apart; or one 32-channel
 // group (64B swizzle), 8-position groups 512 B apart
 __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo_bytes, bool sw64) {
@@ -399,7 +407,8 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo_bytes, b
   d |= (uint64_t)(sw64 ? 4 : 2) << 61;
   return d;
 }
-constexpr int kStageBytes = 16384 * 2 + 16384 * 2;      // dense: 2 x [128][64]; sampled: up to 2 x [128][64]
+constexpr int kDenseBytes = 16384 * 2;                   // dense: 2 x [128][64]
+constexpr int kStageBytes = kDenseBytes + 65536;         // + TC sampled boxes: 4 x [128][64] or 8 x [128][32]
 constexpr int kSmemBytes = WG_STAGES * kStageBytes + 1024 + 256;
 }  // namespace wg
 
@@ -419,16 +428,17 @@ unet_wgrad_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constan
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  // blockIdx.x = tap, blockIdx.y = (m tile, n tile), blockIdx.z = position slice
-  const int tap = blockIdx.x, kh = tap >> 2, kw = tap & 3;
+  // blockIdx.x = tap group, blockIdx.y = (m tile, n tile), blockIdx.z = position slice
+  const int tap0 = blockIdx.x * L.TC;
   const int n_tiles_n = (L.Cs + L.BN - 1) / L.BN;
   const int mt = blockIdx.y / n_tiles_n, nt = blockIdx.y % n_tiles_n;
   const int m0 = mt * 128, n0 = nt * L.BN;
   const int kc0 = blockIdx.z * L.kchunks_per_cta;
   int kc1 = kc0 + L.kchunks_per_cta;
   if (kc1 > L.n_kchunks) kc1 = L.n_kchunks;
-  const bool live = ((L.tap_mask >> tap) & 1) && kc0 < kc1;
-  const uint32_t tmem_cols = L.BN < 32 ? 32u : (uint32_t)L.BN;
+  const uint32_t grp_mask = ((uint32_t)L.tap_mask >> tap0) & ((1u << L.TC) - 1u);      // live taps of this group
+  const bool live = grp_mask != 0 && kc0 < kc1;
+  const uint32_t tmem_cols = 256;
 
   if (tid == 0) {
     for (int s = 0; s < WG_STAGES; ++s) { ug::mbar_init(full_bar(s), 1); ug::mbar_init(empty_bar(s), 1); }
@@ -445,9 +455,8 @@ unet_wgrad_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const int chunks_per_img_grp = L.Hq / L.rows_y;          // position chunks per group of nb images
   const uint32_t s_box_bytes = L.s_sw64 ? 128u * 64u : 128u * 128u;
-  const int n_sboxes = L.s_sw64 ? 1 : (L.BN + 63) / 64;
   const int n_dboxes = (L.Cd - m0) >= 128 ? 2 : 1;
-  const uint32_t stage_tx = (uint32_t)n_dboxes * 16384u + (uint32_t)n_sboxes * s_box_bytes;
+  const uint32_t stage_tx = (uint32_t)n_dboxes * 16384u + (uint32_t)__popc(grp_mask) * s_box_bytes;
 
   if (live) {
     if (warp == 5) {
@@ -463,12 +472,15 @@ unet_wgrad_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constan
           for (int j = 0; j < n_dboxes; ++j)     // dense: interior pixels (1 + y0 .., 1 ..) of images b0 ..
             wg::tma_load_4d(st + j * 16384, &tm_d, L.d_coff + m0 + j * 64, L.d_pad, L.d_pad + y0, b0, full_bar(s));
           // sampled: pixel (2y + kh, 2x + kw) of the haloed map = cell (y + (kh >> 1), x + (kw >> 1)), parity (kh & 1, kw & 1)
-          for (int j = 0; j < n_sboxes; ++j)
-            wg::tma_load_5d(st + 32768 + j * 16384, &tm_s, (kw & 1) * L.s_ld + L.s_coff + n0 + j * 64, (kw >> 1), (kh & 1), y0 + (kh >> 1), b0, full_bar(s));
+          for (int j = 0; j < L.TC; ++j) {
+            if (!((grp_mask >> j) & 1u)) continue;
+            const int kh = (tap0 + j) >> 2, kw = (tap0 + j) & 3;
+            wg::tma_load_5d(st + wg::kDenseBytes + j * s_box_bytes, &tm_s, (kw & 1) * L.s_ld + L.s_coff + n0, (kw >> 1), (kh & 1), y0 + (kh >> 1), b0, full_bar(s));
+          }
         }
       }
     } else if (warp == 4) {
-      // ------------------------------ MMA issuer: D[m, n] += dense[k, m] * sampled[k, n], both MN-major ------------------------------
+      // ------------------------------ MMA issuer: D_j[m, n] += dense[k, m] * sampled_j[k, n], both MN-major ------------------------------
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(L.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int it = 0;
       for (int kc = kc0; kc < kc1; ++kc, ++it) {
@@ -476,28 +488,41 @@ unet_wgrad_kernel(const __grid_constant__ CUtensorMap tm_d, const __grid_constan
         ug::mbar_wait(full_bar(s), (uint32_t)((it / WG_STAGES) & 1));
         ug::tc_fence_after();
         const uint32_t st = tiles + s * wg::kStageBytes;
+        for (int j = 0; j < L.TC; ++j) {
+          if (!((grp_mask >> j) & 1u)) continue;
+          const uint32_t sb = st + wg::kDenseBytes + j * s_box_bytes, d = tmem_base + (uint32_t)(j * L.BN);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {          // 128 positions = 8 steps of K = 16
-          const uint64_t adesc = wg::desc_mn(st + k * 2048, 16384, false);
-          const uint64_t bdesc = L.s_sw64 ? wg::desc_mn(st + 32768 + k * 1024, 0, true) : wg::desc_mn(st + 32768 + k * 2048, 16384, false);
-          us::umma_bf16_elect(tmem_base, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {          // 128 positions = 8 steps of K = 16
+            const uint64_t adesc = wg::desc_mn(st + k * 2048, 16384, false);
+            const uint64_t bdesc = L.s_sw64 ? wg::desc_mn(sb + k * 1024, 0, true) : wg::desc_mn(sb + k * 2048, 16384, false);
+            us::umma_bf16_elect(d, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          }
         }
         us::umma_commit_elect(empty_bar(s));
       }
       us::umma_commit_elect(accum_bar);
     } else {
-      // ------------------------------ epilogue: accumulator row m -> dW[m][n][tap] ------------------------------
+      // ------------------------------ epilogue: accumulator row m, taps 4g .. 4g + 3 of column n -> one 16-byte reduction ------------------------------
       ug::mbar_wait(accum_bar, 0);
       ug::tc_fence_after();
       const int m = m0 + warp * 32 + lane;
-      for (int cb = 0; cb < L.BN; cb += 32) {
-        uint32_t v[32];
-        ug::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
-        if (m < L.Cd) {
-          float* o = L.dw + ((size_t)m * L.Cs_full + n0 + cb) * 16 + tap;
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int g = 0; g < L.TC; g += 4) {
+        const uint32_t gm = (grp_mask >> g) & 15u;
+        if (gm == 0) continue;
+        for (int cb = 0; cb < L.BN; cb += 16) {
+          uint32_t v[4][16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + cb + i < L.Cs) atomicAdd(o + (size_t)i * 16, __uint_as_float(v[i]));
+          for (int j = 0; j < 4; ++j) ug::tmem_ld16_nowait(trow + (uint32_t)((g + j) * L.BN + cb), v[j]);
+          ug::tmem_ld_wait();
+          if (m < L.Cd) {
+            float* o = L.dw + ((size_t)m * L.Cs_full + n0 + cb) * 16 + tap0 + g;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + cb + i < L.Cs)       // accumulators of taps that cannot touch the image were never written: they add zero
+                wg::red_add_v4(o + (size_t)i * 16, (gm & 1u) ? __uint_as_float(v[0][i]) : 0.f, (gm & 2u) ? __uint_as_float(v[1][i]) : 0.f,
+                               (gm & 4u) ? __uint_as_float(v[2][i]) : 0.f, (gm & 8u) ? __uint_as_float(v[3][i]) : 0.f);
+          }
         }
       }
       ug::tc_fence_before();
