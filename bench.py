@@ -715,7 +715,9 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
             from move2hear_active_av_separation_b200.distributed import make_reduction_group
             red = GradientAllReducer(pol.parameters(), modules=pol, overlap=True, group=make_reduction_group(int(os.environ.get("M2H_DDP_CTAS", "8"))))
         else:
-            red = GradientAllReducer(pol.parameters(), modules=pol)
+            from move2hear_active_av_separation_b200.pretrain import separator_param_groups
+            red = GradientAllReducer(pol.parameters(), modules=pol, param_groups=None if mode == "one_group" else separator_param_groups(pol),
+                                     start_groups_from_hooks=mode not in ("one_group", "two_groups"))
     B = B_TRAIN
     mono, rir, ln, tc = d_mono[:B], d_rir[:B], d_len[:B], d_tc[:B]
 
@@ -723,7 +725,7 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
         out = rend.render(mono, rir, ln, n_gt=1)                                   # dataset path: fp32 log-mag mixture + target GT magnitude
         mixed, gt_bin = out["mix_mag"], out["gt"][:, 0]
         gt_mono, _ = rend.stft_f32((mono[:, :1].float() * (1.0 / 32768)).contiguous())      # monaural GT magnitude [B,512,T,1]
-        b_, m_ = train_step(pol, opt, mixed, gt_bin, gt_mono, tc, grad_sync=red.finish if red else None)
+        b_, m_ = train_step(pol, opt, mixed, gt_bin, gt_mono, tc, grad_sync=red if red else None)
         return b_.detach(), m_.detach()          # keep no autograd graph alive between steps
 
     def timed(fn, steps):
@@ -750,7 +752,7 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
         try:
             from move2hear_active_av_separation_b200.pretrain import GraphedTrainStep
             gstep = GraphedTrainStep(pol, opt, B, dev, renderer=rend, n_sources=K_SRC, n_samples=N_SAMPLES, rir_taps=L_TAPS,
-                                     grad_sync=red.finish if red else None, two_streams=bool(int(os.environ.get("M2H_TRAIN_TWO_STREAMS", "1"))))
+                                     grad_sync=red if red else None, two_streams=bool(int(os.environ.get("M2H_TRAIN_TWO_STREAMS", "1"))))
             for _ in range(3):
                 gstep(mono, rir, ln, target_class=tc)
             (b, m), ms_total, per_step = timed(lambda: gstep(mono, rir, ln, target_class=tc), steps)

@@ -24,26 +24,42 @@ class GradientAllReducer:
     the NCCL kernels of the side stream are scheduled piecemeal and every rank waits for the slowest one."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None, overlap: bool = False,
-                 modules: torch.nn.Module = None):
+                 modules: torch.nn.Module = None, param_groups=None, start_groups_from_hooks: bool = False):
         """``modules`` (optional): a module tree containing the separator modules of ``separator_cnn``.  Their backward then
         writes every parameter gradient straight into this reducer's flat per-bucket buffers (the autograd Functions hand
         out views of the arena, which ``AccumulateGrad`` adopts as ``p.grad`` without a copy), so a bucket is all-reduced
         IN PLACE: no ``torch.cat`` pack, no un-pack copy (each cost a 134 MB read + write per step)."""
+        """``param_groups`` (optional list of parameter lists, together = ``params``): buckets never straddle two groups and
+        :meth:`start` reduces one group early - ``pretrain.train_step`` starts the binaural separator's group as soon as its
+        backward is done, under the converter's backward (the two passes are independent: detached masks).
+        ``start_groups_from_hooks``: a group is started by the gradient hook of its last parameter, i.e. in the middle of a
+        backward pass as soon as the autograd Function that owns the group has returned (decoder gradients travel while the
+        encoder's backward runs)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.overlap = overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         # buckets in reverse registration order (gradients of late layers are ready first)
         self.buckets: List[List[torch.nn.Parameter]] = []
-        cur, cur_bytes = [], 0
-        for p in reversed(self.params):
-            cur.append(p)
-            cur_bytes += p.numel() * 4
-            if cur_bytes >= bucket_bytes:
+        self._bucket_group: List[int] = []
+        if param_groups is None:
+            param_groups = [self.params]
+        else:
+            param_groups = [[p for p in g if p.requires_grad] for g in param_groups]
+            if sorted(id(p) for g in param_groups for p in g) != sorted(id(p) for p in self.params):
+                raise ValueError("param_groups must partition params")
+        for gi in reversed(range(len(param_groups))):
+            cur, cur_bytes = [], 0
+            for p in reversed(param_groups[gi]):
+                cur.append(p)
+                cur_bytes += p.numel() * 4
+                if cur_bytes >= bucket_bytes:
+                    self.buckets.append(cur)
+                    self._bucket_group.append(gi)
+                    cur, cur_bytes = [], 0
+            if cur:
                 self.buckets.append(cur)
-                cur, cur_bytes = [], 0
-        if cur:
-            self.buckets.append(cur)
+                self._bucket_group.append(gi)
         self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
         self._arena = None            # per bucket: flat fp32 buffer; _slot[id(p)] = (bucket, offset)
         self._slot = {}
@@ -63,12 +79,25 @@ class GradientAllReducer:
         self._work = [None] * len(self.buckets)
         self._stream = None
         self._hooks = []
+        self._group_of = {id(p): gi for gi, g in enumerate(param_groups) for p in g}
+        self._group_size = [len(g) for g in param_groups]
+        self._group_pending = list(self._group_size)
         if self.world > 1 and self.overlap:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        elif self.world > 1 and start_groups_from_hooks:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_group_grad))
         self._reset()
 
+    def _on_group_grad(self, p):
+        gi = self._group_of[id(p)]
+        self._group_pending[gi] -= 1
+        if self._group_pending[gi] == 0:
+            self.start(gi)
+
     def _reset(self):
+        self._group_pending = list(self._group_size)
         self._pending = [len(b) for b in self.buckets]
         self._work = [None] * len(self.buckets)
 
@@ -111,6 +140,18 @@ class GradientAllReducer:
         self._pending[i] -= 1
         if self._pending[i] == 0:
             self._launch(i)
+
+    def start(self, group_index: int):
+        """Launch the all-reduce of every bucket of one parameter group NOW (its gradients are complete on the current stream);
+        :meth:`finish` launches the rest and waits for all of them."""
+        if self.world <= 1 or self.overlap:
+            return
+        for i, bucket in enumerate(self.buckets):
+            if self._bucket_group[i] == group_index and self._work[i] is None and all(p.grad is not None for p in bucket):
+                self._launch(i)
+
+    def __call__(self):
+        self.finish()
 
     def finish(self):
         """Wait for every bucket, write the averaged gradients back.  Call between ``backward()`` and ``optimizer.step()``."""

@@ -42,6 +42,16 @@ def prepack_weights(actor_critic, batch_size: int, device) -> None:
     prepack_train_weights(ac.bin2mono_enc.passive_sep_encoder, ac.bin2mono_dec.passive_sep_decoder, batch_size, device)
 
 
+def separator_param_groups(actor_critic):
+    """``[separator encoder, separator decoder, converter encoder, converter decoder]`` parameters in registration order: the
+    ``param_groups`` argument of ``distributed.GradientAllReducer`` (with ``start_groups_from_hooks=True``) that lets a
+    group's all-reduce start as soon as its backward function has returned - the separator's under the converter's forward
+    and backward, each decoder's under its encoder's backward; only the converter encoder's 28 MB stay exposed."""
+    ac = actor_critic
+    return [list(ac.binSep_enc.parameters()), list(ac.binSep_dec.parameters()),
+            list(ac.bin2mono_enc.parameters()), list(ac.bin2mono_dec.parameters())]
+
+
 def train_step(actor_critic, optimizer, mixed_audio, gt_bin_mag, gt_mono_mag, target_class, grad_sync=None, side_stream=None,
                gt_ready=None):
     """One train-split iteration of ``PassiveTrainer.train`` (passive_trainer.py:218-245) -> ``(bin_loss, mono_loss)``.
@@ -71,9 +81,15 @@ def train_step(actor_critic, optimizer, mixed_audio, gt_bin_mag, gt_mono_mag, ta
         main.wait_event(gt_ready)
     bin_loss = l1_mask_loss(pred_binSepMasks, gt_bin_mag, mixed_audio=mixed_audio)
     optimizer.zero_grad()
-    main.wait_stream(side_stream)                       # the sum below reads the converter's loss
-    loss = bin_loss + mono_loss
-    loss.backward()                                     # converter nodes run on the side stream, separator nodes here
+    # (bin_loss + mono_loss).backward() of the reference = two backward passes over DISJOINT parameter sets (detached masks):
+    # the separator's starts as soon as its loss exists, next to the converter's forward on the side stream, and its gradients
+    # are complete - ready for the data-parallel all-reduce - while the converter's backward still runs
+    bin_loss.backward()
+    if grad_sync is not None and hasattr(grad_sync, "start"):
+        for gi in (0, 1):                               # separator groups (separator_param_groups): reduced under the converter's backward
+            grad_sync.start(gi)
+    with torch.cuda.stream(side_stream):
+        mono_loss.backward()
     main.wait_stream(side_stream)
     if grad_sync is not None:
         grad_sync()

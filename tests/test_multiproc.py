@@ -118,8 +118,40 @@ GRAD_WORKER = textwrap.dedent("""
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     arena_ok = bool(in_place and torch.allclose(toy.w.grad, sum(gathered) / world, atol=1e-6) and toy.w.grad.data_ptr() == red2._arena[0].data_ptr())
+    # parameter groups: two independent halves, the first one reduced early (start) while the second is still being computed
+    a, b = torch.nn.Linear(8, 4), torch.nn.Linear(8, 4)
+    both = torch.nn.ModuleList([a, b])
+    broadcast_module_state(both)
+    red3 = GradientAllReducer(both.parameters(), bucket_bytes=64, param_groups=[list(a.parameters()), list(b.parameters())])
+    groups_split = all(len({id(q) for q in bk} & {id(q) for q in a.parameters()}) in (0, len(bk)) for bk in red3.buckets)
+    torch.nn.functional.mse_loss(a(x), y).backward()
+    la = [q.grad.clone() for q in a.parameters()]
+    red3.start(0)
+    started = [red3._work[i] is not None for i in range(len(red3.buckets))]
+    torch.nn.functional.mse_loss(b(x), y).backward()
+    lb = [q.grad.clone() for q in b.parameters()]
+    red3()
+    groups_ok = groups_split and started == [g == 0 for g in red3._bucket_group]
+    for q, l in zip(list(a.parameters()) + list(b.parameters()), la + lb):
+        gathered = [torch.zeros_like(l) for _ in range(world)]
+        dist.all_gather(gathered, l)
+        groups_ok = groups_ok and torch.allclose(q.grad, sum(gathered) / world, atol=1e-6)
+    # the same with hook-started groups: no explicit start()
+    for q in both.parameters():
+        q.grad = None
+    red4 = GradientAllReducer(both.parameters(), bucket_bytes=64, param_groups=[list(a.parameters()), list(b.parameters())], start_groups_from_hooks=True)
+    torch.nn.functional.mse_loss(a(x), y).backward()
+    hooks_ok = [red4._work[i] is not None for i in range(len(red4.buckets))] == [g == 0 for g in red4._bucket_group]
+    torch.nn.functional.mse_loss(b(x), y).backward()
+    hooks_ok = hooks_ok and all(w is not None for w in red4._work)
+    red4()
+    for q, l in zip(list(a.parameters()) + list(b.parameters()), la + lb):
+        gathered = [torch.zeros_like(l) for _ in range(world)]
+        dist.all_gather(gathered, l)
+        hooks_ok = hooks_ok and torch.allclose(q.grad, sum(gathered) / world, atol=1e-6)
+    groups_ok = groups_ok and hooks_ok
     if rank == 0:
-        print(json.dumps({"ok": bool(ok), "same_init": same_init, "n_buckets": len(red.buckets), "arena_ok": arena_ok}))
+        print(json.dumps({"ok": bool(ok), "same_init": same_init, "n_buckets": len(red.buckets), "arena_ok": arena_ok, "groups_ok": bool(groups_ok)}))
     dist.destroy_process_group()
 """) % ROOT
 
@@ -136,3 +168,4 @@ def test_two_rank_gloo_gradient_allreduce(tmp_path, overlap):
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert d["ok"] and d["same_init"] and d["n_buckets"] > 1
     assert d["arena_ok"]            # gradients written into the flat arena are adopted by autograd and reduced in place
+    assert d["groups_ok"]           # buckets respect parameter groups; start(0) launches only the first group's

@@ -2,8 +2,8 @@
 # data-parallel pretraining step on N GPUs, both reduction modes: tools/ddp_iter.sh <N> <tag>
 N=${1:-2}; tag=${2:-ddp}
 mkdir -p gpurun_out
-for mode in after_backward overlap; do
-  M2H_DDP_MODE=$mode timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${tag}_${N}gpu_$mode.json 2> gpurun_out/bench_${tag}_${N}gpu_$mode.err
+for mode in ${3:-after_backward one_group}; do
+  M2H_DDP_MODE=$mode timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --no-procs > gpurun_out/bench_${tag}_${N}gpu_$mode.json 2> gpurun_out/bench_${tag}_${N}gpu_$mode.err
   tail -2 gpurun_out/bench_${tag}_${N}gpu_$mode.err
   python - <<PY
 import json
