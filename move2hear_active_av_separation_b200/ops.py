@@ -31,6 +31,8 @@ _LIB = torch.library.Library("m2h", "DEF")
 _LIB.define("rir_convolve(Tensor mono, Tensor rir, Tensor rir_len) -> Tensor")
 _LIB.define("stft_waves(Tensor waves, int n_gt, bool sim_dtypes, bool want_phase, bool raw_mag) -> (Tensor, Tensor, Tensor)")
 _LIB.define("render_mixture(Tensor mono, Tensor rir, Tensor rir_len, int n_gt, bool sim_dtypes, bool want_phase) -> (Tensor, Tensor, Tensor, Tensor)")
+_LIB.define("stft_waves_x0(Tensor waves) -> Tensor")
+_LIB.define("unet_forward_x0(Tensor x0, Tensor target_class, Tensor enc_packed, Tensor dec_packed) -> Tensor")
 _LIB.define("istft(Tensor mag, Tensor phase, int length) -> Tensor")
 _LIB.define("unet_forward(Tensor obs, Tensor target_class, Tensor enc_packed, Tensor dec_packed) -> Tensor")
 _LIB.define("bin2mono_forward(Tensor masks, Tensor obs, Tensor enc_packed, Tensor dec_packed) -> Tensor")
@@ -62,6 +64,11 @@ def _render_mixture(mono, rir, rir_len, n_gt, sim_dtypes, want_phase):
     return mix, phase, gt, waves
 
 
+def _stft_waves_x0(waves):
+    """int16 ``[B,K,2,N]`` (32 frames) -> bf16 ``[B,18,18,128]``: log1p |STFT| of the mixture in the separator's first-layer layout."""
+    return _renderer(waves).stft_waves_x0(waves).x0
+
+
 def _istft(mag, phase, length):
     return _renderer(mag).istft(mag, phase, length)
 
@@ -80,13 +87,18 @@ def _workspace(B, device):
     return ws
 
 
-def _separator(obs, enc_packed, dec_packed, bin2mono, cls=None, masks=None):
+def _separator(obs, enc_packed, dec_packed, bin2mono, cls=None, masks=None, x0=None):
     lib = _lib.load()
-    dev = obs.device
-    obs = obs.contiguous().float()
-    B = obs.size(0)
-    if tuple(obs.shape[1:]) != (512, 32, 2):
-        raise _lib.M2HError(f"expected a [B,512,32,2] spectrogram, got {tuple(obs.shape)}")
+    dev = (obs if x0 is None else x0).device
+    if x0 is None:
+        obs = obs.contiguous().float()
+        B = obs.size(0)
+        if tuple(obs.shape[1:]) != (512, 32, 2):
+            raise _lib.M2HError(f"expected a [B,512,32,2] spectrogram, got {tuple(obs.shape)}")
+    else:
+        B = x0.size(0)
+        if x0.dtype != torch.bfloat16 or tuple(x0.shape[1:]) != (18, 18, 128) or not x0.is_contiguous():
+            raise _lib.M2HError(f"expected a contiguous bf16 [B,18,18,128] first-layer operand, got {x0.dtype} {tuple(x0.shape)}")
     for name, t in (("enc_packed", enc_packed), ("dec_packed", dec_packed)):
         if t.device != dev or t.dtype != torch.uint8:
             raise _lib.M2HError(f"{name} must be the uint8 buffer of m2h_unet_pack_* on {dev}")
@@ -102,8 +114,12 @@ def _separator(obs, enc_packed, dec_packed, bin2mono, cls=None, masks=None):
         cls_ptr = cls.data_ptr()
     st = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
-        _lib.check(lib.m2h_unet_encoder_forward(enc_packed.data_ptr(), int(bin2mono), obs.data_ptr(), cls_ptr, mask_ptr, strides, B,
-                                                ws.buf.data_ptr(), ws.nbytes, bott.data_ptr(), st), "m2h_unet_encoder_forward")
+        if x0 is not None:
+            _lib.check(lib.m2h_unet_encoder_forward_x0(enc_packed.data_ptr(), x0.data_ptr(), cls_ptr, B, ws.buf.data_ptr(), ws.nbytes,
+                                                       bott.data_ptr(), st), "m2h_unet_encoder_forward_x0")
+        else:
+            _lib.check(lib.m2h_unet_encoder_forward(enc_packed.data_ptr(), int(bin2mono), obs.data_ptr(), cls_ptr, mask_ptr, strides, B,
+                                                    ws.buf.data_ptr(), ws.nbytes, bott.data_ptr(), st), "m2h_unet_encoder_forward")
         _lib.check(lib.m2h_unet_decoder_forward(dec_packed.data_ptr(), int(bin2mono), B, ws.buf.data_ptr(), ws.nbytes, out.data_ptr(), st),
                    "m2h_unet_decoder_forward")
     return out
@@ -111,6 +127,10 @@ def _separator(obs, enc_packed, dec_packed, bin2mono, cls=None, masks=None):
 
 def _unet_forward(obs, target_class, enc_packed, dec_packed):
     return _separator(obs, enc_packed, dec_packed, False, cls=target_class)
+
+
+def _unet_forward_x0(x0, target_class, enc_packed, dec_packed):
+    return _separator(None, enc_packed, dec_packed, False, cls=target_class, x0=x0)
 
 
 def _bin2mono_forward(masks, obs, enc_packed, dec_packed):
@@ -139,13 +159,23 @@ def _acoustic_mem(pred_mono, prev, conv1_w, conv2_w, bn_w, bn_b, bn_mean, bn_var
 
 for _name, _fn in (("rir_convolve", _rir_convolve), ("stft_waves", _stft_waves), ("render_mixture", _render_mixture), ("istft", _istft),
                    ("unet_forward", _unet_forward), ("bin2mono_forward", _bin2mono_forward), ("stft_l2_distance", _stft_l2),
-                   ("acoustic_mem", _acoustic_mem)):
+                   ("acoustic_mem", _acoustic_mem), ("stft_waves_x0", _stft_waves_x0), ("unet_forward_x0", _unet_forward_x0)):
     _LIB.impl(_name, _fn, "CUDA")
 
 
 # ---- fake (meta) implementations: shapes and dtypes only ---------------------------------------------------------------
 def _T(n):
     return 1 + (n - 1) // 512
+
+
+@torch.library.register_fake("m2h::stft_waves_x0")
+def _(waves):
+    return waves.new_empty((waves.shape[0], 18, 18, 128), dtype=torch.bfloat16)
+
+
+@torch.library.register_fake("m2h::unet_forward_x0")
+def _(x0, target_class, enc_packed, dec_packed):
+    return x0.new_empty((x0.shape[0], 2, 512, 32), dtype=torch.float32)
 
 
 @torch.library.register_fake("m2h::rir_convolve")

@@ -8,7 +8,7 @@ from oracle import render as R
 from oracle import unet as U
 from oracle.gen_golden import unet_case_inputs
 
-OPS = ["rir_convolve", "stft_waves", "render_mixture", "istft", "unet_forward", "bin2mono_forward", "stft_l2_distance", "acoustic_mem"]
+OPS = ["rir_convolve", "stft_waves", "render_mixture", "istft", "unet_forward", "bin2mono_forward", "stft_l2_distance", "acoustic_mem", "stft_waves_x0", "unet_forward_x0"]
 
 
 def test_namespace_is_registered_cuda_only():
@@ -30,6 +30,9 @@ def test_fake_kernels_give_shapes_and_dtypes():
         mask = torch.ops.m2h.unet_forward(torch.zeros(3, 512, 32, 2), torch.zeros(3, 1), torch.zeros(4, dtype=torch.uint8), torch.zeros(4, dtype=torch.uint8))
         assert mask.shape == (3, 2, 512, 32)
         assert torch.ops.m2h.istft(torch.zeros(2, 512, 32, 2), torch.zeros(2, 512, 32, 2), 16000).shape == (2, 2, 16000)
+        x0 = torch.ops.m2h.stft_waves_x0(waves)
+        assert x0.shape == (3, 18, 18, 128) and x0.dtype == torch.bfloat16
+        assert torch.ops.m2h.unet_forward_x0(x0, torch.zeros(3, 1), torch.zeros(4, dtype=torch.uint8), torch.zeros(4, dtype=torch.uint8)).shape == (3, 2, 512, 32)
 
 
 @pytest.mark.gpu
@@ -55,6 +58,11 @@ def test_operators_against_oracle():
     assert float((mask.cpu() - want_mask).norm() / want_mask.norm()) < 2e-2
     with torch.no_grad():
         assert torch.equal(mask, dec(*enc({"mixed_bin_audio_mag": obs.to(dev), "target_class": tc.to(dev)})))
+    # fused hand-over: STFT -> first-layer operand -> separator, bit-identical to the route through the fp32 observation
+    tc3 = tc.to(dev)
+    m_two_step = torch.ops.m2h.unet_forward(mix, tc3, enc._pack(dev), dec._pack(dev)).clone()
+    m_fused = torch.ops.m2h.unet_forward_x0(torch.ops.m2h.stft_waves_x0(waves), tc3, enc._pack(dev), dec._pack(dev))
+    assert torch.equal(m_two_step, m_fused)
     enc2_sd, dec2_sd = U.init_state(True, seed=4)
     enc2, dec2 = PassiveSepEncCNN(True).to(dev).eval(), PassiveSepDecCNN(True).to(dev).eval()
     enc2.load_state_dict(enc2_sd)
