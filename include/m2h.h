@@ -210,8 +210,10 @@ int m2h_unet_workspace_clear_halos(int B, void* workspace, size_t workspace_byte
 int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2mono, const float* obs,
                              const float* target_class_plus1, const float* masks, const int64_t* mask_strides,
                              int B, void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream);
-/* Same, for the binaural separator, with the first-layer operand x0 (see m2h_stft_waves_x0) instead of the fp32 observation. */
-int m2h_unet_encoder_forward_x0(const void* packed_enc, const void* x0, const float* target_class_plus1, int B,
+/* Same, for the binaural separator, with the first-layer operand x0 (see m2h_stft_waves_x0) instead of the fp32 observation.
+ * target_class: the observation's raw int64 class indices [B] (separator_cnn.py:91-100 adds 1 and broadcasts the plane: done
+ * in the first layer's epilogue here).  bottleneck_f32 may be NULL: the decoder reads the bf16 copy in the workspace. */
+int m2h_unet_encoder_forward_x0(const void* packed_enc, const void* x0, const int64_t* target_class, int B,
                                 void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream);
 /* Decoder.  mask_out: fp32 [B, C, 512, 32] (C = 2 or 1) - the memory layout behind the reference's permuted
  * [B, 512, 32, C] return value (separator_cnn.py:163-170). */

@@ -718,12 +718,12 @@ extern "C" int m2h_unet_workspace_clear_halos(int B, void* workspace, size_t wor
 // x0_ext != null: the first layer's operand (bf16 [B][18][18][128], zero border) was written by the STFT kernel
 // (m2h_stft_waves_x0): no fp32 observation, no pack_input_kernel
 static int encoder_forward_impl(const void* packed_enc, int convert_bin2mono, const float* obs, const __nv_bfloat16* x0_ext,
-                                const float* target_class_plus1, const float* masks, const int64_t* mask_strides,
+                                const float* target_class_plus1, const int64_t* target_class_i64, const float* masks, const int64_t* mask_strides,
                                 int B, void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream) {
   if (B < 0) { m2h_set_error("m2h_unet_encoder_forward: B < 0"); return M2H_ERR_ARG; }
   if (B == 0) return M2H_OK;
   if (!packed_enc || (!obs && !x0_ext) || !workspace) { m2h_set_error("m2h_unet_encoder_forward: null pointer"); return M2H_ERR_ARG; }
-  if (convert_bin2mono ? (!masks || !mask_strides) : !target_class_plus1) { m2h_set_error("m2h_unet_encoder_forward: %s", convert_bin2mono ? "bin2mono needs masks + strides" : "binaural separator needs target_class"); return M2H_ERR_ARG; }
+  if (convert_bin2mono ? (!masks || !mask_strides) : (!target_class_plus1 && !target_class_i64)) { m2h_set_error("m2h_unet_encoder_forward: %s", convert_bin2mono ? "bin2mono needs masks + strides" : "binaural separator needs target_class"); return M2H_ERR_ARG; }
   if (workspace_bytes < m2h_unet_workspace_bytes(B)) { m2h_set_error("m2h_unet_encoder_forward: workspace too small"); return M2H_ERR_WORKSPACE; }
   int rc = unet_prepare_device();
   if (rc != M2H_OK) return rc;
@@ -748,7 +748,7 @@ static int encoder_forward_impl(const void* packed_enc, int convert_bin2mono, co
     build_conv0_items(18, 0, sl, pd);
     sl.in_coff = 0;
     sl.scale = (const float*)(pk + PL.scale[0]); sl.bias = (const float*)(pk + PL.bias[0]); sl.slope = 0.2f;
-    if (!convert_bin2mono) { sl.cls = target_class_plus1; sl.cls_w = (const float*)(pk + PL.cls_w); }
+    if (!convert_bin2mono) { sl.cls = target_class_plus1; sl.cls_i64 = (const long long*)target_class_i64; sl.cls_w = (const float*)(pk + PL.cls_w); }
     sl.out = W.cat[1]; sl.out_mode = UG_OUT_NHWC_BF16; sl.out_stride = 1; sl.Hop = sl.Wop = 18; sl.out_ld = 128; sl.out_coff = 64;
     rc = launch_slab(sl, x0_ext ? x0_ext : W.x0, 128, 18, B, (const __nv_bfloat16*)(pk + PL.w[0]), st);
     if (rc != M2H_OK) return rc;
@@ -785,13 +785,13 @@ extern "C" int m2h_unet_encoder_forward(const void* packed_enc, int convert_bin2
                                         const float* target_class_plus1, const float* masks, const int64_t* mask_strides,
                                         int B, void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream) {
   if (B > 0 && !obs) { m2h_set_error("m2h_unet_encoder_forward: null pointer"); return M2H_ERR_ARG; }
-  return encoder_forward_impl(packed_enc, convert_bin2mono, obs, nullptr, target_class_plus1, masks, mask_strides, B, workspace, workspace_bytes, bottleneck_f32, stream);
+  return encoder_forward_impl(packed_enc, convert_bin2mono, obs, nullptr, target_class_plus1, nullptr, masks, mask_strides, B, workspace, workspace_bytes, bottleneck_f32, stream);
 }
 
-extern "C" int m2h_unet_encoder_forward_x0(const void* packed_enc, const void* x0, const float* target_class_plus1, int B,
+extern "C" int m2h_unet_encoder_forward_x0(const void* packed_enc, const void* x0, const int64_t* target_class, int B,
                                            void* workspace, size_t workspace_bytes, float* bottleneck_f32, void* stream) {
   if (B > 0 && (!x0 || ((uintptr_t)x0 & 127) != 0)) { m2h_set_error("m2h_unet_encoder_forward_x0: x0 must be a 128-byte aligned device pointer"); return M2H_ERR_ARG; }
-  return encoder_forward_impl(packed_enc, 0, nullptr, (const __nv_bfloat16*)x0, target_class_plus1, nullptr, nullptr, B, workspace, workspace_bytes, bottleneck_f32, stream);
+  return encoder_forward_impl(packed_enc, 0, nullptr, (const __nv_bfloat16*)x0, nullptr, target_class, nullptr, nullptr, B, workspace, workspace_bytes, bottleneck_f32, stream);
 }
 
 extern "C" int m2h_unet_decoder_forward(const void* packed_dec, int convert_bin2mono, int B, void* workspace,

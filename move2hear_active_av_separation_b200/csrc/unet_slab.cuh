@@ -69,7 +69,8 @@ struct USLayer {
   int n_phase, Cout;
   // epilogue
   const float* scale; const float* bias; float slope;
-  const float* cls; const float* cls_w;           // class-plane term (encoder layer 0)
+  const float* cls; const float* cls_w;           // class-plane term (encoder layer 0): cls[b] = target class + 1 as fp32 ...
+  const long long* cls_i64;                         // ... or the raw int64 class indices (the + 1 and the conversion happen here)
   void* out; int out_mode;                          // UG_OUT_NHWC_BF16 | UG_OUT_HEAD_NCHW_F32
   int out_stride, Hop, Wop, out_ld, out_coff;       // output pixel (y-1)*out_stride + py + 1 in a haloed [Hop][Wop] grid
   int n_valid; const __nv_bfloat16* head_w; const float* head_b;   // head weights: bf16 [32 n][64 k], zero padded (pack_head_kernel)
@@ -173,7 +174,7 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     us::fence_async_smem();
   }
   for (int i = tid; i < L.Cout; i += US_THREADS) { sb_smem[2 * i] = L.scale ? L.scale[i] : 1.f; sb_smem[2 * i + 1] = L.bias ? L.bias[i] : 0.f; }
-  if (L.cls != nullptr)
+  if (L.cls != nullptr || L.cls_i64 != nullptr)
     for (int i = tid; i < 9 * L.Cout; i += US_THREADS) cls_smem[i] = L.cls_w[i];
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ug::smem_u32(tmem_slot)), "r"((uint32_t)L.tmem_cols) : "memory");
@@ -338,8 +339,8 @@ unet_slab_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       if (L.out_mode == UG_OUT_NHWC_BF16) {
         float clsv = 0.f;
         const float* clsw = nullptr;
-        if (L.cls != nullptr && ok) {
-          clsv = L.cls[b];
+        if ((L.cls != nullptr || L.cls_i64 != nullptr) && ok) {
+          clsv = L.cls != nullptr ? L.cls[b] : (float)(L.cls_i64[b] + 1);
           const int cy = y == 1 ? 0 : (y == L.Hp - 2 ? 2 : 1), cx = x == 1 ? 0 : (x == L.Wp - 2 ? 2 : 1);
           clsw = cls_smem + (cy * 3 + cx) * L.Cout;
         }

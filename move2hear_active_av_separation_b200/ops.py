@@ -109,6 +109,9 @@ def _separator(obs, enc_packed, dec_packed, bin2mono, cls=None, masks=None, x0=N
     if bin2mono:
         masks = masks.float()
         mask_ptr, strides = masks.data_ptr(), (ctypes.c_int64 * 4)(*masks.stride())
+    elif x0 is not None:
+        cls = cls.reshape(B).to(torch.int64).contiguous()
+        cls_ptr = cls.data_ptr()
     else:
         cls = (cls.reshape(B).float() + 1).contiguous()
         cls_ptr = cls.data_ptr()

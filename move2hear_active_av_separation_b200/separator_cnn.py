@@ -78,7 +78,9 @@ class PackedMixture:
     (space-to-depth, haloed NHWC of ``log1p |STFT|``), written directly by the STFT kernel (``AudioRenderer.stft_waves_x0``).
     Passed as ``observations["mixed_bin_audio_mag"]`` to ``PassiveSepEncCNN`` (eval mode) instead of the fp32
     ``[B,512,32,2]`` tensor: the observation skips its fp32 round trip through HBM and the repacking kernel.  ``mag`` holds the
-    fp32 observation when the caller also asked for it."""
+    fp32 observation when the caller also asked for it.  On this route the encoder hands the int64 ``target_class`` to its first
+    kernel as is and returns the bottleneck features as the bf16 tensor the decoder reads (the fp32 copy of the reference's
+    return value is one ``.float()`` away): no launch sits between the STFT kernel and the first convolution."""
     __slots__ = ("x0", "mag")
 
     def __init__(self, x0: torch.Tensor, mag: Optional[torch.Tensor] = None):
@@ -551,25 +553,33 @@ class PassiveSepEncCNN(_PackedModule):
         if getattr(self, "_ws_pool", None) is None:
             self._ws_pool = _WorkspacePool()
         ws, lease = self._ws_pool.acquire(B, device)
-        bott = torch.empty((B, 512), dtype=torch.float32, device=device)
         cls_ptr = mask_ptr = strides = None
         keep = []
-        if self._convert_bin2mono:
-            masks = masks.detach()
-            if masks.dtype != torch.float32:
-                masks = masks.float()
-            keep.append(masks)
-            mask_ptr = masks.data_ptr()
-            strides = (ctypes.c_int64 * 4)(*masks.stride())
-        else:
-            cls = (observations["target_class"].detach().reshape(B).float() + 1).contiguous()
+        if packed_obs is not None:
+            # fused hand-over: raw int64 classes go to the kernel (no conversion launch between the STFT and the first layer) and
+            # the bottleneck features are returned as the workspace's bf16 copy (no fp32 conversion launch)
+            cls = observations["target_class"].detach().reshape(B)
+            if cls.dtype != torch.int64 or not cls.is_contiguous():
+                cls = cls.to(torch.int64).contiguous()
             keep.append(cls)
-            cls_ptr = cls.data_ptr()
-        with torch.cuda.device(device):
-            if packed_obs is not None:
-                rc = lib.m2h_unet_encoder_forward_x0(packed.data_ptr(), packed_obs.x0.data_ptr(), cls_ptr, B, ws.buf.data_ptr(), ws.nbytes,
-                                                     bott.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+            bott = ws.view(5, (B, 512))
+            with torch.cuda.device(device):
+                rc = lib.m2h_unet_encoder_forward_x0(packed.data_ptr(), packed_obs.x0.data_ptr(), cls.data_ptr(), B, ws.buf.data_ptr(), ws.nbytes,
+                                                     None, torch.cuda.current_stream(device).cuda_stream)
+        else:
+            bott = torch.empty((B, 512), dtype=torch.float32, device=device)
+            if self._convert_bin2mono:
+                masks = masks.detach()
+                if masks.dtype != torch.float32:
+                    masks = masks.float()
+                keep.append(masks)
+                mask_ptr = masks.data_ptr()
+                strides = (ctypes.c_int64 * 4)(*masks.stride())
             else:
+                cls = (observations["target_class"].detach().reshape(B).float() + 1).contiguous()
+                keep.append(cls)
+                cls_ptr = cls.data_ptr()
+            with torch.cuda.device(device):
                 rc = lib.m2h_unet_encoder_forward(packed.data_ptr(), int(self._convert_bin2mono), obs.data_ptr(), cls_ptr,
                                                   mask_ptr, strides, B, ws.buf.data_ptr(), ws.nbytes, bott.data_ptr(),
                                                   torch.cuda.current_stream(device).cuda_stream)

@@ -1,7 +1,7 @@
 #!/bin/bash
 tag=${1:-x0}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_bench_shapes_gpu.py tests/test_render_gpu.py tests/test_unet_gpu.py -m gpu -x -q 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_bench_shapes_gpu.py tests/test_ops.py tests/test_unet_gpu.py tests/test_graphs_gpu.py -m gpu -x -q 2>&1 | tail -4
 for v in "" 1; do
   M2H_BENCH_FP32_OBS=$v timeout 600 python bench.py --no-train --no-cpu-baseline --no-procs > gpurun_out/bench_${tag}_fp32obs$v.json 2> gpurun_out/bench_${tag}_fp32obs$v.err
   tail -2 gpurun_out/bench_${tag}_fp32obs$v.err
