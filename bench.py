@@ -762,7 +762,9 @@ def run_train_step(args, torch, dist, dev, world, rank, rend, d_mono, d_rir, d_l
             torch.cuda.synchronize(dev)
     losses.append((float(b.detach()), float(m.detach())))
     info = {"workload": "configs[2] pretraining step: render (dataset path) + binSep & bin2mono U-Nets fwd/bwd (train-mode BN) + L1 losses + fused Adam",
-            "batch_per_gpu": B, "steps": steps, "unit": "mixtures/s", "grad_allreduce": "NCCL AVG in place on the flat gradient arena the wgrad kernels write (32 MB fp32 buckets, no pack / un-pack), after backward on the compute stream" if world > 1 else "none (1 GPU)",
+            "batch_per_gpu": B, "steps": steps, "unit": "mixtures/s", "grad_allreduce": ("NCCL AVG in place on the flat gradient arena the wgrad kernels write (32 MB fp32 buckets per module group, no pack / un-pack); "
+                               "mode " + os.environ.get("M2H_DDP_MODE", "after_backward") + ": a module group's buckets start from the gradient hook of its last parameter - the separator's under the "
+                               "converter's forward and backward, each decoder's under its encoder's backward") if world > 1 else "none (1 GPU)",
             "bin_mono_loss_first_last": losses, "ms_per_step_median_this_rank": per_step[len(per_step) // 2], "ms_per_step_max_this_rank": per_step[-1],
             "mode": mode, "ms_per_step_eager_this_rank": ms_eager / steps, "graph_capture_error": graph_err,
             "graph_note": "one CUDA graph per step; the converter branch and the weight gradients are parallel branches of it (pretrain.train_step side_stream, csrc wgrad fork)"}

@@ -530,6 +530,20 @@ static int launch_layer_auto(const UGLayer& L, int bn, int B, cudaStream_t st) {
   const int Hq = L.Hq;
   G.rows_y = Hq >= 8 ? 8 : Hq; G.nb = 128 / (Hq * G.rows_y); G.tiles_per_grp = Hq / G.rows_y; G.conv = L.in_stride == 2 ? 1 : 0; G.B = B;
   const int n_mtiles = ((B + G.nb - 1) / G.nb) * G.tiles_per_grp;
+  // 256-wide N tiles (opt-in: M2H_TMA_BN256_MIN_CTAS = smallest grid that may use them; default 0 = never): the tensor core
+  // re-reads the 128-row A tile once per MMA whatever N is, so a 128 x 256 tile moves 25 % fewer shared-memory wavefronts per
+  // FLOP than two 128 x 128 tiles.  Measured at B = 1024 (enc2, dec1: 128 CTAs of 256 columns, 4 stages, one
+  // CTA per SM, against 256 CTAs of 128 columns, two per SM): U-Net forward 0.505 vs 0.494 ms - two co-resident CTAs hide each
+  // other's pipeline bubbles better than one wide CTA saves on operand reads.
+  {
+    static int min_ctas = -1;
+    if (min_ctas < 0) { const char* e = getenv("M2H_TMA_BN256_MIN_CTAS"); min_ctas = e ? atoi(e) : 0; }
+    int sms = 148;
+    if (bn == 128 && min_ctas > 0 && L.Cout % 256 == 0) {
+      const long long ctas = (long long)n_mtiles * (L.Cout / 256) * L.n_phase;
+      if (ctas >= min_ctas && ctas <= sms) bn = 256;
+    }
+  }
   alignas(64) CUtensorMap tm_a, tm_w;
   int rc;
   if (G.conv) {
@@ -552,6 +566,10 @@ static int launch_layer_auto(const UGLayer& L, int bn, int B, cudaStream_t st) {
     cuuint32_t box[2] = {64, (cuuint32_t)bn};
     rc = make_tmap_nd(&tm_w, L.w, 2, dims, strides, box, false);
     if (rc != M2H_OK) return rc;
+  }
+  if (bn == 256) {
+    dim3 grid(n_mtiles, L.Cout / 256, L.n_phase);
+    return launch_tma_cfg<256, true>(tm_a, tm_w, L, G, grid, st);
   }
   return bn == 128 ? launch_tma_bn<128>(tm_a, tm_w, L, G, n_mtiles, st) : launch_tma_bn<64>(tm_a, tm_w, L, G, n_mtiles, st);
 }

@@ -24,7 +24,7 @@ struct UTGeom {
 // SM (the 1x1 / 2x2 / 4x4 layers: 32-128 CTAs at B = 1024) keeps 6-7 stages in flight instead - the ring depth, not the
 // tensor pipe, sets the pace of a lone CTA (TMA round trip ~1 us per stage).
 template <int BN, bool DEEP = false> struct UTCfg {
-  static constexpr int kStages = DEEP ? (BN >= 128 ? 6 : 7) : (BN >= 128 ? 3 : 4);
+  static constexpr int kStages = BN >= 256 ? 4 : (DEEP ? (BN >= 128 ? 6 : 7) : (BN >= 128 ? 3 : 4));    // 256-wide tiles: one CTA per SM, 48 KB per stage
   static constexpr int kABytes = 16384, kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
