@@ -86,6 +86,7 @@ static int bn_zero_slots(const TW& W, int first, int count, cudaStream_t st) {
 static int bn_forward(const TW& W, int layer, const FMap& z, const FMap& a, int C, int Creal, double n, const float* gamma, const float* beta,
                       float* run_mean, float* run_var, long long* nbt, float eps, float momentum, float slope, cudaStream_t st) {
   double* stats = W.stats(layer);
+  if (z.P * (C / 8) >= (1LL << 31) || (C & (C - 1)) != 0) { m2h_set_error("BatchNorm: map of %lld positions x %d channels is outside the kernels' 32-bit index range", z.P, C); return M2H_ERR_ARG; }
   M2H_CUDA_CHECK(launch_pdl(bn_stats_kernel, dim3(grid_for(z.P, 4 * (256 / (C / 8)))), dim3(256), (size_t)(2 * 256 * 8 * sizeof(float)), st, z, C, stats));
   // (a fused finalize + apply kernel was measured and dropped: every thread of the wide apply grid re-derives eight channels'
   // scale / shift in fp64, which costs more than the 20 tiny finalize launches it saves: 3.33 vs 3.18 ms per step)
@@ -98,9 +99,11 @@ static int bn_forward(const TW& W, int layer, const FMap& z, const FMap& a, int 
 static int bn_backward(const TW& W, int layer, const FMap& da1, const FMap& da2, const FMap& a, const FMap& z, int C, int Creal, double n,
                        float slope, float* dgamma, float* dbeta, cudaStream_t st) {
   double* red = W.stats(layer) + 2 * 512;          // zeroed by the forward pass of the same step (bn_zero_slots)
+  static int gate_from_a = -1;                     // M2H_BN_GATE_FROM_A=1: read the stored activation for the gate (first version)
+  if (gate_from_a < 0) { const char* e = getenv("M2H_BN_GATE_FROM_A"); gate_from_a = e && atoi(e) ? 1 : 0; }
   // reductions use [C] strides inside the 512-wide slots: kernels index red[c] and red[C + c]
-  M2H_CUDA_CHECK(launch_pdl(bn_bwd_reduce_kernel, dim3(grid_for(z.P, 4 * (256 / (C / 8)))), dim3(256), (size_t)(2 * 256 * 8 * sizeof(float)), st, da1, da2, a, z, C, W.aux(layer), slope, red));
-  M2H_CUDA_CHECK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(z.P * (C / 8), 256)), dim3(256), (size_t)(0), st, da1, da2, a, z, C, Creal, W.aux(layer), slope, red, n, dgamma, dbeta));
+  M2H_CUDA_CHECK(launch_pdl(bn_bwd_reduce_kernel, dim3(grid_for(z.P, 4 * (256 / (C / 8)))), dim3(256), (size_t)(2 * 256 * 8 * sizeof(float)), st, da1, da2, a, z, C, W.aux(layer), slope, red, gate_from_a));
+  M2H_CUDA_CHECK(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(z.P * (C / 8), 256)), dim3(256), (size_t)(0), st, da1, da2, a, z, C, Creal, W.aux(layer), slope, red, n, dgamma, dbeta, gate_from_a));
   M2H_CUDA_CHECK(cudaGetLastError());
   return M2H_OK;
 }

@@ -17,10 +17,12 @@
 struct FMap {
   __nv_bfloat16* p; int ld, coff, Hp; long long P;     // P = B * Hp * Hp positions (or B rows)
 };
+// position counts stay below 2^31 (checked on the host: bn_forward / bn_backward): 32-bit unsigned divisions - the 64-bit
+// modulo of the first version was a ~150-instruction call per position in kernels that otherwise do 8 FMAs
 __device__ __forceinline__ bool fmap_interior(const FMap& m, long long pos) {
   if (m.Hp == 0) return true;
-  const int r = (int)(pos % (m.Hp * m.Hp)), y = r / m.Hp, x = r - y * m.Hp;
-  return y >= 1 && y <= m.Hp - 2 && x >= 1 && x <= m.Hp - 2;
+  const unsigned hp = (unsigned)m.Hp, r = (unsigned)pos % (hp * hp), y = r / hp, x = r - y * hp;
+  return y >= 1u && y <= hp - 2u && x >= 1u && x <= hp - 2u;
 }
 __device__ __forceinline__ void ld8(const FMap& m, long long pos, int c8, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(m.p + pos * m.ld + m.coff + c8 * 8);
@@ -98,11 +100,14 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double n, c
 __global__ void bn_apply_kernel(const FMap z, const FMap a, int C, const float* __restrict__ aux, float slope) {
   ug::pdl_wait();
   ug::pdl_launch_dependents();
-  const int chunks = C / 8;
-  const long long total = z.P * chunks;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long pos = i / chunks;
-    const int c8 = (int)(i - pos * chunks);
+  // C / 8 is a power of two and divides the grid stride: a thread keeps its eight channels.  (Their constants stay in L1: with
+  // ~4 items per thread, hoisting 16-48 loads into a prologue cost more than it saved - measured.)
+  const unsigned chunks = (unsigned)C / 8u, cshift = 31u - (unsigned)__clz((int)chunks);
+  const unsigned total = (unsigned)z.P * chunks, stride = gridDim.x * blockDim.x;
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = (int)(i0 & (chunks - 1u));
+  for (unsigned i = i0; i < total; i += stride) {
+    const long long pos = (long long)(i >> cshift);
     if (!fmap_interior(z, pos)) continue;
     float v[8];
     ld8(z, pos, c8, v);
@@ -117,8 +122,11 @@ __global__ void bn_apply_kernel(const FMap z, const FMap a, int C, const float* 
 
 // ---- BatchNorm backward -------------------------------------------------------------------------------------------------------
 // dy = (da1 + da2) * act'(a);  red[0][C] = sum dy * xhat, red[1][C] = sum dy      (xhat = (z - mean) * invstd)
+// The gate a > 0 is re-derived from z (a = act(z * scale + shift) with a slope in [0, 1): a > 0 <=> z * scale + shift > 0, the very
+// fmaf the forward pass evaluated) instead of being read back: one 2-byte read per element less in each of the two backward
+// passes - they are streaming kernels over 1.3 GB per step.
 __global__ void bn_bwd_reduce_kernel(const FMap da1, const FMap da2, const FMap a, const FMap z, int C, const float* __restrict__ aux,
-                                     float slope, double* __restrict__ red) {
+                                     float slope, double* __restrict__ red, int gate_from_a) {
   ug::pdl_wait();
   ug::pdl_launch_dependents();
   extern __shared__ float bn_sm[];
@@ -132,10 +140,11 @@ __global__ void bn_bwd_reduce_kernel(const FMap da1, const FMap da2, const FMap 
     if (da2.p) { ld8(da2, pos, c8, g2);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] += g2[k]; }
-    ld8(a, pos, c8, av);
     ld8(z, pos, c8, zv);
+    if (gate_from_a) ld8(a, pos, c8, av);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+      if (!gate_from_a) av[k] = fmaf(zv[k], aux[c8 * 8 + k], aux[C + c8 * 8 + k]);
       const float dy = av[k] > 0.f ? g[k] : g[k] * slope;
       const float xh = (zv[k] - aux[2 * C + c8 * 8 + k]) * aux[3 * C + c8 * 8 + k];
       sg[k] = fmaf(dy, xh, sg[k]);
@@ -146,28 +155,31 @@ __global__ void bn_bwd_reduce_kernel(const FMap da1, const FMap da2, const FMap 
 }
 // dz = scale * (dy - dbeta/n - xhat * dgamma/n), written over z (interior positions); block 0 also emits the fp32 parameter grads
 __global__ void bn_bwd_apply_kernel(const FMap da1, const FMap da2, const FMap a, const FMap z, int C, int Creal, const float* __restrict__ aux,
-                                    float slope, const double* __restrict__ red, double n, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                    float slope, const double* __restrict__ red, double n, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    int gate_from_a) {
   ug::pdl_wait();
   ug::pdl_launch_dependents();
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < Creal; c += blockDim.x) { dgamma[c] = (float)red[c]; dbeta[c] = (float)red[C + c]; }
-  const int chunks = C / 8;
-  const long long total = z.P * chunks;
+  const unsigned chunks = (unsigned)C / 8u, cshift = 31u - (unsigned)__clz((int)chunks);
+  const unsigned total = (unsigned)z.P * chunks, stride = gridDim.x * blockDim.x;
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = (int)(i0 & (chunks - 1u));
   const float inv_n = (float)(1.0 / n);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long pos = i / chunks;
-    const int c8 = (int)(i - pos * chunks);
+  for (unsigned i = i0; i < total; i += stride) {
+    const long long pos = (long long)(i >> cshift);
     if (!fmap_interior(z, pos)) continue;
     float g[8], g2[8], av[8], zv[8];
     ld8(da1, pos, c8, g);
     if (da2.p) { ld8(da2, pos, c8, g2);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] += g2[k]; }
-    ld8(a, pos, c8, av);
     ld8(z, pos, c8, zv);
+    if (gate_from_a) ld8(a, pos, c8, av);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = c8 * 8 + k;
+      if (!gate_from_a) av[k] = fmaf(zv[k], aux[c], aux[C + c]);
       const float dy = av[k] > 0.f ? g[k] : g[k] * slope;
       const float xh = (zv[k] - aux[2 * C + c]) * aux[3 * C + c];
       zv[k] = aux[c] * (dy - (float)red[C + c] * inv_n - xh * (float)red[c] * inv_n);
