@@ -196,15 +196,17 @@ M2H_DEV void c24_spectrum_a(int tid, int round, const M2hConv24Tables* M2H_RESTR
   M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) {
     const float2 zo = zp(bitrev<4>(15 - q3));                      // every lane takes part in the exchange
     const float2 x2 = c24_untangle(v[bitrev<4>(q3)], zo, mul_tw32<false>(wU, q3));       // w = W_F^(f0 + 768 q3)
-    if (MONO) { if (!R.special) gx[q3 * M2H_C24_THREADS] = x2; }
+    if (MONO) { if (!R.special) m2h_st2_keep(gx + q3 * M2H_C24_THREADS, x2); }
     else y[q3] = c_mul(y[q3], x2);                                   // y arrives holding 2 X[f] of the clip (c24_load_x)
   }
 }
+// (Scratch accesses carry the L2 evict_last policy, the clip / RIR loads and the int16 stores evict_first: the launch's 460 MB of
+// streaming traffic no longer pushes dirty scratch lines out - DRAM traffic 555 -> 438 MB per 1024 mixtures, ncu.)
 // The clip's spectrum row comes from the L2-resident scratch: issued BEFORE the row's own radix pass so that the ~300-cycle
 // L2 latency runs under the butterflies (ncu r2f: 12.7 % of the kernel's samples waited on these loads at the product)
 M2H_DEV void c24_load_x(int tid, int round, const float2* g, float2 (&y)[16]) {
   const float2* gx = g + (size_t)round * 16 * M2H_C24_THREADS + tid;
-  M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) y[q3] = m2h_ldg2_nc(gx + q3 * M2H_C24_THREADS);
+  M2H_UNROLL for (int q3 = 0; q3 < 16; ++q3) y[q3] = m2h_ld2_keep(gx + q3 * M2H_C24_THREADS);
 }
 template <typename PartnerY>
 M2H_DEV void c24_spectrum_b(int tid, int round, const M2hConv24Tables* M2H_RESTRICT t, const float2 (&y)[16], float2 (&u)[16], PartnerY yp) {
@@ -225,8 +227,8 @@ M2H_DEV void c24_special_a(Conv24Smem& s, int tid, int round, float2* g) {      
   float2 x2 = c24_untangle(zm, s.sp[0][(16 - q3) & 15], s.t256[8 * 16 + q3]);
   if (q3 == 0) x2 = make_float2(2.f * (zm.x + zm.y), 2.f * (zm.x - zm.y));             // f = 0 | f = M: both real
   float2* gx = g + (size_t)round * 16 * M2H_C24_THREADS + q3 * M2H_C24_THREADS + c24_special_tid(round);
-  if (MONO) *gx = x2;
-  else { const float2 x = *gx; s.sp[1][q3] = q3 == 0 ? make_float2(x.x * x2.x, x.y * x2.y) : c_mul(x, x2); }
+  if (MONO) m2h_st2_keep(gx, x2);
+  else { const float2 x = m2h_ld2_keep(gx); s.sp[1][q3] = q3 == 0 ? make_float2(x.x * x2.x, x.y * x2.y) : c_mul(x, x2); }
 }
 M2H_DEV void c24_special_b(Conv24Smem& s, int tid) {                                       // lanes 0..15 of the special warp
   const int q3 = tid & 31;
@@ -285,7 +287,7 @@ M2H_DEV void c24_copy_out(const Conv24Smem& s, int tid, int16_t* out, int N, int
   if (VEC) {
     uint32_t* o = (uint32_t*)out;
     const int sh = (c_off & 1) * 16, k0 = c_off >> 1;
-    for (int w = tid; w < (N >> 1); w += M2H_C24_THREADS) o[w] = m2h_funnel_r(stage[k0 + w], stage[k0 + w + 1], sh);
+    for (int w = tid; w < (N >> 1); w += M2H_C24_THREADS) m2h_st_u32_stream(o + w, m2h_funnel_r(stage[k0 + w], stage[k0 + w + 1], sh));
   } else {
     for (int m = tid; m < N; m += M2H_C24_THREADS) {
       const int q = m + c_off;
@@ -403,7 +405,7 @@ M2H_DEV void conv24_cta_body(const ConvParams& P, Conv24Smem& s, const M2hConv24
       float a = 0.f, b = 0.f;
       if (VEC) {
         uint32_t w = 0;
-        if (2 * j < N) w = m2h_ldg_u32((const uint32_t*)x + j);     // N even: a packed sample is one aligned 32-bit load
+        if (2 * j < N) w = m2h_ldg_u32_stream((const uint32_t*)x + j);     // N even: a packed sample is one aligned 32-bit load
         a = (float)(int16_t)(w & 0xffffu);
         b = (float)(int16_t)(w >> 16);
       } else {
@@ -422,11 +424,11 @@ M2H_DEV void conv24_cta_body(const ConvParams& P, Conv24Smem& s, const M2hConv24
       c24_transform<false>(s, gtab, g, [&](int tid, int j) {
         float2 a = make_float2(0.f, 0.f);
         if (VEC) {
-          if (2 * j < Leff) a = m2h_ldg2((const float2*)h + j);
+          if (2 * j < Leff) a = m2h_ldg2_stream((const float2*)h + j);
           if (2 * j + 1 >= Leff) a.y = 0.f;
         } else {
-          if (2 * j < Leff) a.x = m2h_ldg(h + 2 * j);
-          if (2 * j + 1 < Leff) a.y = m2h_ldg(h + 2 * j + 1);
+          if (2 * j < Leff) a.x = m2h_ldg_stream(h + 2 * j);
+          if (2 * j + 1 < Leff) a.y = m2h_ldg_stream(h + 2 * j + 1);
         }
         return a;
       });
