@@ -77,26 +77,28 @@
   M2H_DEV uint32_t m2h_ldg_u32(const uint32_t* p) { return __ldg(p); }
   // L2 eviction priorities (cache-hint policies: compile-time descriptors).  "keep": a CTA's L2-resident scratch slot, rewritten
   // for every work item; "stream": inputs read once / outputs written once.  Without them the streaming traffic of a launch
-  // pushes dirty scratch lines out to DRAM (conv24: 555 MB of DRAM traffic for 459 MB of compulsory bytes).
-  M2H_DEV unsigned long long m2h_policy_keep() { unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
-  M2H_DEV unsigned long long m2h_policy_stream() { unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+  // pushes dirty scratch lines out to DRAM (conv24: 555 MB of DRAM traffic for 459 MB of compulsory bytes).  No "memory" clobbers:
+  // the scratch is re-read only after a CTA barrier, the outputs never; a clobber would serialise the copy-out loop's
+  // shared-memory loads behind each store.
+  M2H_DEV unsigned long long m2h_policy_keep() { unsigned long long p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+  M2H_DEV unsigned long long m2h_policy_stream() { unsigned long long p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
   M2H_DEV float2 m2h_ld2_keep(const float2* p) {
     float2 v; asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(m2h_policy_keep())); return v;
   }
   M2H_DEV void m2h_st2_keep(float2* p, float2 v) {
-    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(m2h_policy_keep()) : "memory");
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" :: "l"(p), "f"(v.x), "f"(v.y), "l"(m2h_policy_keep()));
   }
   M2H_DEV float2 m2h_ldg2_stream(const float2* p) {
-    float2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(m2h_policy_stream())); return v;
+    float2 v; asm("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(m2h_policy_stream())); return v;
   }
   M2H_DEV float m2h_ldg_stream(const float* p) {
-    float v; asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(m2h_policy_stream())); return v;
+    float v; asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(m2h_policy_stream())); return v;
   }
   M2H_DEV uint32_t m2h_ldg_u32_stream(const uint32_t* p) {
-    uint32_t v; asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(m2h_policy_stream())); return v;
+    uint32_t v; asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(m2h_policy_stream())); return v;
   }
   M2H_DEV void m2h_st_u32_stream(uint32_t* p, uint32_t v) {
-    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(m2h_policy_stream()) : "memory");
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(m2h_policy_stream()));
   }
   M2H_DEV int m2h_f2i_rn(float v) { return __float2int_rn(v); }
   M2H_DEV uint32_t m2h_funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }

@@ -411,36 +411,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
 
-template <int BN>
-static int launch_bn(const UGLayer& L, cudaStream_t st) {
-  dim3 grid((L.M + UG_BM - 1) / UG_BM, L.Cout / BN, L.n_phase);
-  M2H_CUDA_CHECK(launch_pdl(unet_gemm_kernel<BN>, dim3(grid), dim3(UG_THREADS), (size_t)(ug::Cfg<BN>::kSmemBytes), st, L));
-  M2H_CUDA_CHECK(cudaGetLastError());
-  return M2H_OK;
-}
-static int launch_layer(const UGLayer& L, int bn, cudaStream_t st) {
-  if (L.Cout % bn != 0 || L.Kpad % UG_BK != 0 || (1 << L.cin_shift) != L.Cin || L.M <= 0) { m2h_set_error("unet layer: unsupported shape Cout=%d bn=%d Kpad=%d Cin=%d M=%d", L.Cout, bn, L.Kpad, L.Cin, L.M); return M2H_ERR_ARG; }
-  switch (bn) {
-    case 32: return launch_bn<32>(L, st);
-    case 64: return launch_bn<64>(L, st);
-    case 128: return launch_bn<128>(L, st);
-    default: m2h_set_error("unet layer: no kernel for BN=%d", bn); return M2H_ERR_ARG;
-  }
-}
 static const int kSlabMaxSmem = 227 * 1024;
 static int unet_prepare_device() {
   int dev;
   int rc = m2h_current_device_checked(&dev);
   if (rc != M2H_OK) return rc;
   if (!g_unet_attr_set[dev]) {
-    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<32>::kSmemBytes));
-    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<64>::kSmemBytes));
-    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ug::Cfg<128>::kSmemBytes));
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlabMaxSmem));
     // the default carve-out left room for one CTA per SM (first ncu capture: 100 KB config, 5 warps/SM): ask for the maximum
-    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_gemm_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     M2H_CUDA_CHECK(cudaFuncSetAttribute(unet_slab_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     g_unet_attr_set[dev] = true;
   }
@@ -474,7 +452,7 @@ static int make_tmap_nd(CUtensorMap* tm, const void* base, int rank, const cuuin
   if (r != CUDA_SUCCESS) { m2h_set_error("cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r); return M2H_ERR_CUDA; }
   return M2H_OK;
 }
-// TMA-fed layer launch (unet_gemm_tma.cuh) for Cin >= 64 layers with bf16 NHWC output; falls back to the gather kernel otherwise
+// TMA-fed layer launch (unet_gemm_tma.cuh): Cin >= 64 (64-channel boxes, 128B swizzle) or the 32-channel stride-2 conv (64B swizzle), bf16 NHWC output
 template <int BN, bool DEEP>
 static int launch_tma_cfg(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const UGLayer& L, const UTGeom& G, dim3 grid, cudaStream_t st) {
   static bool attr_set[M2H_MAX_DEVICES];
@@ -521,14 +499,15 @@ static int launch_tma_bn(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const
   return launch_tma_cfg<BN, false>(tm_a, tm_w, L, G, grid, st);
 }
 static int launch_layer_auto(const UGLayer& L, int bn, int B, cudaStream_t st) {
-  static int use_tma = -1;
-  if (use_tma < 0) { const char* e = getenv("M2H_UNET_TMA"); use_tma = e ? atoi(e) : 1; }
-  if (!use_tma || L.Cin < 64 || L.out_mode != UG_OUT_NHWC_BF16 || L.cls != nullptr || (bn != 64 && bn != 128) || L.Hq != L.Wq || L.Hq > 16 || L.Kvalid != L.Kpad)
-    return launch_layer(L, bn, st);
+  const bool k32 = L.Cin == 32 && L.in_stride == 2 && L.in_ld == 32;      // 32-channel stride-2 conv: 64B-swizzled boxes
+  if ((L.Cin < 64 && !k32) || L.out_mode != UG_OUT_NHWC_BF16 || L.cls != nullptr || (bn != 64 && bn != 128) || L.Hq != L.Wq || L.Hq > 16 || L.Kvalid != L.Kpad) {
+    m2h_set_error("unet layer: no kernel for Cin=%d in_stride=%d in_ld=%d Hq=%dx%d bn=%d out_mode=%d", L.Cin, L.in_stride, L.in_ld, L.Hq, L.Wq, bn, L.out_mode);
+    return M2H_ERR_ARG;
+  }
   if (L.Cout % bn != 0 || L.M <= 0) { m2h_set_error("unet layer: unsupported shape Cout=%d bn=%d", L.Cout, bn); return M2H_ERR_ARG; }
   UTGeom G;
   const int Hq = L.Hq;
-  G.rows_y = Hq >= 8 ? 8 : Hq; G.nb = 128 / (Hq * G.rows_y); G.tiles_per_grp = Hq / G.rows_y; G.conv = L.in_stride == 2 ? 1 : 0; G.B = B;
+  G.rows_y = Hq >= 8 ? 8 : Hq; G.nb = 128 / (Hq * G.rows_y); G.tiles_per_grp = Hq / G.rows_y; G.conv = L.in_stride == 2 ? 1 : 0; G.B = B; G.k32 = k32 ? 1 : 0;
   const int n_mtiles = ((B + G.nb - 1) / G.nb) * G.tiles_per_grp;
   // 256-wide N tiles (opt-in: M2H_TMA_BN256_MIN_CTAS = smallest grid that may use them; default 0 = never): the tensor core
   // re-reads the 128-row A tile once per MMA whatever N is, so a 128 x 256 tile moves 25 % fewer shared-memory wavefronts per
@@ -550,8 +529,8 @@ static int launch_layer_auto(const UGLayer& L, int bn, int B, cudaStream_t st) {
     const int hp = L.Hin + 2;
     cuuint64_t dims[5] = {(cuuint64_t)2 * L.in_ld, (cuuint64_t)hp / 2, 2, (cuuint64_t)hp / 2, (cuuint64_t)B};
     cuuint64_t strides[4] = {(cuuint64_t)2 * L.in_ld * 2, (cuuint64_t)hp * L.in_ld * 2, (cuuint64_t)2 * hp * L.in_ld * 2, (cuuint64_t)hp * hp * L.in_ld * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)Hq, 1, (cuuint32_t)G.rows_y, (cuuint32_t)G.nb};
-    rc = make_tmap_nd(&tm_a, L.in, 5, dims, strides, box, false);
+    cuuint32_t box[5] = {(cuuint32_t)(k32 ? 32 : 64), (cuuint32_t)Hq, 1, (cuuint32_t)G.rows_y, (cuuint32_t)G.nb};
+    rc = make_tmap_nd(&tm_a, L.in, 5, dims, strides, box, k32);
   } else {
     const int hp = L.Hin + 2 * L.in_pad;
     cuuint64_t dims[4] = {(cuuint64_t)L.Cin, (cuuint64_t)hp, (cuuint64_t)hp, (cuuint64_t)B};
@@ -563,9 +542,13 @@ static int launch_layer_auto(const UGLayer& L, int bn, int B, cudaStream_t st) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.Kpad, (cuuint64_t)L.n_phase * L.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)L.Kpad * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)bn};
-    rc = make_tmap_nd(&tm_w, L.w, 2, dims, strides, box, false);
+    cuuint32_t box[2] = {(cuuint32_t)(k32 ? 32 : 64), (cuuint32_t)bn};
+    rc = make_tmap_nd(&tm_w, L.w, 2, dims, strides, box, k32);
     if (rc != M2H_OK) return rc;
+  }
+  if (k32) {      // one-tile kernel, two CTAs per SM (the 256-row persistent form assumes 64-channel boxes)
+    dim3 grid(n_mtiles, L.Cout / bn, L.n_phase);
+    return bn == 128 ? launch_tma_cfg<128, false>(tm_a, tm_w, L, G, grid, st) : launch_tma_cfg<64, false>(tm_a, tm_w, L, G, grid, st);
   }
   if (bn == 256) {
     dim3 grid(n_mtiles, L.Cout / 256, L.n_phase);

@@ -18,6 +18,8 @@ struct UTGeom {
   int tiles_per_grp;       // Hq / rows_y
   int conv;                // 1: stride-2 conv (5-D parity view), 0: stride-1 taps (4-D map)
   int B;
+  int k32;                 // 1: Cin = 32 - a k-block is one tap x 32 channels, boxes of 64-byte rows in the 64B swizzle (the data
+                           // gradient of the last decoder layer; was the one call site of the cp.async gather kernel)
 };
 
 // DEEP = false: 3-4 stages, two CTAs per SM (grids of several waves).  DEEP = true: a grid that leaves at most one CTA per
@@ -49,7 +51,7 @@ unet_gemm_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int n0 = blockIdx.y * BN, phase = blockIdx.z;
   const int grp = blockIdx.x / G.tiles_per_grp, b0 = grp * G.nb, y0 = (blockIdx.x % G.tiles_per_grp) * G.rows_y;
-  const int kpt = L.Cin >> 6;                     // 64-channel chunks per tap
+  const int kpt = G.k32 ? 1 : L.Cin >> 6;         // 64-channel chunks per tap (k32: one 32-channel chunk)
   const int nkb = L.n_taps * kpt;
 
   if (tid == 0) {
@@ -77,14 +79,14 @@ unet_gemm_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         const int tap = kb / kpt, c0 = (kb - tap * kpt) * 64;
         const int dy = L.dy[phase][tap], dx = L.dx[phase][tap];
         const uint32_t st = tiles + s * C::kStageBytes;
-        us::mbar_expect_tx(full_bar(s), (uint32_t)C::kStageBytes);
+        us::mbar_expect_tx(full_bar(s), G.k32 ? (uint32_t)(C::kStageBytes / 2) : (uint32_t)C::kStageBytes);
         if (G.conv) {     // dy, dx hold kh - 1, kw - 1: haloed pixel (2y + kh, 2x + kw)
           const int kh = dy + 1, kw = dx + 1;
           us::tma_load_5d(st, &tm_a, (kw & 1) * L.in_ld + c0, (kw >> 1), (kh & 1), y0 + (kh >> 1), b0, full_bar(s));
         } else {
           us::tma_load_4d(st, &tm_a, c0, L.in_pad + dx, L.in_pad + y0 + dy, b0, full_bar(s));
         }
-        us::tma_load_2d(st + C::kABytes, &tm_w, kb * 64, phase * L.Cout + n0, full_bar(s));
+        us::tma_load_2d(st + C::kABytes, &tm_w, kb * (G.k32 ? 32 : 64), phase * L.Cout + n0, full_bar(s));
       }
     }
   } else if (warp == 4) {
@@ -95,9 +97,15 @@ unet_gemm_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       ug::mbar_wait(full_bar(s), (uint32_t)((kb / C::kStages) & 1));
       ug::tc_fence_after();
       const uint32_t st = tiles + s * C::kStageBytes;
-      const uint64_t adesc = ug::smem_desc_sw128(st), bdesc = ug::smem_desc_sw128(st + C::kABytes);
+      if (G.k32) {
+        const uint64_t adesc = ug::smem_desc_sw64(st), bdesc = ug::smem_desc_sw64(st + C::kABytes);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) us::umma_bf16_elect(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 2; ++k) us::umma_bf16_elect(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+      } else {
+        const uint64_t adesc = ug::smem_desc_sw128(st), bdesc = ug::smem_desc_sw128(st + C::kABytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) us::umma_bf16_elect(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+      }
       us::umma_commit_elect(empty_bar(s));
     }
     us::umma_commit_elect(accum_bar);
