@@ -178,12 +178,18 @@ static int launch_conv(const int16_t* mono, const int32_t* mono_index, const flo
   if (force_f32768 < 0) { const char* e = getenv("M2H_CONV_F32768"); force_f32768 = (e && atoi(e)) ? 1 : 0; }
   if (Lmax <= M2H_C24_MAX_TAPS && !force_f32768) {       // every RIR fits the F = 24576 kernel (the reference's RIRs are 1 s = 16000 taps)
     int grid24 = M2H_C24_CTAS_PER_SM * g_tables[dev].n_sms;
-    if (grid24 > n_items) grid24 = n_items;
+    // fewer items than half the CTA slots: one CTA per (item, ear) - the clip's transform is repeated, the item's critical path
+    // drops from 5 to 3 transforms (M2H_CONV_EAR_SPLIT=0 disables)
+    static int allow_split = -1;
+    if (allow_split < 0) { const char* e = getenv("M2H_CONV_EAR_SPLIT"); allow_split = (e && !atoi(e)) ? 0 : 1; }
+    const int ear_split = allow_split && 2 * n_items <= grid24 ? 1 : 0;
+    const int n_units = ear_split ? 2 * n_items : n_items;
+    if (grid24 > n_units) grid24 = n_units;
     if (workspace_bytes < (size_t)grid24 * M2H_C24_SCRATCH_F2 * sizeof(float2)) { m2h_set_error("%s: workspace %zu B < %zu B", who, workspace_bytes, (size_t)grid24 * M2H_C24_SCRATCH_F2 * sizeof(float2)); return M2H_ERR_WORKSPACE; }
     ConvParams P;
     P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.mono_index = mono_index; P.rir_index = rir_index;
     P.waves = waves; P.scratch = (float4*)workspace;
-    P.n_items = n_items; P.N = N; P.Lmax = Lmax;
+    P.n_items = n_items; P.N = N; P.Lmax = Lmax; P.ear_split = ear_split;
     const M2hConv24Tables* tab24 = g_tables[dev].conv24;
     if (conv_can_vectorise(P)) M2H_CUDA_CHECK(launch_pdl(m2h_rir_conv24_kernel<true>, grid24, M2H_C24_THREADS, sizeof(Conv24Smem), stream, P, tab24));
     else M2H_CUDA_CHECK(launch_pdl(m2h_rir_conv24_kernel<false>, grid24, M2H_C24_THREADS, sizeof(Conv24Smem), stream, P, tab24));
@@ -195,7 +201,7 @@ static int launch_conv(const int16_t* mono, const int32_t* mono_index, const flo
   ConvParams P;
   P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.mono_index = mono_index; P.rir_index = rir_index;
   P.waves = waves; P.scratch = (float4*)workspace;
-  P.n_items = n_items; P.N = N; P.Lmax = Lmax;
+  P.n_items = n_items; P.N = N; P.Lmax = Lmax; P.ear_split = 0;
   const M2hConvTables* tab = g_tables[dev].conv;
   if (conv_can_vectorise(P)) M2H_CUDA_CHECK(launch_pdl(m2h_rir_conv_kernel<true>, grid, M2H_CONV_THREADS, sizeof(ConvSmem), stream, P, tab));
   else M2H_CUDA_CHECK(launch_pdl(m2h_rir_conv_kernel<false>, grid, M2H_CONV_THREADS, sizeof(ConvSmem), stream, P, tab));

@@ -36,6 +36,9 @@ struct ConvParams {
   int n_items;             // B * K
   int N;
   int Lmax;
+  int ear_split;           // F = 24576 kernel only: a work unit is (item, ear) - two CTAs per item, each repeating the clip's
+                           // transform - for launches that cannot fill the GPU with whole items (rollout ranks, B = 1 shims):
+                           // 3 instead of 5 transforms on an item's critical path
 };
 
 struct ConvSmem {

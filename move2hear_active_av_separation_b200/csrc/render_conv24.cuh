@@ -382,7 +382,11 @@ M2H_DEV void conv24_cta_body(const ConvParams& P, Conv24Smem& s, const M2hConv24
   M2H_PDL_WAIT();
   M2H_SYNC();
   const int N = P.N;
-  for (int item = cta; item < P.n_items; item += n_ctas) {
+  const int n_units = P.ear_split ? 2 * P.n_items : P.n_items;
+  for (int unit = cta; unit < n_units; unit += n_ctas) {
+    const int item = P.ear_split ? unit >> 1 : unit;
+    const int ear_lo = P.ear_split ? (unit & 1) : 0, ear_hi = P.ear_split ? ear_lo + 1 : 2;
+    const int next_item = P.ear_split ? (unit + n_ctas) >> 1 : unit + n_ctas;       // whose clip this CTA transforms next
     const int mi = P.mono_index ? P.mono_index[item] : item;
     const int ri = P.rir_index ? P.rir_index[item] : item;
     const int L = P.rir_len[ri];
@@ -394,13 +398,13 @@ M2H_DEV void conv24_cta_body(const ConvParams& P, Conv24Smem& s, const M2hConv24
     const int c_off = c - jmin;
     if (L <= 0) {     // unreadable / empty RIR -> the reference substitutes zeros (simulator_train.py:407-415)
       M2H_FOR_THREADS(tid, M2H_C24_THREADS) {
-        int16_t* out = P.waves + (size_t)item * 2 * N;
-        for (int i = tid; i < 2 * N; i += M2H_C24_THREADS) out[i] = 0;
+        int16_t* out = P.waves + ((size_t)item * 2 + ear_lo) * N;
+        for (int i = tid; i < (ear_hi - ear_lo) * N; i += M2H_C24_THREADS) out[i] = 0;
       }
       continue;
     }
     const int16_t* x = P.mono + (size_t)mi * N;
-    M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_prefetch_row(tid, P.rir + (size_t)ri * 2 * P.Lmax + jmin, Leff * 4);      // ear 0, loaded one transform from now
+    M2H_FOR_THREADS(tid, M2H_C24_THREADS) c24_prefetch_row(tid, P.rir + ((size_t)ri * 2 + ear_lo) * P.Lmax + jmin, Leff * 4);      // first ear, loaded one transform from now
     c24_transform<true>(s, gtab, g, [&](int tid, int j) {
       float a = 0.f, b = 0.f;
       if (VEC) {
@@ -414,12 +418,12 @@ M2H_DEV void conv24_cta_body(const ConvParams& P, Conv24Smem& s, const M2hConv24
       }
       return make_float2(a, b);
     });
-    for (int ear = 0; ear < 2; ++ear) {
+    for (int ear = ear_lo; ear < ear_hi; ++ear) {
       const float* h = P.rir + ((size_t)ri * 2 + ear) * P.Lmax + jmin;
       M2H_FOR_THREADS(tid, M2H_C24_THREADS) {          // rows the next transform will load: the other ear, or the next item's clip
-        if (ear == 0) c24_prefetch_row(tid, h + P.Lmax, Leff * 4);
-        else if (item + n_ctas < P.n_items)
-          c24_prefetch_row(tid, P.mono + (size_t)(P.mono_index ? P.mono_index[item + n_ctas] : item + n_ctas) * N, N * 2);
+        if (ear + 1 < ear_hi) c24_prefetch_row(tid, h + P.Lmax, Leff * 4);
+        else if (unit + n_ctas < n_units)
+          c24_prefetch_row(tid, P.mono + (size_t)(P.mono_index ? P.mono_index[next_item] : next_item) * N, N * 2);
       }
       c24_transform<false>(s, gtab, g, [&](int tid, int j) {
         float2 a = make_float2(0.f, 0.f);

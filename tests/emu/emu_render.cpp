@@ -60,7 +60,7 @@ extern "C" int emu_rir_convolve(const int16_t* mono, const float* rir, const int
   ConvSmem* s = new ConvSmem;
   ConvParams P;
   P.mono = mono; P.rir = rir; P.rir_len = rir_len; P.waves = waves; P.scratch = scratch.data();
-  P.n_items = B * K; P.N = N; P.Lmax = Lmax; P.mono_index = nullptr; P.rir_index = nullptr;
+  P.n_items = B * K; P.N = N; P.Lmax = Lmax; P.mono_index = nullptr; P.rir_index = nullptr; P.ear_split = 0;
   const bool vec = conv_can_vectorise(P);      // same dispatch rules as m2h_rir_convolve
   if (Lmax <= M2H_C24_MAX_TAPS) {              // F = 24576 kernel (render_conv24.cuh)
     Conv24Smem* s24 = new Conv24Smem;
